@@ -1,0 +1,124 @@
+"""ctypes binding of libbrainseg_b200.so (the C ABI in include/brainseg_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or the device is not sm_100 the calls raise.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbrainseg_b200.so")
+
+BSG_CONV_K3, BSG_CONVT_K2S2, BSG_CONV_K1 = 0, 1, 2
+BSG_ACT_NONE, BSG_ACT_LRELU = 0, 1
+
+
+class BsgError(RuntimeError):
+    pass
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int), ("stride", C.c_int),
+        ("N", C.c_int), ("D", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("cin", C.c_int), ("in_ptr", C.c_void_p), ("in_ctot", C.c_int),
+        ("cout", C.c_int), ("out_ptr", C.c_void_p), ("out_ctot", C.c_int), ("out_coff", C.c_int),
+        ("weights", C.c_void_p), ("bias", C.c_void_p),
+        ("act", C.c_int), ("slope", C.c_float), ("stats", C.c_void_p),
+        ("use_khshift", C.c_int), ("max_ctas", C.c_int),
+    ]
+
+
+class ConvInfo(C.Structure):
+    _fields_ = [
+        ("bw", C.c_int), ("bh", C.c_int), ("bd", C.c_int), ("bn", C.c_int),
+        ("ntile", C.c_int), ("n_ntiles", C.c_int), ("cc", C.c_int), ("nstages", C.c_int),
+        ("khshift", C.c_int), ("grid", C.c_int), ("smem_bytes", C.c_size_t), ("flops", C.c_double),
+    ]
+
+
+_lib = None
+
+
+def _declare(lib):
+    vp, i, f = C.c_void_p, C.c_int, C.c_float
+    lib.bsg_version.restype = i
+    lib.bsg_last_error.restype = C.c_size_t
+    lib.bsg_last_error.argtypes = [C.c_char_p, C.c_size_t]
+    lib.bsg_check_device.restype = i
+    lib.bsg_sm_count.restype = i
+    lib.bsg_conv_plan_create.restype = i
+    lib.bsg_conv_plan_create.argtypes = [C.POINTER(ConvDesc), C.POINTER(vp)]
+    lib.bsg_conv_plan_run.restype = i
+    lib.bsg_conv_plan_run.argtypes = [vp, vp]
+    lib.bsg_conv_plan_destroy.restype = None
+    lib.bsg_conv_plan_destroy.argtypes = [vp]
+    lib.bsg_conv_plan_info.restype = i
+    lib.bsg_conv_plan_info.argtypes = [vp, C.POINTER(ConvInfo)]
+    for name, sig in _EXTRA_SIGS.items():
+        fn = getattr(lib, name)
+        fn.restype = i
+        fn.argtypes = sig
+
+
+# name -> argtypes for the flat (non-plan) entry points; filled in as kernels are added (see postproc.cu, tail.cu)
+_EXTRA_SIGS = {}
+
+
+def lib():
+    """Returns the loaded library; raises if it was never built (no CPU fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise BsgError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`; "
+                "brainseg_b200 has no CPU fallback")
+        l = C.CDLL(LIB_PATH)
+        _declare(l)
+        _lib = l
+    return _lib
+
+
+def last_error():
+    buf = C.create_string_buffer(512)
+    lib().bsg_last_error(buf, 512)
+    return buf.value.decode()
+
+
+def check(rc):
+    if rc != 0:
+        raise BsgError(f"brainseg_b200 error {rc}: {last_error()}")
+
+
+def stream_ptr(stream=None):
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)
+
+
+class ConvPlan:
+    """Owns one bsg_conv_plan (tensor maps + launch geometry bound to fixed device buffers)."""
+
+    def __init__(self, **kw):
+        d = ConvDesc()
+        d.use_khshift = -1
+        for k, v in kw.items():
+            setattr(d, k, v)
+        self._h = C.c_void_p()
+        check(lib().bsg_conv_plan_create(C.byref(d), C.byref(self._h)))
+        self.desc = d
+
+    def run(self, stream=None):
+        check(lib().bsg_conv_plan_run(self._h, stream_ptr(stream)))
+
+    def info(self):
+        inf = ConvInfo()
+        check(lib().bsg_conv_plan_info(self._h, C.byref(inf)))
+        return inf
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().bsg_conv_plan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass

@@ -1,0 +1,270 @@
+// Host planner for the tcgen05 conv kernel: picks the tile box / N tile / K chunk / pipeline depth for a layer,
+// encodes the TMA tensor maps once, and launches.  Exposed through the C ABI as bsg_conv_plan_*.
+#include <cudaTypedefs.h>
+#include <string.h>
+#include <new>
+#include "bsg_common.cuh"
+#include "conv_tc.cuh"
+
+namespace bsg {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+namespace {
+
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    return fn;
+}
+
+int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+               const uint32_t* box, int cc) {
+    auto fn = get_encode_fn();
+    if (fn == nullptr) return set_error(BSG_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+    uint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUtensorMapSwizzle sw = (cc == 64)   ? CU_TENSOR_MAP_SWIZZLE_128B
+                            : (cc == 32) ? CU_TENSOR_MAP_SWIZZLE_64B
+                                         : CU_TENSOR_MAP_SWIZZLE_32B;
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
+                    reinterpret_cast<const cuuint64_t*>(dims), reinterpret_cast<const cuuint64_t*>(strides_bytes),
+                    reinterpret_cast<const cuuint32_t*>(box), reinterpret_cast<const cuuint32_t*>(estr),
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return set_error(BSG_ECUDA,
+                         "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu,%llu,%llu box %u,%u,%u cc %d",
+                         static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                         (unsigned long long)dims[2], box[0], box[1], box[2], cc);
+    return BSG_OK;
+}
+
+uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+}  // namespace bsg
+
+struct bsg_conv_plan {
+    bsg::ConvArgs args;
+    int grid;
+    size_t smem_bytes;
+    double flops;
+};
+
+using namespace bsg;
+
+extern "C" {
+
+int bsg_version(void) { return 100; }
+
+size_t bsg_last_error(char* buf, size_t cap) {
+    size_t n = strlen(g_err);
+    if (buf != nullptr && cap > 0) {
+        size_t m = n < cap - 1 ? n : cap - 1;
+        memcpy(buf, g_err, m);
+        buf[m] = 0;
+    }
+    return n;
+}
+
+int bsg_check_device(void) {
+    int dev = 0, major = 0;
+    BSG_CUDA_OK(cudaGetDevice(&dev));
+    BSG_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) return set_error(BSG_EARCH, "device compute capability %d.x is not sm_100", major);
+    return BSG_OK;
+}
+
+int bsg_sm_count(void) { return sm_count_cached(); }
+
+int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
+    BSG_REQUIRE(d != nullptr && out_plan != nullptr, "null argument");
+    BSG_REQUIRE(d->kind == BSG_CONV_K3 || d->kind == BSG_CONVT_K2S2 || d->kind == BSG_CONV_K1, "bad kind %d", d->kind);
+    BSG_REQUIRE(d->cin > 0 && d->cin % 16 == 0, "cin %d must be a positive multiple of 16", d->cin);
+    BSG_REQUIRE(d->in_ctot % 8 == 0 && d->out_ctot % 8 == 0 && d->out_coff % 8 == 0,
+                "channel strides/offsets must be multiples of 8 (16-byte alignment)");
+    BSG_REQUIRE(d->N > 0 && d->D > 0 && d->H > 0 && d->W > 0 && d->cout > 0, "empty tensor");
+    BSG_REQUIRE((reinterpret_cast<uintptr_t>(d->in) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(d->weights) & 15) == 0,
+                "pointers must be 16-byte aligned");
+    const int stride = (d->kind == BSG_CONV_K3) ? d->stride : 1;
+    BSG_REQUIRE(stride == 1 || stride == 2, "stride %d", stride);
+    if (stride == 2) BSG_REQUIRE(d->D % 2 == 0 && d->H % 2 == 0 && d->W % 2 == 0, "stride 2 needs even extents");
+
+    bsg_conv_plan* p = new (std::nothrow) bsg_conv_plan();
+    if (p == nullptr) return set_error(BSG_ENOMEM, "host allocation failed");
+    ConvArgs& a = p->args;
+    memset(&a, 0, sizeof(a));
+
+    // tile coordinate space = output voxels (K3/K1) or input voxels (transposed conv)
+    a.Wo = d->W / stride;
+    a.Ho = d->H / stride;
+    a.Do = d->D / stride;
+    a.No = d->N;
+    a.stride = stride;
+    a.ntaps = (d->kind == BSG_CONV_K3) ? 27 : 1;
+    a.cc = (d->cin % 64 == 0) ? 64 : (d->cin % 32 == 0 ? 32 : 16);
+    a.nchunks = d->cin / a.cc;
+
+    // tile box: 128 voxels, w fastest
+    auto pow2_le = [](int x) {
+        int r = 1;
+        while (r * 2 <= x) r *= 2;
+        return r;
+    };
+    a.bw = a.Wo >= 8 ? 8 : pow2_le(a.Wo);
+    int rem = 128 / a.bw;
+    a.bh = a.Ho >= rem ? rem : pow2_le(a.Ho);
+    rem /= a.bh;
+    a.bd = a.Do >= rem ? rem : pow2_le(a.Do);
+    rem /= a.bd;
+    a.bn = rem;
+    a.tw = ceil_div(a.Wo, a.bw);
+    a.th = ceil_div(a.Ho, a.bh);
+    a.td = ceil_div(a.Do, a.bd);
+    a.tn = ceil_div(a.No, a.bn);
+
+    // N tiling
+    a.cout = d->cout;
+    a.cout_pad = static_cast<int>(round_up(d->cout, 32));
+    int split = 1;
+    while (a.cout_pad / split > 256 || a.cout_pad % split != 0 || (a.cout_pad / split) % 32 != 0) {
+        ++split;
+        if (split > 64) {
+            delete p;
+            return set_error(BSG_EINVAL, "cannot tile cout %d", d->cout);
+        }
+    }
+    a.ntile = a.cout_pad / split;
+    a.out_mul = (d->kind == BSG_CONVT_K2S2) ? 2 : 1;
+    a.n_ntiles = split * (a.out_mul == 2 ? 8 : 1);
+    a.tmem_cols = 32;
+    while (a.tmem_cols < static_cast<uint32_t>(2 * a.ntile)) a.tmem_cols *= 2;
+
+    // kh halo reuse: needs the canonical 8 x 16 x 1 x 1 box, stride 1, 27 taps and >= 3 pipeline stages
+    const uint32_t budget = 227 * 1024 - 2048;
+    auto stage_bytes = [&](int khs, uint32_t* ab, uint32_t* bb) {
+        const uint32_t rows = khs ? static_cast<uint32_t>((a.bh + 2) * 8) : 128u;
+        *ab = round_up(rows * a.cc * 2, 1024);
+        *bb = round_up(static_cast<uint32_t>(a.ntile) * a.cc * 2 * (khs ? 3 : 1), 1024);
+        return *ab + *bb;
+    };
+    int khs = 0;
+    if (a.ntaps == 27 && stride == 1 && a.bw == 8 && a.bd == 1 && a.bn == 1 && d->use_khshift != 0) {
+        uint32_t ab, bb;
+        const uint32_t sb = stage_bytes(1, &ab, &bb);
+        if (budget / sb >= 3 || d->use_khshift == 1) khs = 1;
+        if (budget / sb < 2) khs = 0;
+    }
+    a.khshift = khs;
+    const uint32_t sb = stage_bytes(khs, &a.a_stage_bytes, &a.b_stage_bytes);
+    a.nstages = static_cast<int>(budget / sb);
+    if (a.nstages > 12) a.nstages = 12;
+    if (a.nstages < 2) {
+        delete p;
+        return set_error(BSG_EINVAL, "layer does not fit shared memory (stage %u bytes)", sb);
+    }
+
+    // tensor maps
+    const uint64_t ct = static_cast<uint64_t>(d->in_ctot);
+    const __nv_bfloat16* in = static_cast<const __nv_bfloat16*>(d->in);
+    int rc = BSG_OK;
+    if (stride == 1) {
+        uint64_t dims[5] = {static_cast<uint64_t>(d->cin), static_cast<uint64_t>(d->W), static_cast<uint64_t>(d->H),
+                            static_cast<uint64_t>(d->D), static_cast<uint64_t>(d->N)};
+        uint64_t str[4] = {ct * 2, ct * 2 * d->W, ct * 2 * d->W * d->H, ct * 2 * d->W * d->H * d->D};
+        uint32_t box[5] = {static_cast<uint32_t>(a.cc), static_cast<uint32_t>(a.bw),
+                           static_cast<uint32_t>(a.bh + (khs ? 2 : 0)), static_cast<uint32_t>(a.bd),
+                           static_cast<uint32_t>(a.bn)};
+        rc = encode_map(&a.mapA[0], in, 5, dims, str, box, a.cc);
+    } else {
+        for (int par = 0; par < 8 && rc == BSG_OK; ++par) {
+            const int pw = par & 1, ph = (par >> 1) & 1, pd = (par >> 2) & 1;
+            const __nv_bfloat16* base =
+                in + (static_cast<uint64_t>(pw) + static_cast<uint64_t>(ph) * d->W +
+                      static_cast<uint64_t>(pd) * d->W * d->H) * ct;
+            uint64_t dims[5] = {static_cast<uint64_t>(d->cin), static_cast<uint64_t>(d->W / 2),
+                                static_cast<uint64_t>(d->H / 2), static_cast<uint64_t>(d->D / 2),
+                                static_cast<uint64_t>(d->N)};
+            uint64_t str[4] = {ct * 4, ct * 4 * d->W, ct * 4 * d->W * d->H, ct * 2 * d->W * d->H * d->D};
+            uint32_t box[5] = {static_cast<uint32_t>(a.cc), static_cast<uint32_t>(a.bw), static_cast<uint32_t>(a.bh),
+                               static_cast<uint32_t>(a.bd), static_cast<uint32_t>(a.bn)};
+            rc = encode_map(&a.mapA[par], base, 5, dims, str, box, a.cc);
+        }
+    }
+    if (rc == BSG_OK) {
+        const uint64_t rows = static_cast<uint64_t>(a.cout_pad) * (a.out_mul == 2 ? 8 : 1);
+        uint64_t dims[3] = {static_cast<uint64_t>(d->cin), rows, static_cast<uint64_t>(a.ntaps)};
+        uint64_t str[2] = {static_cast<uint64_t>(d->cin) * 2, static_cast<uint64_t>(d->cin) * 2 * rows};
+        uint32_t box[3] = {static_cast<uint32_t>(a.cc), static_cast<uint32_t>(a.ntile), khs ? 3u : 1u};
+        rc = encode_map(&a.mapW, d->weights, 3, dims, str, box, a.cc);
+    }
+    if (rc != BSG_OK) {
+        delete p;
+        return rc;
+    }
+
+    // epilogue
+    const int Wout = a.Wo * a.out_mul, Hout = a.Ho * a.out_mul, Dout = a.Do * a.out_mul;
+    a.out = static_cast<__nv_bfloat16*>(d->out);
+    a.os_w = d->out_ctot;
+    a.os_h = static_cast<long long>(d->out_ctot) * Wout;
+    a.os_d = a.os_h * Hout;
+    a.os_n = a.os_d * Dout;
+    a.out_c_off = d->out_coff;
+    a.bias = d->bias;
+    a.slope = d->slope;
+    a.act = d->act;
+    a.stats = d->stats;
+
+    const int total_tiles = a.tn * a.td * a.th * a.tw * a.n_ntiles;
+    int max_ctas = d->max_ctas > 0 ? d->max_ctas : sm_count_cached();
+    p->grid = total_tiles < max_ctas ? total_tiles : max_ctas;
+    p->smem_bytes = conv_tc_smem_bytes(a);
+    p->flops = 2.0 * a.ntaps * (a.out_mul == 2 ? 8 : 1) * static_cast<double>(d->cin) * d->cout *
+               (static_cast<double>(a.Wo) * a.Ho * a.Do * a.No);
+    *out_plan = p;
+    return BSG_OK;
+}
+
+int bsg_conv_plan_run(const bsg_conv_plan* plan, void* stream) {
+    BSG_REQUIRE(plan != nullptr, "null plan");
+    BSG_CUDA_OK(launch_conv_tc(plan->args, plan->grid, plan->smem_bytes, static_cast<cudaStream_t>(stream)));
+    return BSG_OK;
+}
+
+void bsg_conv_plan_destroy(bsg_conv_plan* plan) { delete plan; }
+
+int bsg_conv_plan_info(const bsg_conv_plan* plan, bsg_conv_info* info) {
+    BSG_REQUIRE(plan != nullptr && info != nullptr, "null argument");
+    const ConvArgs& a = plan->args;
+    info->bw = a.bw;
+    info->bh = a.bh;
+    info->bd = a.bd;
+    info->bn = a.bn;
+    info->ntile = a.ntile;
+    info->n_ntiles = a.n_ntiles;
+    info->cc = a.cc;
+    info->nstages = a.nstages;
+    info->khshift = a.khshift;
+    info->grid = plan->grid;
+    info->smem_bytes = plan->smem_bytes;
+    info->flops = plan->flops;
+    return BSG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,302 @@
+// tcgen05 / TMEM / TMA implicit-GEMM kernel for the 3-D conv stacks of Generic_UNet
+// (reference: model_architecture/generic_UNet.py:56,69 Conv3d k3; :285-288 stride-2 conv pooling; :363-364
+// ConvTranspose3d k2 s2).  Persistent, warp-specialised:
+//   warp 0      TMA producer   (activation halo boxes + weight slabs -> swizzled smem ring)
+//   warp 1      MMA issuer     (one elected lane, tcgen05.mma kind::f16, fp32 accumulators in TMEM, 2 buffers)
+//   warps 2..5  epilogue       (tcgen05.ld -> bias / LeakyReLU / norm statistics -> bf16 channels-last stores)
+#include "bsg_ptx.cuh"
+#include "conv_tc.cuh"
+
+namespace bsg {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 12;
+
+struct TileCoord {
+    int nt;              // N tile
+    int w0, h0, d0, n0;  // tile origin in the tile coordinate space
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvArgs& a, int tile) {
+    TileCoord t;
+    t.nt = tile % a.n_ntiles;
+    int s = tile / a.n_ntiles;
+    int iw = s % a.tw;
+    s /= a.tw;
+    int ih = s % a.th;
+    s /= a.th;
+    int id = s % a.td;
+    s /= a.td;
+    t.w0 = iw * a.bw;
+    t.h0 = ih * a.bh;
+    t.d0 = id * a.bd;
+    t.n0 = s * a.bn;
+    return t;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-B aligned carve-up (swizzle-128B atoms need it)
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t stage_bytes = a.a_stage_bytes + a.b_stage_bytes;
+    uint8_t* bar_area = smem + static_cast<size_t>(a.nstages) * stage_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_area);
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tfull_bar = empty_bar + kMaxStages;  // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&a.mapW);
+        tma_prefetch_desc(&a.mapA[0]);
+        for (int s = 0; s < a.nstages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, a.tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_tiles = a.tn * a.td * a.th * a.tw * a.n_ntiles;
+    const int ntg = a.khshift ? 9 : a.ntaps;  // pipeline steps per chunk: (kd,kw) pairs or single taps
+    const int ksteps = ntg * a.nchunks;
+    const int nkh = a.khshift ? 3 : 1;
+    const uint32_t row_bytes = static_cast<uint32_t>(a.cc) * 2u;
+    const uint32_t sbo = 8u * row_bytes;
+
+    if (warp == 0) {
+        // =========================================================== TMA producer
+        if (elect_one()) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const TileCoord t = decode_tile(a, tile);
+                const int nrow0 = t.nt * a.ntile;
+                for (int tg = 0; tg < ntg; ++tg) {
+                    int kd, kw, kh, tap;
+                    if (a.ntaps == 1) {
+                        kd = kw = kh = 1;
+                        tap = 0;
+                    } else if (a.khshift) {
+                        kd = tg / 3;
+                        kw = tg % 3;
+                        kh = 0;
+                        tap = tg * 3;
+                    } else {
+                        kd = tg / 9;
+                        kw = (tg / 3) % 3;
+                        kh = tg % 3;
+                        tap = tg;
+                    }
+                    int cw, ch, cd, mi = 0;
+                    if (a.stride == 1) {
+                        cw = t.w0 + kw - 1;
+                        ch = t.h0 + kh - 1;
+                        cd = t.d0 + kd - 1;
+                    } else {
+                        // input index 2*o + k - 1: k=0 -> odd parity, o-1; k=1 -> even parity, o; k=2 -> odd parity, o
+                        const int pw = (kw + 1) & 1, ph = (kh + 1) & 1, pd = (kd + 1) & 1;
+                        mi = pw | (ph << 1) | (pd << 2);
+                        cw = t.w0 - (kw == 0);
+                        ch = t.h0 - (kh == 0);
+                        cd = t.d0 - (kd == 0);
+                    }
+                    for (int c = 0; c < a.nchunks; ++c, ++it) {
+                        const int s = it % a.nstages;
+                        const uint32_t ph_bit = (it / a.nstages) & 1u;
+                        mbar_wait(&empty_bar[s], ph_bit ^ 1u);
+                        uint8_t* sa = smem + static_cast<size_t>(s) * stage_bytes;
+                        uint8_t* sb = sa + a.a_stage_bytes;
+                        mbar_expect_tx(&full_bar[s], a.a_stage_bytes + a.b_stage_bytes);
+                        tma_load_5d(sa, &a.mapA[mi], &full_bar[s], c * a.cc, cw, ch, cd, t.n0);
+                        tma_load_3d(sb, &a.mapW, &full_bar[s], c * a.cc, nrow0, tap);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================================================== MMA issuer
+        const uint32_t idesc = make_idesc_bf16(128, static_cast<uint32_t>(a.ntile));
+        const uint32_t layout = (a.cc == 64) ? kLayoutSW128 : (a.cc == 32 ? kLayoutSW64 : kLayoutSW32);
+        const uint32_t b_tap_bytes = static_cast<uint32_t>(a.ntile) * row_bytes;
+        const int k16s = a.cc / 16;
+        uint32_t it = 0;
+        uint32_t tcount = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+            const uint32_t acc = tcount & 1u;
+            const uint32_t acc_phase = (tcount >> 1) & 1u;
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * static_cast<uint32_t>(a.ntile);
+            for (int ks = 0; ks < ksteps; ++ks, ++it) {
+                const int s = it % a.nstages;
+                const uint32_t ph_bit = (it / a.nstages) & 1u;
+                mbar_wait(&full_bar[s], ph_bit);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t sa = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
+                    const uint32_t sb = sa + a.a_stage_bytes;
+                    for (int kh = 0; kh < nkh; ++kh) {
+                        for (int k = 0; k < k16s; ++k) {
+                            const uint64_t ad = make_smem_desc(sa + kh * sbo + k * 32, sbo, layout);
+                            const uint64_t bd = make_smem_desc(sb + kh * b_tap_bytes + k * 32, sbo, layout);
+                            umma_bf16(d_tmem, ad, bd, idesc, (ks | kh | k) != 0 ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+                    if (ks == ksteps - 1) umma_commit(&tfull_bar[acc]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // =========================================================== epilogue (4 warps, one TMEM lane quadrant each)
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        int r = row;
+        const int iw = r % a.bw;
+        r /= a.bw;
+        const int ih = r % a.bh;
+        r /= a.bh;
+        const int id = r % a.bd;
+        r /= a.bd;
+        const int in = r;
+        uint32_t tcount = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+            const TileCoord t = decode_tile(a, tile);
+            const uint32_t acc = tcount & 1u;
+            const uint32_t acc_phase = (tcount >> 1) & 1u;
+            const int w = t.w0 + iw, h = t.h0 + ih, d = t.d0 + id, n = t.n0 + in;
+            const bool valid = (w < a.Wo) && (h < a.Ho) && (d < a.Do) && (n < a.No);
+            int q0 = t.nt * a.ntile;  // first GEMM column of this tile
+            int pw = 0, phh = 0, pd = 0;
+            if (a.out_mul == 2) {
+                const int par = q0 / a.cout_pad;
+                q0 -= par * a.cout_pad;
+                pw = par & 1;
+                phh = (par >> 1) & 1;
+                pd = (par >> 2) & 1;
+            }
+            __nv_bfloat16* orow = a.out + n * a.os_n + static_cast<long long>(d * a.out_mul + pd) * a.os_d +
+                                  static_cast<long long>(h * a.out_mul + phh) * a.os_h +
+                                  static_cast<long long>(w * a.out_mul + pw) * a.os_w + a.out_c_off;
+
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + acc * static_cast<uint32_t>(a.ntile) + (static_cast<uint32_t>(q * 32) << 16);
+            for (int cb = 0; cb < a.ntile; cb += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_addr + cb, v);
+                tmem_ld_wait();
+                const int co = q0 + cb;
+                float f[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float x = __uint_as_float(v[i]);
+                    if (a.bias != nullptr) x += __ldg(&a.bias[co + i]);
+                    f[i] = x;
+                }
+                if (a.stats != nullptr) {
+                    // per-channel sum / sum of squares over this warp's 32 voxels: transpose-reduce (31 shuffles each)
+                    float s1[32], s2[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float x = valid ? f[i] : 0.f;
+                        s1[i] = x;
+                        s2[i] = x * x;
+                    }
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        const bool up = (lane & off) != 0;
+#pragma unroll
+                        for (int i = 0; i < off; ++i) {
+                            const float send1 = up ? s1[i] : s1[i + off];
+                            const float keep1 = up ? s1[i + off] : s1[i];
+                            s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, off);
+                            const float send2 = up ? s2[i] : s2[i + off];
+                            const float keep2 = up ? s2[i + off] : s2[i];
+                            s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+                        }
+                    }
+                    // lane l now owns channel co + l; rows of one warp always share the batch index n
+                    const int nn = __shfl_sync(0xffffffffu, n, 0);
+                    if (co + lane < a.cout && nn < a.No) {
+                        float* sp = a.stats + (static_cast<long long>(nn) * a.cout + co + lane) * 2;
+                        atomicAdd(sp, s1[0]);
+                        atomicAdd(sp + 1, s2[0]);
+                    }
+                }
+                if (a.act == 1) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = f[i] > 0.f ? f[i] : f[i] * a.slope;
+                }
+                if (valid) {
+                    if (co + 32 <= a.cout) {
+                        uint4* dst = reinterpret_cast<uint4*>(orow + co);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            __nv_bfloat162 p0 = __floats2bfloat162_rn(f[8 * i + 0], f[8 * i + 1]);
+                            __nv_bfloat162 p1 = __floats2bfloat162_rn(f[8 * i + 2], f[8 * i + 3]);
+                            __nv_bfloat162 p2 = __floats2bfloat162_rn(f[8 * i + 4], f[8 * i + 5]);
+                            __nv_bfloat162 p3 = __floats2bfloat162_rn(f[8 * i + 6], f[8 * i + 7]);
+                            uint4 u;
+                            u.x = *reinterpret_cast<uint32_t*>(&p0);
+                            u.y = *reinterpret_cast<uint32_t*>(&p1);
+                            u.z = *reinterpret_cast<uint32_t*>(&p2);
+                            u.w = *reinterpret_cast<uint32_t*>(&p3);
+                            dst[i] = u;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (co + i < a.cout) orow[co + i] = __float2bfloat16_rn(f[i]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, a.tmem_cols);
+    }
+}
+
+}  // namespace
+
+size_t conv_tc_smem_bytes(const ConvArgs& a) {
+    return static_cast<size_t>(a.nstages) * (a.a_stage_bytes + a.b_stage_bytes) + 1024 /*barriers*/ + 1024 /*align*/;
+}
+
+cudaError_t launch_conv_tc(const ConvArgs& a, int grid, size_t smem_bytes, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    conv_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace bsg

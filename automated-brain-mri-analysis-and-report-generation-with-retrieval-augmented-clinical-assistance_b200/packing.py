@@ -1,0 +1,60 @@
+"""Weight / activation layout helpers for the tcgen05 conv kernels (host side, torch tensors)."""
+import torch
+
+
+def round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def pack_conv3_weight(w, cin_pad=None):
+    """nn.Conv3d weight (Cout, Cin, kd, kh, kw) -> bf16 [27 taps (kd,kw,kh)][cout_pad][cin_pad]."""
+    cout, cin = w.shape[0], w.shape[1]
+    cin_pad = cin_pad or round_up(cin, 16)
+    cout_pad = round_up(cout, 32)
+    p = torch.zeros(27, cout_pad, cin_pad, dtype=torch.float32, device=w.device)
+    p[:, :cout, :cin] = w.float().permute(2, 4, 3, 0, 1).reshape(27, cout, cin)
+    return p.to(torch.bfloat16).contiguous()
+
+
+def pack_conv1_weight(w, cin_pad=None):
+    """1x1x1 conv weight (Cout, Cin, 1, 1, 1) -> bf16 [1][cout_pad][cin_pad]."""
+    cout, cin = w.shape[0], w.shape[1]
+    cin_pad = cin_pad or round_up(cin, 16)
+    cout_pad = round_up(cout, 32)
+    p = torch.zeros(1, cout_pad, cin_pad, dtype=torch.float32, device=w.device)
+    p[0, :cout, :cin] = w.float().reshape(cout, cin)
+    return p.to(torch.bfloat16).contiguous()
+
+
+def pack_convT2_weight(w, cin_pad=None):
+    """nn.ConvTranspose3d k2 s2 weight (Cin, Cout, kd, kh, kw) -> bf16 [1][8 parities (kd,kh,kw) * cout_pad][cin_pad]."""
+    cin, cout = w.shape[0], w.shape[1]
+    cin_pad = cin_pad or round_up(cin, 16)
+    cout_pad = round_up(cout, 32)
+    p = torch.zeros(8, cout_pad, cin_pad, dtype=torch.float32, device=w.device)
+    p[:, :cout, :cin] = w.float().permute(2, 3, 4, 1, 0).reshape(8, cout, cin)
+    return p.reshape(1, 8 * cout_pad, cin_pad).to(torch.bfloat16).contiguous()
+
+
+def pad_bias(b, cout):
+    cout_pad = round_up(cout, 32)
+    out = torch.zeros(cout_pad, dtype=torch.float32, device=b.device if b is not None else None)
+    if b is not None:
+        out[:cout] = b.float()
+    return out
+
+
+def to_ndhwc_bf16(x, c_pad=None):
+    """(N, C, D, H, W) float -> (N, D, H, W, c_pad) bf16, zero-padded channels."""
+    n, c, d, h, w = x.shape
+    c_pad = c_pad or round_up(c, 16)
+    out = torch.zeros(n, d, h, w, c_pad, dtype=torch.bfloat16, device=x.device)
+    out[..., :c] = x.permute(0, 2, 3, 4, 1).to(torch.bfloat16)
+    return out
+
+
+def from_ndhwc(x, c=None):
+    """(N, D, H, W, C) -> (N, c, D, H, W) float32."""
+    if c is not None:
+        x = x[..., :c]
+    return x.permute(0, 4, 1, 2, 3).float().contiguous()

@@ -1,0 +1,157 @@
+"""Generates tests/golden/* by running the REFERENCE's own code (imported from /root/reference, see ref_import.py)
+on small seeded inputs.  Run in the build container:  python -m oracle.make_golden
+
+Fixtures (all small, committed):
+  unet_{bn,in,gn}.pt      state_dict + arch + input + logits of the reference Generic_UNet (tiny widths)
+  unet_keys.json          state_dict key list / shapes, parameter count and forward GFLOPs of the two BraTS shapes
+  postproc.npz/.json      label volumes and the reference functions' outputs on them (remap, Dice, step3, step4)
+  sliding_window.json     known-answer facts for the restated nnU-Net v1 tiler
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_import as R  # noqa: E402
+from oracle import unet as U  # noqa: E402
+from oracle import sliding_window as SW  # noqa: E402
+from oracle import synthetic as SY  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def jsonable(o):
+    if isinstance(o, dict):
+        return {str(k): jsonable(v) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return [jsonable(v) for v in o]
+    if isinstance(o, np.generic):
+        # keep float32 results exactly: repr via float() is exact for float32 -> float64
+        return o.item()
+    if isinstance(o, np.ndarray):
+        return o.tolist()
+    return o
+
+
+def unet_fixtures():
+    for variant in ("bn", "in", "gn"):
+        net = R.build_reference_unet(variant, base=4, num_pool=3, groups=2, seed=11)
+        g = torch.Generator().manual_seed(5)
+        x = torch.randn(1, 4, 16, 16, 16, generator=g)
+        with torch.no_grad():
+            y = net(x)
+        torch.save({"state_dict": {k: v.clone() for k, v in net.state_dict().items()},
+                    "arch": U.arch_from_module(net), "x": x, "logits": y}, os.path.join(OUT, f"unet_{variant}.pt"))
+    keys = {}
+    for name, variant, kw in (("model1_bn", "bn", {}),
+                              ("model2_gn_large", "gn", dict(encoder_scale=2, max_num_features=512, groups=8))):
+        net = R.build_reference_unet(variant, **kw)
+        sd = net.state_dict()
+        arch = U.arch_from_module(net)
+        keys[name] = {"keys": {k: list(v.shape) for k, v in sd.items()},
+                      "params": int(sum(p.numel() for p in net.parameters())),
+                      "gflops_128": U.conv_flops(sd, arch, (128, 128, 128)) / 1e9, "arch": jsonable(arch)}
+    with open(os.path.join(OUT, "unet_keys.json"), "w") as f:
+        json.dump(keys, f, indent=1)
+
+
+def postproc_fixtures():
+    ns = R.load_reference()
+    shape = (48, 40, 36)
+    vols, results = {}, {}
+    voxel_dims = (1.0, 1.0, 1.0)
+    aniso = (0.9, 1.1, 1.25)
+    for seed in (0, 1, 2):
+        pred, gt = SY.label_pair(seed, shape)
+        # sprinkle a few isolated voxels / label-4 voxels so fragments, ties and "other" labels are exercised
+        rng = np.random.default_rng(100 + seed)
+        for _ in range(12):
+            p = tuple(rng.integers(0, s) for s in shape)
+            pred[p] = rng.integers(1, 4)
+        if seed == 2:
+            pred[pred == 3] = 4  # BraTS-2021 convention volume
+        vols[f"pred{seed}"] = pred
+        vols[f"gt{seed}"] = gt
+        predf, gtf = pred.astype(np.float64), gt.astype(np.float64)
+        r = {}
+        r["remap2025_sha"] = ns.convert_labels.convert_labels_to_brats2025(predf).tolist() if False else None
+        vols[f"remap2025_{seed}"] = ns.convert_labels.convert_labels_to_brats2025(predf)
+        vols[f"remap2021_{seed}"] = ns.convert_labels.convert_labels_to_brats2021(predf)
+        vols[f"ensemble_{seed}"] = np.round((predf + gtf) / 2.0).astype(np.uint8)  # run_brats...py:305 expression
+        labs = sorted(set(np.unique(predf)) | set(np.unique(gtf)))
+        r["metrics"] = {str(int(l)): ns.evaluate.calculate_metrics(predf, gtf, l) for l in labs if l != 0}
+        r["wt"] = ns.evaluate.calculate_metrics_binary(np.isin(predf, [1, 2, 3]).astype(np.float32),
+                                                       np.isin(gtf, [1, 2, 3]).astype(np.float32))
+        r["tc"] = ns.evaluate.calculate_metrics_binary(np.isin(predf, [1, 3]).astype(np.float32),
+                                                       np.isin(gtf, [1, 3]).astype(np.float32))
+        seg = np.round(predf).astype(np.int32)  # step3_multiplicity.py:460
+        for tag, vd in (("iso", voxel_dims), ("aniso", aniso)):
+            r[f"components_{tag}"] = ns.step3.detect_connected_components(seg, vd)
+            r[f"enhancing_{tag}"] = ns.step3.analyze_enhancing_components(seg, vd)
+            masks = ns.utils.get_tumor_masks(predf)
+            r[f"shape_{tag}"] = ns.step4.calculate_shape_descriptors(predf, masks, vd)
+            r[f"necrosis_{tag}"] = ns.step4.analyze_necrosis_pattern(predf, masks, np.array(vd))
+        masks = ns.utils.get_tumor_masks(predf)
+        r["mask_counts"] = {k: int(v.sum()) for k, v in masks.items()}
+        r["centroids"] = {k: ns.utils.get_centroid(v) for k, v in masks.items()}
+        r["bboxes"] = {k: ns.utils.get_bounding_box(v) for k, v in masks.items()}
+        r["surface_count_wt"] = int((masks["wt"] & ~__import__("scipy.ndimage").ndimage.binary_erosion(masks["wt"])).sum())
+        lab, n = __import__("scipy.ndimage").ndimage.label(seg > 0, structure=np.ones((3, 3, 3)))
+        vols[f"cc_labels_{seed}"] = lab.astype(np.int32)
+        r["cc_count"] = int(n)
+        r.pop("remap2025_sha")
+        results[str(seed)] = jsonable(r)
+    # empty-volume behaviour
+    empty = np.zeros((8, 8, 8))
+    results["empty"] = jsonable({
+        "components": ns.step3.detect_connected_components(empty.astype(np.int32), voxel_dims),
+        "enhancing": ns.step3.analyze_enhancing_components(empty.astype(np.int32), voxel_dims),
+        "shape": ns.step4.calculate_shape_descriptors(empty, ns.utils.get_tumor_masks(empty), voxel_dims),
+        "necrosis": ns.step4.analyze_necrosis_pattern(empty, ns.utils.get_tumor_masks(empty), np.array(voxel_dims)),
+    })
+    np.savez_compressed(os.path.join(OUT, "postproc.npz"), **vols)
+    with open(os.path.join(OUT, "postproc.json"), "w") as f:
+        json.dump(results, f, indent=1)
+
+
+def sliding_window_facts():
+    g = SW.get_gaussian((128, 128, 128), 1.0 / 8)
+    facts = {
+        "source": "restated nnU-Net v1 (UPSTREAM, not in /root/reference); values from SURVEY.md §8c/§8d",
+        "steps": {
+            "155x240x240_p128_s0.5": SW.compute_steps_for_sliding_window((128,) * 3, (155, 240, 240), 0.5),
+            "155x240x240_p128_s0.25": SW.compute_steps_for_sliding_window((128,) * 3, (155, 240, 240), 0.25),
+            "256_p128_s0.5": SW.compute_steps_for_sliding_window((128,) * 3, (256,) * 3, 0.5),
+            "256_p128_s0.25": SW.compute_steps_for_sliding_window((128,) * 3, (256,) * 3, 0.25),
+            "256_p160_s0.5": SW.compute_steps_for_sliding_window((160,) * 3, (256,) * 3, 0.5),
+            "256_p160_s0.25": SW.compute_steps_for_sliding_window((160,) * 3, (256,) * 3, 0.25),
+            "137x171x140_p128_s0.5": SW.compute_steps_for_sliding_window((128,) * 3, (137, 171, 140), 0.5),
+        },
+        "survey_expected_steps": {
+            "155x240x240_p128_s0.5": [[0, 27], [0, 56, 112], [0, 56, 112]],
+            "155x240x240_p128_s0.25": [[0, 27], [0, 28, 56, 84, 112], [0, 28, 56, 84, 112]],
+            "256_p128_s0.5": [[0, 64, 128]] * 3,
+            "256_p128_s0.25": [[0, 32, 64, 96, 128]] * 3,
+            "256_p160_s0.5": [[0, 48, 96]] * 3,
+            "256_p160_s0.25": [[0, 32, 64, 96]] * 3,
+        },
+        "gaussian_128": {"min": float(g.min()), "max": float(g.max()), "corner": float(g[0, 0, 0]),
+                         "center": float(g[64, 64, 64]), "survey_min": 3.7751344e-11},
+        "ensemble_lut": [[int(np.round((a + b) / 2.0)) for b in range(4)] for a in range(4)],
+        "survey_ensemble_lut": [[0, 0, 1, 2], [0, 1, 2, 2], [1, 2, 2, 2], [2, 2, 2, 3]],
+    }
+    with open(os.path.join(OUT, "sliding_window.json"), "w") as f:
+        json.dump(facts, f, indent=1)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    unet_fixtures()
+    postproc_fixtures()
+    sliding_window_facts()
+    for fn in sorted(os.listdir(OUT)):
+        print(fn, os.path.getsize(os.path.join(OUT, fn)))

@@ -1,0 +1,28 @@
+"""Seeded synthetic inputs shared by the tests, smoke() and bench.py."""
+import numpy as np
+import torch
+from scipy.ndimage import gaussian_filter
+
+
+def case_volume(seed=0, shape=(4, 155, 240, 240)):
+    """BASELINE config 1/2 input: randn(4,155,240,240) fp32, array order (C, z, y, x)."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g, dtype=torch.float32).numpy()
+
+
+def label_volume(seed=0, shape=(240, 240, 155), sigma=6.0):
+    """Blobby label volume: smoothed noise thresholded at 1.5/2.0/2.5 sigma -> labels 1/2/3 (≈6 % tumour)."""
+    rng = np.random.default_rng(seed)
+    f = gaussian_filter(rng.standard_normal(shape), sigma)
+    f = (f - f.mean()) / f.std()
+    lab = np.zeros(shape, dtype=np.uint8)
+    lab[f > 1.5] = 1
+    lab[f > 2.0] = 2
+    lab[f > 2.5] = 3
+    return lab
+
+
+def label_pair(seed=0, shape=(240, 240, 155)):
+    """(prediction, ground truth) pair: the prediction is the GT rolled by 3 voxels along axis 0."""
+    gt = label_volume(seed, shape)
+    return np.roll(gt, 3, axis=0).copy(), gt
