@@ -58,10 +58,26 @@ def _declare(lib):
         fn = getattr(lib, name)
         fn.restype = i
         fn.argtypes = sig
+    lib.bsg_ccl26_workspace_bytes.restype = C.c_size_t
+    lib.bsg_ccl26_workspace_bytes.argtypes = [i, i, i]
 
 
-# name -> argtypes for the flat (non-plan) entry points; filled in as kernels are added (see postproc.cu, tail.cu)
-_EXTRA_SIGS = {}
+_vp, _i, _sz, _u32, _f, _d = C.c_void_p, C.c_int, C.c_size_t, C.c_uint32, C.c_float, C.c_double
+# name -> argtypes for the flat (non-plan) entry points (postproc.cu, tail.cu); all return int
+_EXTRA_SIGS = {
+    "bsg_label_lut_u8": [_vp, _vp, _sz, C.c_char_p, _vp],
+    "bsg_label_pair_round_u8": [_vp, _vp, _vp, _sz, C.c_char_p, _vp],
+    "bsg_round_to_u8": [_vp, _i, _vp, _sz, _vp],
+    "bsg_joint_hist_u8": [_vp, _vp, _sz, _vp, _vp, _vp],
+    "bsg_ccl26_stats": [_vp, _i, _i, _i, _u32, _vp, _vp, _vp, _i, _vp, _sz, _vp],
+    "bsg_masked_moments": [_vp, _i, _i, _i, C.POINTER(_u32), _i, _u32, _vp, _vp],
+    "bsg_gather_patch_tta": [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(_i), _i, _vp, _i, _vp],
+    "bsg_norm_finalize": [_vp, _i, _i, _i, _d, _f, _vp, _vp, _vp, _vp],
+    "bsg_norm_apply_lrelu": [_vp, _sz, _i, _i, _i, _i, _vp, _f, _vp],
+    "bsg_head_tta_accumulate": [_vp, _i, _i, _i, _i, _i, C.POINTER(_i), _i, C.POINTER(_f), C.POINTER(_f), _i, _i,
+                                _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "bsg_finalize": [C.POINTER(_vp), _i, _vp, _i, _sz, _i, C.POINTER(_i), _vp, _vp, _vp],
+}
 
 
 def lib():

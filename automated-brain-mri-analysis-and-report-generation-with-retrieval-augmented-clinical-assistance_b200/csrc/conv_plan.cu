@@ -172,6 +172,8 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
     }
     a.khshift = khs;
     const uint32_t sb = stage_bytes(khs, &a.a_stage_bytes, &a.b_stage_bytes);
+    a.stage_tx_bytes = (khs ? static_cast<uint32_t>((a.bh + 2) * 8) : 128u) * a.cc * 2 +
+                       static_cast<uint32_t>(a.ntile) * a.cc * 2 * (khs ? 3 : 1);
     a.nstages = static_cast<int>(budget / sb);
     if (a.nstages > 12) a.nstages = 12;
     if (a.nstages < 2) {

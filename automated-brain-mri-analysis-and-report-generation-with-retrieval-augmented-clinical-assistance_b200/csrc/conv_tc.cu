@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                         mbar_wait(&empty_bar[s], ph_bit ^ 1u);
                         uint8_t* sa = smem + static_cast<size_t>(s) * stage_bytes;
                         uint8_t* sb = sa + a.a_stage_bytes;
-                        mbar_expect_tx(&full_bar[s], a.a_stage_bytes + a.b_stage_bytes);
+                        mbar_expect_tx(&full_bar[s], a.stage_tx_bytes);
                         tma_load_5d(sa, &a.mapA[mi], &full_bar[s], c * a.cc, cw, ch, cd, t.n0);
                         tma_load_3d(sb, &a.mapW, &full_bar[s], c * a.cc, nrow0, tap);
                     }

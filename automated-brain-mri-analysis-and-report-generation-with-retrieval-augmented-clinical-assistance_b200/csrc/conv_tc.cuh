@@ -21,7 +21,8 @@ struct ConvArgs {
     int stride;           // 1 or 2
     int khshift;          // 1: an A stage holds bh+2 rows of h (box (cc, 8, bh+2, 1, 1)) and serves 3 kh taps
     int nstages;
-    uint32_t a_stage_bytes, b_stage_bytes;  // both multiples of 1024
+    uint32_t a_stage_bytes, b_stage_bytes;  // smem footprint of one stage, both multiples of 1024
+    uint32_t stage_tx_bytes;                // bytes the two TMA boxes of a stage actually deliver
     uint32_t tmem_cols;                     // power of two >= 2*ntile
     // epilogue
     __nv_bfloat16* out;

@@ -1,0 +1,367 @@
+// Fused HBM-bound passes around the conv stacks of predict_3D (nnU-Net v1 `_internal_predict_3D_3Dconv_tiled` and
+// `_internal_maybe_mirror_and_pred_3D`; call site
+// run_brats2021_inference_singlethread.py:97-106):
+//   gather_patch_tta      tile crop + 8-way mirror flips + fp32 -> bf16 channels-last (input side of the TTA)
+//   norm_finalize / norm_apply_lrelu   InstanceNorm / GroupNorm from the conv epilogue's (sum, sumsq) + LeakyReLU
+//   head_tta_accumulate   1x1x1 seg head + sigmoid/softmax + un-flip + mean over mirrors + Gaussian weight +
+//                         accumulate into the full-volume fp32 accumulator
+//   finalize              / weight-sum, mean over folds, ordered-threshold or argmax decision -> uint8 labels
+#include <cuda_bf16.h>
+#include "bsg_common.cuh"
+
+namespace bsg {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxMirrors = 8;
+constexpr int kMaxClasses = 8;
+
+struct MirrorSet {
+    int n;
+    int code[kMaxMirrors];  // bit0: flip x (tensor dim 4), bit1: flip y (dim 3), bit2: flip z (dim 2)
+};
+
+// out[m][d][h][w][c] = vol[c][z0 + fz(d)][y0 + fy(h)][x0 + fx(w)], c < C; channels C..cpad-1 are zero.
+__global__ void __launch_bounds__(kThreads) gather_patch_kernel(const float* __restrict__ vol, int C, int Z, int Y,
+                                                                int X, int z0, int y0, int x0, int P0, int P1, int P2,
+                                                                const MirrorSet ms, __nv_bfloat16* __restrict__ out,
+                                                                int cpad) {
+    const size_t pv = static_cast<size_t>(P0) * P1 * P2;
+    const size_t total = pv * ms.n;
+    const size_t plane = static_cast<size_t>(Z) * Y * X;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int m = static_cast<int>(i / pv);
+        size_t r = i - static_cast<size_t>(m) * pv;
+        const int w = static_cast<int>(r % P2);
+        r /= P2;
+        const int h = static_cast<int>(r % P1);
+        const int d = static_cast<int>(r / P1);
+        const int code = ms.code[m];
+        const int sx = x0 + ((code & 1) ? P2 - 1 - w : w);
+        const int sy = y0 + ((code & 2) ? P1 - 1 - h : h);
+        const int sz = z0 + ((code & 4) ? P0 - 1 - d : d);
+        const float* src = vol + (static_cast<size_t>(sz) * Y + sy) * X + sx;
+        __nv_bfloat16* dst = out + i * cpad;
+        // cpad is a multiple of 8: write 16-byte groups
+        for (int c0 = 0; c0 < cpad; c0 += 8) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int ca = c0 + 2 * k, cb = ca + 1;
+                const float fa = ca < C ? __ldg(src + ca * plane) : 0.f;
+                const float fb = cb < C ? __ldg(src + cb * plane) : 0.f;
+                __nv_bfloat162 p = __floats2bfloat162_rn(fa, fb);
+                pk[k] = *reinterpret_cast<uint32_t*>(&p);
+            }
+            *reinterpret_cast<uint4*>(dst + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- norms
+// stats [N][C][2] (sum, sumsq over `count` voxels) -> per (n,c) affine: y = x*scale + shift.
+// groups == 0: InstanceNorm (per channel); groups > 0: GroupNorm (C/groups channels share statistics).
+__global__ void norm_finalize_kernel(const float* __restrict__ stats, int N, int C, int groups, double count, float eps,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     float* __restrict__ scale_shift /* [N][C][2] */) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * C) return;
+    const int n = i / C, c = i % C;
+    double s1, s2, cnt;
+    if (groups > 0) {
+        const int cg = C / groups, g = c / cg;
+        s1 = s2 = 0.0;
+        for (int k = 0; k < cg; ++k) {
+            s1 += stats[(static_cast<size_t>(n) * C + g * cg + k) * 2];
+            s2 += stats[(static_cast<size_t>(n) * C + g * cg + k) * 2 + 1];
+        }
+        cnt = count * cg;
+    } else {
+        s1 = stats[static_cast<size_t>(i) * 2];
+        s2 = stats[static_cast<size_t>(i) * 2 + 1];
+        cnt = count;
+    }
+    const double mean = s1 / cnt;
+    double var = s2 / cnt - mean * mean;  // biased variance, as torch's instance_norm / group_norm
+    if (var < 0.0) var = 0.0;
+    const double rstd = 1.0 / sqrt(var + static_cast<double>(eps));
+    const double ga = gamma ? static_cast<double>(gamma[c]) : 1.0, be = beta ? static_cast<double>(beta[c]) : 0.0;
+    scale_shift[static_cast<size_t>(i) * 2] = static_cast<float>(ga * rstd);
+    scale_shift[static_cast<size_t>(i) * 2 + 1] = static_cast<float>(be - mean * ga * rstd);
+}
+
+// in place on a channel slice [coff, coff+C) of a (N, V, ctot) bf16 buffer: x <- lrelu(x*scale + shift)
+__global__ void __launch_bounds__(kThreads) norm_apply_kernel(__nv_bfloat16* __restrict__ x, size_t V, int N, int C,
+                                                              int ctot, int coff,
+                                                              const float* __restrict__ scale_shift, float slope) {
+    const int c8n = C / 8;
+    const size_t total = static_cast<size_t>(N) * V * c8n;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int c8 = static_cast<int>(i % c8n);
+        const size_t nv = i / c8n;
+        const int n = static_cast<int>(nv / V);
+        uint4* p = reinterpret_cast<uint4*>(x + nv * ctot + coff + c8 * 8);
+        uint4 u = *p;
+        uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        const float4* ss = reinterpret_cast<const float4*>(scale_shift + (static_cast<size_t>(n) * C + c8 * 8) * 2);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float4 s = __ldg(ss + k);  // (scale0, shift0, scale1, shift1)
+            __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&w[k]);
+            float a = __bfloat162float(v.x) * s.x + s.y;
+            float b = __bfloat162float(v.y) * s.z + s.w;
+            a = a > 0.f ? a : a * slope;
+            b = b > 0.f ? b : b * slope;
+            __nv_bfloat162 o = __floats2bfloat162_rn(a, b);
+            w[k] = *reinterpret_cast<uint32_t*>(&o);
+        }
+        *p = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- head + TTA + accumulate
+struct HeadParams {
+    float w[kMaxClasses][32];
+    float b[kMaxClasses];
+    int ncls;
+    int nonlin;  // 0: sigmoid, 1: softmax over classes, 2: identity
+};
+
+__global__ void __launch_bounds__(kThreads) head_tta_accumulate_kernel(
+    const __nv_bfloat16* __restrict__ feat, int ctot, int P0, int P1, int P2, const MirrorSet ms,
+    const __grid_constant__ HeadParams hp, const float* __restrict__ gauss, float* __restrict__ acc, int Z, int Y, int X,
+    int z0, int y0, int x0) {
+    const size_t pv = static_cast<size_t>(P0) * P1 * P2;
+    const size_t plane = static_cast<size_t>(Z) * Y * X;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    const float inv = 1.0f / static_cast<float>(ms.n);
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < pv; i += stride) {
+        size_t r = i;
+        const int w = static_cast<int>(r % P2);
+        r /= P2;
+        const int h = static_cast<int>(r % P1);
+        const int d = static_cast<int>(r / P1);
+        float res[kMaxClasses];
+#pragma unroll
+        for (int k = 0; k < kMaxClasses; ++k) res[k] = 0.f;
+        for (int m = 0; m < ms.n; ++m) {
+            const int code = ms.code[m];
+            // prediction m was computed on the flipped tile: its voxel for (d,h,w) sits at the flipped position
+            const int sw = (code & 1) ? P2 - 1 - w : w;
+            const int sh = (code & 2) ? P1 - 1 - h : h;
+            const int sd = (code & 4) ? P0 - 1 - d : d;
+            const size_t v = ((static_cast<size_t>(m) * P0 + sd) * P1 + sh) * P2 + sw;
+            const uint4* fp = reinterpret_cast<const uint4*>(feat + v * ctot);
+            float f[32];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint4 u = __ldg(fp + q);
+                const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&ww[k]);
+                    f[q * 8 + 2 * k] = __bfloat162float(b2.x);
+                    f[q * 8 + 2 * k + 1] = __bfloat162float(b2.y);
+                }
+            }
+            float logit[kMaxClasses];
+#pragma unroll
+            for (int k = 0; k < kMaxClasses; ++k) {
+                if (k < hp.ncls) {
+                    float s = hp.b[k];
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) s = fmaf(hp.w[k][c], f[c], s);
+                    logit[k] = s;
+                }
+            }
+            if (hp.nonlin == 0) {
+#pragma unroll
+                for (int k = 0; k < kMaxClasses; ++k)
+                    if (k < hp.ncls) res[k] += inv * (1.0f / (1.0f + expf(-logit[k])));
+            } else if (hp.nonlin == 1) {
+                float mx = -INFINITY;
+#pragma unroll
+                for (int k = 0; k < kMaxClasses; ++k)
+                    if (k < hp.ncls) mx = fmaxf(mx, logit[k]);
+                float e[kMaxClasses], sum = 0.f;
+#pragma unroll
+                for (int k = 0; k < kMaxClasses; ++k)
+                    if (k < hp.ncls) {
+                        e[k] = expf(logit[k] - mx);
+                        sum += e[k];
+                    }
+#pragma unroll
+                for (int k = 0; k < kMaxClasses; ++k)
+                    if (k < hp.ncls) res[k] += inv * (e[k] / sum);
+            } else {
+#pragma unroll
+                for (int k = 0; k < kMaxClasses; ++k)
+                    if (k < hp.ncls) res[k] += inv * logit[k];
+            }
+        }
+        const float g = gauss ? __ldg(gauss + i) : 1.0f;
+        float* ap = acc + (static_cast<size_t>(z0 + d) * Y + (y0 + h)) * X + (x0 + w);
+#pragma unroll
+        for (int k = 0; k < kMaxClasses; ++k)
+            if (k < hp.ncls) ap[k * plane] += res[k] * g;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- finalize
+struct FinalizeParams {
+    const float* acc[8];  // K accumulators (folds / models to average), each [ncls][nvox]
+    int K;
+    int ncls;
+    int mode;                // 0: argmax, 1: ordered threshold > 0.5 (regions)
+    int order[kMaxClasses];  // regions_class_order
+};
+
+__global__ void __launch_bounds__(kThreads) finalize_kernel(const FinalizeParams fp, const float* __restrict__ wsum,
+                                                            size_t nvox, float* __restrict__ probs,
+                                                            uint8_t* __restrict__ seg) {
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvox; i += stride) {
+        const float wv = __ldg(wsum + i);
+        float p[kMaxClasses];
+#pragma unroll
+        for (int k = 0; k < kMaxClasses; ++k) {
+            if (k < fp.ncls) {
+                // class_probabilities = aggregated_results / aggregated_nb_of_predictions, then np.mean over folds
+                float s = __ldg(fp.acc[0] + k * nvox + i) / wv;
+                for (int j = 1; j < fp.K; ++j) s += __ldg(fp.acc[j] + k * nvox + i) / wv;
+                if (fp.K > 1) s = s / static_cast<float>(fp.K);
+                p[k] = s;
+                if (probs) probs[k * nvox + i] = s;
+            }
+        }
+        if (seg) {
+            int lab = 0;
+            if (fp.mode == 0) {
+                float best = p[0];
+#pragma unroll
+                for (int k = 1; k < kMaxClasses; ++k)
+                    if (k < fp.ncls && p[k] > best) {
+                        best = p[k];
+                        lab = k;
+                    }
+            } else {
+#pragma unroll
+                for (int k = 0; k < kMaxClasses; ++k)
+                    if (k < fp.ncls && p[k] > 0.5f) lab = fp.order[k];
+            }
+            seg[i] = static_cast<uint8_t>(lab);
+        }
+    }
+}
+
+inline int grid_for(size_t work, int per_block, int waves = 8) {
+    size_t blocks = (work + per_block - 1) / per_block;
+    const size_t cap = static_cast<size_t>(sm_count_cached()) * waves;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return static_cast<int>(blocks);
+}
+
+int fill_mirrors(MirrorSet* ms, const int* codes, int n) {
+    BSG_REQUIRE(n >= 1 && n <= kMaxMirrors && codes != nullptr, "mirror count %d (1..8)", n);
+    ms->n = n;
+    for (int i = 0; i < kMaxMirrors; ++i) ms->code[i] = i < n ? (codes[i] & 7) : 0;
+    return BSG_OK;
+}
+
+}  // namespace
+}  // namespace bsg
+
+using namespace bsg;
+
+extern "C" {
+
+int bsg_gather_patch_tta(const float* vol, int C, int Z, int Y, int X, int z0, int y0, int x0, int P0, int P1, int P2,
+                         const int* mirror_codes_host, int nmirrors, void* out_bf16, int cpad, void* stream) {
+    BSG_REQUIRE(vol != nullptr && out_bf16 != nullptr, "null argument");
+    BSG_REQUIRE(cpad % 8 == 0 && cpad >= C, "cpad %d must be a multiple of 8 and >= C=%d", cpad, C);
+    BSG_REQUIRE(z0 >= 0 && y0 >= 0 && x0 >= 0 && z0 + P0 <= Z && y0 + P1 <= Y && x0 + P2 <= X,
+                "tile exceeds the volume");
+    MirrorSet ms;
+    int rc = fill_mirrors(&ms, mirror_codes_host, nmirrors);
+    if (rc != BSG_OK) return rc;
+    const size_t total = static_cast<size_t>(P0) * P1 * P2 * nmirrors;
+    gather_patch_kernel<<<grid_for(total, kThreads, 16), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        vol, C, Z, Y, X, z0, y0, x0, P0, P1, P2, ms, static_cast<__nv_bfloat16*>(out_bf16), cpad);
+    BSG_CUDA_OK(cudaGetLastError());
+    return BSG_OK;
+}
+
+int bsg_norm_finalize(const float* stats, int N, int C, int groups, double count, float eps, const float* gamma,
+                      const float* beta, float* scale_shift, void* stream) {
+    BSG_REQUIRE(stats != nullptr && scale_shift != nullptr, "null argument");
+    BSG_REQUIRE(groups >= 0 && (groups == 0 || C % groups == 0), "C %d not divisible by groups %d", C, groups);
+    norm_finalize_kernel<<<ceil_div(N * C, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        stats, N, C, groups, count, eps, gamma, beta, scale_shift);
+    BSG_CUDA_OK(cudaGetLastError());
+    return BSG_OK;
+}
+
+int bsg_norm_apply_lrelu(void* x_bf16, size_t voxels_per_item, int N, int C, int ctot, int coff,
+                         const float* scale_shift, float slope, void* stream) {
+    BSG_REQUIRE(x_bf16 != nullptr && scale_shift != nullptr, "null argument");
+    BSG_REQUIRE(C % 8 == 0 && ctot % 8 == 0 && coff % 8 == 0, "channel counts must be multiples of 8");
+    const size_t total = static_cast<size_t>(N) * voxels_per_item * (C / 8);
+    norm_apply_kernel<<<grid_for(total, kThreads, 16), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<__nv_bfloat16*>(x_bf16), voxels_per_item, N, C, ctot, coff, scale_shift, slope);
+    BSG_CUDA_OK(cudaGetLastError());
+    return BSG_OK;
+}
+
+int bsg_head_tta_accumulate(const void* feat_bf16, int cfeat, int ctot, int P0, int P1, int P2,
+                            const int* mirror_codes_host, int nmirrors, const float* head_w_host,
+                            const float* head_b_host, int ncls, int nonlin, const float* gauss, float* acc, int Z, int Y,
+                            int X, int z0, int y0, int x0, void* stream) {
+    BSG_REQUIRE(feat_bf16 != nullptr && head_w_host != nullptr && acc != nullptr, "null argument");
+    BSG_REQUIRE(cfeat == 32, "the fused head expects 32 feature channels (got %d)", cfeat);
+    BSG_REQUIRE(ctot % 8 == 0, "ctot must be a multiple of 8");
+    BSG_REQUIRE(ncls >= 1 && ncls <= kMaxClasses, "ncls %d (1..%d)", ncls, kMaxClasses);
+    BSG_REQUIRE(nonlin >= 0 && nonlin <= 2, "nonlin %d", nonlin);
+    BSG_REQUIRE(z0 >= 0 && y0 >= 0 && x0 >= 0 && z0 + P0 <= Z && y0 + P1 <= Y && x0 + P2 <= X,
+                "tile exceeds the volume");
+    MirrorSet ms;
+    int rc = fill_mirrors(&ms, mirror_codes_host, nmirrors);
+    if (rc != BSG_OK) return rc;
+    HeadParams hp;
+    memset(&hp, 0, sizeof(hp));
+    hp.ncls = ncls;
+    hp.nonlin = nonlin;
+    for (int k = 0; k < ncls; ++k) {
+        for (int c = 0; c < 32; ++c) hp.w[k][c] = head_w_host[k * 32 + c];
+        hp.b[k] = head_b_host ? head_b_host[k] : 0.f;
+    }
+    const size_t pv = static_cast<size_t>(P0) * P1 * P2;
+    head_tta_accumulate_kernel<<<grid_for(pv, kThreads, 64), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(feat_bf16), ctot, P0, P1, P2, ms, hp, gauss, acc, Z, Y, X, z0, y0, x0);
+    BSG_CUDA_OK(cudaGetLastError());
+    return BSG_OK;
+}
+
+int bsg_finalize(const float* const* acc_list_host, int K, const float* wsum, int ncls, size_t nvox, int mode,
+                 const int* order_host, float* probs, uint8_t* seg, void* stream) {
+    BSG_REQUIRE(acc_list_host != nullptr && wsum != nullptr, "null argument");
+    BSG_REQUIRE(K >= 1 && K <= 8, "K %d (1..8)", K);
+    BSG_REQUIRE(ncls >= 1 && ncls <= kMaxClasses, "ncls %d", ncls);
+    BSG_REQUIRE(mode == 0 || (mode == 1 && order_host != nullptr), "mode %d", mode);
+    FinalizeParams fp;
+    memset(&fp, 0, sizeof(fp));
+    for (int j = 0; j < K; ++j) fp.acc[j] = acc_list_host[j];
+    fp.K = K;
+    fp.ncls = ncls;
+    fp.mode = mode;
+    for (int k = 0; k < ncls; ++k) fp.order[k] = order_host ? order_host[k] : k;
+    if (nvox == 0) return BSG_OK;
+    finalize_kernel<<<grid_for(nvox, kThreads, 16), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(fp, wsum, nvox,
+                                                                                                     probs, seg);
+    BSG_CUDA_OK(cudaGetLastError());
+    return BSG_OK;
+}
+
+}  // extern "C"

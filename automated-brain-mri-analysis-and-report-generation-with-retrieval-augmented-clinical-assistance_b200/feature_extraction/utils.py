@@ -1,0 +1,115 @@
+"""Drop-in for the mask helpers of the reference's feature_extraction/utils.py (:167-216).
+
+The reference materialises six boolean volumes; here a mask is a (label volume, label set) pair whose count, centroid,
+bounding box, second moments and surface count all come from ONE device pass (bsg_masked_moments) shared by the
+masks of a volume.
+"""
+import numpy as np
+import torch
+
+from .. import voxelops as V
+
+_REGIONS = {  # utils.py:171-178
+    "ncr": V.bits_of(1),
+    "ed": V.bits_of(2),
+    "et": V.bits_of(3, 4),
+    "tc": V.bits_of(1, 3, 4),
+    "wt": V.MASK_GT0,
+}
+
+
+class LabelVolume:
+    def __init__(self, seg):
+        self.vol = V.as_label_volume(seg)  # np.round(seg).astype(int) happens on the device
+        if self.vol.dim() != 3:
+            raise ValueError("expected a 3-D label volume")
+        self._moments = {}
+
+    def moments(self, bits):
+        if bits not in self._moments:
+            todo = [b for b in dict.fromkeys(list(_REGIONS.values()) + [bits]) if b not in self._moments][:8]
+            if bits not in todo:
+                todo = [bits]
+            res = V.masked_moments(self.vol, todo, surface_flags=(1 << len(todo)) - 1)
+            for b, r in zip(todo, res):
+                self._moments[b] = r
+        return self._moments[bits]
+
+
+class LabelMask:
+    """Lazy boolean mask `isin(volume, labels)`; `.sum()` and `np.asarray()` behave like the reference's arrays."""
+
+    def __init__(self, parent, bits, background=False):
+        self.parent, self.bits, self.background = parent, bits, background
+
+    @property
+    def shape(self):
+        return tuple(self.parent.vol.shape)
+
+    @property
+    def stats(self):
+        if self.background:
+            raise ValueError("only the voxel count is defined for the background mask")
+        return self.parent.moments(self.bits)
+
+    def sum(self):
+        if self.background:
+            return int(self.parent.vol.numel()) - int(self.parent.moments(V.MASK_GT0)["count"])
+        return int(self.stats["count"])
+
+    def tensor(self):
+        v = self.parent.vol.to(torch.int64)
+        m = ((torch.tensor(self.bits, dtype=torch.int64, device=v.device) >> v.clamp(max=31)) & 1).bool() & (v < 32)
+        return ~m if self.background else m
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.tensor().cpu().numpy()
+        return a.astype(dtype) if dtype is not None else a
+
+
+def as_mask(mask):
+    """LabelMask as is; any other boolean/0-1 array becomes a single-label volume."""
+    if isinstance(mask, LabelMask):
+        return mask
+    if isinstance(mask, np.ndarray):
+        mask = mask.astype(np.uint8) if mask.dtype == bool else (mask != 0).astype(np.uint8)
+    elif torch.is_tensor(mask):
+        mask = (mask != 0).to(torch.uint8)
+    return LabelMask(LabelVolume(mask), V.bits_of(1))
+
+
+def get_tumor_masks(seg_data):
+    """Masks for the tumour regions (reference utils.py:167-178): background, ncr, ed, et (3|4), tc (1|3|4), wt (>0)."""
+    parent = seg_data if isinstance(seg_data, LabelVolume) else LabelVolume(seg_data)
+    masks = {"background": LabelMask(parent, V.MASK_GT0, background=True)}
+    for name, bits in _REGIONS.items():
+        masks[name] = LabelMask(parent, bits)
+    return masks
+
+
+def calculate_volume(mask, voxel_volume_cm3):
+    """Volume in cm³ of a mask (reference utils.py:181-183)."""
+    return float(as_mask(mask).sum() * voxel_volume_cm3)
+
+
+def get_centroid(mask):
+    """Centroid of a mask in voxel coordinates (reference utils.py:186-197); None when empty."""
+    m = as_mask(mask)
+    if m.sum() == 0:
+        return None
+    s = m.stats
+    n = int(s["count"])
+    # np.mean of integer coordinates == exact integer sum / count in float64
+    return {"x": float(int(s["s0"]) / n), "y": float(int(s["s1"]) / n), "z": float(int(s["s2"]) / n)}
+
+
+def get_bounding_box(mask):
+    """Bounding box of a mask (reference utils.py:200-216); None when empty."""
+    m = as_mask(mask)
+    if m.sum() == 0:
+        return None
+    s = m.stats
+    mn = [int(s["mn0"]), int(s["mn1"]), int(s["mn2"])]
+    mx = [int(s["mx0"]), int(s["mx1"]), int(s["mx2"])]
+    return {"min_x": mn[0], "max_x": mx[0], "min_y": mn[1], "max_y": mx[1], "min_z": mn[2], "max_z": mx[2],
+            "size_x": mx[0] - mn[0] + 1, "size_y": mx[1] - mn[1] + 1, "size_z": mx[2] - mn[2] + 1}

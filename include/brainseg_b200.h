@@ -84,6 +84,106 @@ typedef struct bsg_conv_info {
 } bsg_conv_info;
 int bsg_conv_plan_info(const bsg_conv_plan* plan, bsg_conv_info* info);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Voxel post-processing (consumers of predict_3D's label volume)
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* out[i] = lut[in[i]].  Replaces the 4 boolean-mask passes of convert_labels_to_brats.py:34-55
+ * (lut = {0,2,1,3,0...} for brats2025, {0,2,1,4,0...} for brats2021).  lut_host: 256 bytes of HOST memory. */
+int bsg_label_lut_u8(const uint8_t* in, uint8_t* out, size_t n, const uint8_t* lut_host, void* stream);
+
+/* out[i] = post[ round_half_even((a[i] + b[i]) / 2) ]: the two-model label ensemble
+ * np.round((seg1+seg2)/2.0).astype(np.uint8) of run_brats2021_inference_singlethread.py:305, optionally fused with a
+ * following label remap (post_lut_host: 256 host bytes, NULL = identity). */
+int bsg_label_pair_round_u8(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, const uint8_t* post_lut_host,
+                            void* stream);
+
+/* np.round(x).astype(np.uint8) (convert_labels_to_brats.py:37, feature_extraction/utils.py:169);
+ * dtype 0 = float32, 1 = float64. */
+int bsg_round_to_u8(const void* in, int dtype, uint8_t* out, size_t n, void* stream);
+
+/* Joint histogram of two label volumes: hist256[p*16+g] = #voxels with pred==p and gt==g (p, g < 16); *bad counts
+ * voxels carrying a label >= 16.  Every TP/FP/FN/TN of evaluate_segmentation.py:25-32 (per label) and of the WT/TC/ET
+ * compounds (:129-151) is a sum of bins.  hist256 (256 x u64) and bad (1 x u64) are device buffers. */
+int bsg_joint_hist_u8(const uint8_t* pred, const uint8_t* gt, size_t n, unsigned long long* hist256,
+                      unsigned long long* bad, void* stream);
+
+/* Per-component record written by bsg_ccl26_stats (88 bytes). */
+typedef struct bsg_comp_stats {
+    unsigned long long count;      /* comp_mask.sum()                       step3_multiplicity.py:65 */
+    unsigned long long s0, s1, s2; /* coordinate sums -> centroids          :71-76 */
+    unsigned long long n1, n2, n3; /* voxels with label 1 / 2 / 3           :104-110 */
+    int mn0, mn1, mn2, mx0, mx1, mx2; /* bounding box                      :86-93 */
+    int pad0, pad1;
+} bsg_comp_stats;
+
+/* 26-connected component labelling (scipy.ndimage.label with generate_binary_structure(3,3),
+ * feature_extraction/step3_multiplicity.py:58-59, :222-223): foreground = voxels whose value v < 32 has bit v set in
+ * maskbits (seg>0 -> 0xFFFFFFFE, seg==3 -> 1<<3).  labels (int32, same shape) receive SciPy's numbering: components
+ * numbered 1.. in C-order raster order of their first voxel.  *ncomp_dev (device int) receives the component count.
+ * comp_stats (device, stats_cap records, may be NULL with stats_cap 0) receives the per-component statistics; if the
+ * count exceeds stats_cap only the first stats_cap components are recorded.  workspace: device scratch of at least
+ * bsg_ccl26_workspace_bytes(). */
+size_t bsg_ccl26_workspace_bytes(int d0, int d1, int d2);
+int bsg_ccl26_stats(const uint8_t* vol, int d0, int d1, int d2, uint32_t maskbits, int* labels, int* ncomp_dev,
+                    void* comp_stats, int stats_cap, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Per-mask record written by bsg_masked_moments (120 bytes). */
+typedef struct bsg_mask_moments {
+    unsigned long long count;                        /* mask.sum()            utils.py:181-183 */
+    unsigned long long s0, s1, s2;                   /* centroid              utils.py:186-197 */
+    unsigned long long s00, s11, s22, s01, s02, s12; /* -> np.cov             step4_morphology.py:100-104 */
+    unsigned long long surface;                      /* (mask & ~binary_erosion(mask)).sum()   step4:42-45 */
+    int mn0, mn1, mn2, mx0, mx1, mx2;                /* bounding box          utils.py:200-216 */
+    int pad[2];
+} bsg_mask_moments;
+
+/* One pass over a label volume computing, for up to 8 label sets (bit masks, bit v = label v, v in 1..31), the voxel
+ * count, first/second coordinate moments, bounding box and — for masks flagged in want_surface — the 6-connected
+ * surface-voxel count with SciPy's border_value=0 semantics.  maskbits_host: nmask host words; out: device records. */
+int bsg_masked_moments(const uint8_t* vol, int d0, int d1, int d2, const uint32_t* maskbits_host, int nmask,
+                       uint32_t want_surface, void* out_moments, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Sliding-window plumbing of predict_3D (nnU-Net v1 _internal_predict_3D_3Dconv_tiled /
+ * _internal_maybe_mirror_and_pred_3D; call site run_brats2021_inference_singlethread.py:97-106)
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* Mirror codes: bit0 = flip x (tensor dim 4), bit1 = flip y (dim 3), bit2 = flip z (dim 2); the upstream order of the
+ * 8 TTA passes is codes 0..7. */
+
+/* out[m][d][h][w][c] (bf16, cpad channels, zero padded) = vol[c][z0+fz(d)][y0+fy(h)][x0+fx(w)]: the tile crop
+ * data[None, :, lb_x:ub_x, ...] plus torch.flip(x, axes) for every mirror m, written as one channels-last batch. */
+int bsg_gather_patch_tta(const float* vol, int C, int Z, int Y, int X, int z0, int y0, int x0, int P0, int P1, int P2,
+                         const int* mirror_codes_host, int nmirrors, void* out_bf16, int cpad, void* stream);
+
+/* InstanceNorm3d / GroupNorm (generic_UNet.py:62-65,72) from the statistics the conv epilogue accumulated:
+ * stats [N][C][2] = (sum, sum of squares) over `count` voxels -> scale_shift [N][C][2] with
+ * y = x*scale + shift == (x-mean)*rsqrt(var+eps)*gamma + beta.  groups = 0: per channel; > 0: GroupNorm. */
+int bsg_norm_finalize(const float* stats, int N, int C, int groups, double count, float eps, const float* gamma,
+                      const float* beta, float* scale_shift, void* stream);
+/* In place on channels [coff, coff+C) of a (N, voxels, ctot) bf16 buffer: x <- LeakyReLU(x*scale + shift). */
+int bsg_norm_apply_lrelu(void* x_bf16, size_t voxels_per_item, int N, int C, int ctot, int coff,
+                         const float* scale_shift, float slope, void* stream);
+
+/* Fused tail of one tile: 1x1x1 segmentation head (generic_UNet.py:389-391, weights [ncls][32] + optional bias, HOST
+ * pointers), inference_apply_nonlin (0 sigmoid / 1 softmax / 2 identity), un-flip of each mirror's prediction,
+ * result += pred/num_mirrors, result *= gaussian, aggregated_results[:, tile] += result.
+ * feat: bf16 (nmirrors, P0, P1, P2, ctot) with the 32 head inputs in channels [0,32); acc: fp32 [ncls][Z][Y][X]. */
+int bsg_head_tta_accumulate(const void* feat_bf16, int cfeat, int ctot, int P0, int P1, int P2,
+                            const int* mirror_codes_host, int nmirrors, const float* head_w_host,
+                            const float* head_b_host, int ncls, int nonlin, const float* gauss, float* acc, int Z, int Y,
+                            int X, int z0, int y0, int x0, void* stream);
+
+/* class_probabilities = aggregated_results / aggregated_nb_of_predictions; mean over K accumulators (np.mean over
+ * folds, run_brats2021_inference_singlethread.py:128); decision: mode 0 argmax(0) (main_files/run_inference.py:150),
+ * mode 1 ordered threshold `for i,c in enumerate(order): seg[p[i] > 0.5] = c`
+ * (save_segmentation_nifti_from_softmax with region_class_order, run_brats...py:144-156).
+ * acc_list_host: K device pointers (host array); wsum: fp32 [nvox]; probs (fp32 [ncls][nvox]) and seg (u8 [nvox]) may
+ * each be NULL. */
+int bsg_finalize(const float* const* acc_list_host, int K, const float* wsum, int ncls, size_t nvox, int mode,
+                 const int* order_host, float* probs, uint8_t* seg, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -132,7 +132,25 @@ CASES = [
     ("perf_320_320_8_b8", dict(kind=0, N=8, D=8, H=8, W=8, cin=320, cout=320, act=1, time_it=True)),
 ]
 
+def _watchdog(limit_s):
+    """A hung kernel cannot be cancelled from inside the process: bail out hard so the GPU box is not held."""
+    import threading
+
+    state = {"t": time.time(), "name": "startup"}
+
+    def loop():
+        while True:
+            time.sleep(1.0)
+            if time.time() - state["t"] > limit_s:
+                print(f"WATCHDOG: case {state['name']} exceeded {limit_s}s, aborting", flush=True)
+                os._exit(3)
+
+    threading.Thread(target=loop, daemon=True).start()
+    return state
+
+
 if __name__ == "__main__":
+    wd = _watchdog(45)
     L.check(L.lib().bsg_check_device())
     print("SMs", L.lib().bsg_sm_count(), torch.cuda.get_device_name(0), flush=True)
     sel = sys.argv[1:]
@@ -140,6 +158,7 @@ if __name__ == "__main__":
     for name, kw in CASES:
         if sel and not any(s in name for s in sel):
             continue
+        wd["t"], wd["name"] = time.time(), name
         try:
             if not run_case(name, **kw):
                 nfail += 1
