@@ -122,11 +122,14 @@ __global__ void __launch_bounds__(kThreads) norm_apply_kernel(__nv_bfloat16* __r
 }
 
 // ---------------------------------------------------------------------------------------------- head + TTA + accumulate
+constexpr int kMaxHeadCh = 64;
 struct HeadParams {
-    float w[kMaxClasses][32];
+    float w[kMaxClasses][kMaxHeadCh];
     float b[kMaxClasses];
     int ncls;
+    int cfeat;   // feature channels feeding the head (multiple of 8, <= 64)
     int nonlin;  // 0: sigmoid, 1: softmax over classes, 2: identity
+    float mirror_weight;  // 1 / num_results of the full TTA (the mirrors of a tile may be split over launches)
 };
 
 __global__ void __launch_bounds__(kThreads) head_tta_accumulate_kernel(
@@ -136,7 +139,7 @@ __global__ void __launch_bounds__(kThreads) head_tta_accumulate_kernel(
     const size_t pv = static_cast<size_t>(P0) * P1 * P2;
     const size_t plane = static_cast<size_t>(Z) * Y * X;
     const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-    const float inv = 1.0f / static_cast<float>(ms.n);
+    const float inv = hp.mirror_weight;
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < pv; i += stride) {
         size_t r = i;
         const int w = static_cast<int>(r % P2);
@@ -154,26 +157,25 @@ __global__ void __launch_bounds__(kThreads) head_tta_accumulate_kernel(
             const int sd = (code & 4) ? P0 - 1 - d : d;
             const size_t v = ((static_cast<size_t>(m) * P0 + sd) * P1 + sh) * P2 + sw;
             const uint4* fp = reinterpret_cast<const uint4*>(feat + v * ctot);
-            float f[32];
+            float logit[kMaxClasses];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int k = 0; k < kMaxClasses; ++k) logit[k] = hp.b[k];
+            for (int q = 0; q < hp.cfeat / 8; ++q) {
                 const uint4 u = __ldg(fp + q);
                 const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+                float f[8];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&ww[k]);
-                    f[q * 8 + 2 * k] = __bfloat162float(b2.x);
-                    f[q * 8 + 2 * k + 1] = __bfloat162float(b2.y);
+                    f[2 * k] = __bfloat162float(b2.x);
+                    f[2 * k + 1] = __bfloat162float(b2.y);
                 }
-            }
-            float logit[kMaxClasses];
 #pragma unroll
-            for (int k = 0; k < kMaxClasses; ++k) {
-                if (k < hp.ncls) {
-                    float s = hp.b[k];
+                for (int k = 0; k < kMaxClasses; ++k) {
+                    if (k < hp.ncls) {
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) s = fmaf(hp.w[k][c], f[c], s);
-                    logit[k] = s;
+                        for (int c = 0; c < 8; ++c) logit[k] = fmaf(hp.w[k][q * 8 + c], f[c], logit[k]);
+                    }
                 }
             }
             if (hp.nonlin == 0) {
@@ -316,11 +318,13 @@ int bsg_norm_apply_lrelu(void* x_bf16, size_t voxels_per_item, int N, int C, int
 }
 
 int bsg_head_tta_accumulate(const void* feat_bf16, int cfeat, int ctot, int P0, int P1, int P2,
-                            const int* mirror_codes_host, int nmirrors, const float* head_w_host,
-                            const float* head_b_host, int ncls, int nonlin, const float* gauss, float* acc, int Z, int Y,
-                            int X, int z0, int y0, int x0, void* stream) {
+                            const int* mirror_codes_host, int nmirrors, float mirror_weight,
+                            const float* head_w_host, const float* head_b_host, int ncls, int nonlin,
+                            const float* gauss, float* acc, int Z, int Y, int X, int z0, int y0, int x0,
+                            void* stream) {
     BSG_REQUIRE(feat_bf16 != nullptr && head_w_host != nullptr && acc != nullptr, "null argument");
-    BSG_REQUIRE(cfeat == 32, "the fused head expects 32 feature channels (got %d)", cfeat);
+    BSG_REQUIRE(cfeat % 8 == 0 && cfeat >= 8 && cfeat <= kMaxHeadCh, "head input channels %d (8..64, multiple of 8)",
+                cfeat);
     BSG_REQUIRE(ctot % 8 == 0, "ctot must be a multiple of 8");
     BSG_REQUIRE(ncls >= 1 && ncls <= kMaxClasses, "ncls %d (1..%d)", ncls, kMaxClasses);
     BSG_REQUIRE(nonlin >= 0 && nonlin <= 2, "nonlin %d", nonlin);
@@ -332,9 +336,11 @@ int bsg_head_tta_accumulate(const void* feat_bf16, int cfeat, int ctot, int P0, 
     HeadParams hp;
     memset(&hp, 0, sizeof(hp));
     hp.ncls = ncls;
+    hp.cfeat = cfeat;
     hp.nonlin = nonlin;
+    hp.mirror_weight = mirror_weight;
     for (int k = 0; k < ncls; ++k) {
-        for (int c = 0; c < 32; ++c) hp.w[k][c] = head_w_host[k * 32 + c];
+        for (int c = 0; c < cfeat; ++c) hp.w[k][c] = head_w_host[k * cfeat + c];
         hp.b[k] = head_b_host ? head_b_host[k] : 0.f;
     }
     const size_t pv = static_cast<size_t>(P0) * P1 * P2;

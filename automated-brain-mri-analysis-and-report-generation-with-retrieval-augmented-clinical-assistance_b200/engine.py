@@ -1,0 +1,205 @@
+"""B200 execution engine for Generic_UNet: turns the module tree into a fixed sequence of sm_100a kernel launches.
+
+Data layout in HBM: every activation is a channels-last (N, D, H, W, C) bf16 tensor.  The skip connection of level d
+and the transposed-conv output that is concatenated with it (generic_UNet.py:435-438) share one buffer of 2*C
+channels — the encoder conv writes channels [C, 2C), the transposed conv writes [0, C) — so `torch.cat` never runs and
+the first decoder conv reads one tensor.  Eval-mode BatchNorm is folded into the conv weights; InstanceNorm / GroupNorm
+use per-(n, c) sums produced by the conv epilogue and one in-place normalise + LeakyReLU pass.
+"""
+import ctypes as C
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import packing as P
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+class _Act:
+    """A channel slice [coff, coff+c) of a channels-last bf16 buffer (n, d, h, w, ctot)."""
+
+    def __init__(self, buf, coff, c):
+        self.buf, self.coff, self.c = buf, coff, c
+
+    @property
+    def ctot(self):
+        return self.buf.shape[-1]
+
+    @property
+    def spatial(self):
+        return tuple(self.buf.shape[1:4])
+
+    def ptr(self):
+        return self.buf.data_ptr() + 2 * self.coff
+
+    def view(self):
+        return self.buf[..., self.coff:self.coff + self.c]
+
+
+class UNetEngine:
+    def __init__(self, net, patch_size, batch, device=None):
+        if not torch.cuda.is_available():
+            raise L.BsgError("brainseg_b200 needs a CUDA device (sm_100); there is no CPU fallback")
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        with torch.cuda.device(self.device):
+            L.check(L.lib().bsg_check_device())
+        self.net, self.batch, self.patch = net, int(batch), tuple(int(p) for p in patch_size)
+        div = [int(v) for v in net.input_shape_must_be_divisible_by]
+        if any(p % d for p, d in zip(self.patch, div)):
+            raise ValueError(f"patch size {self.patch} must be divisible by {div}")
+        self.steps = []       # callables, in launch order
+        self.keep = []        # tensors the plans point at
+        self.launches_per_forward = 0
+        self.flops = 0.0
+        self._build()
+
+    # ------------------------------------------------------------------ construction
+    def _alloc(self, spatial, c):
+        t = torch.zeros((self.batch,) + tuple(spatial) + (c,), dtype=torch.bfloat16, device=self.device)
+        self.keep.append(t)
+        return t
+
+    def _add_block(self, blk, src, dst, spatial_in):
+        conv, norm = blk.conv, blk.instnorm
+        stride = int(conv.stride[0])
+        w = conv.weight.detach().to(self.device, torch.float32)
+        b = conv.bias.detach().to(self.device, torch.float32) if conv.bias is not None else torch.zeros(
+            w.shape[0], device=self.device)
+        slope = float(blk.lrelu.negative_slope)
+        cout = w.shape[0]
+        stats = None
+        if isinstance(norm, nn.BatchNorm3d):
+            # eval BatchNorm == per-channel affine: fold into the conv (generic_UNet.py:72 with network.eval())
+            scale = norm.weight.detach().to(self.device).float() / torch.sqrt(
+                norm.running_var.detach().to(self.device).float() + norm.eps)
+            w = w * scale.view(-1, 1, 1, 1, 1)
+            b = (b - norm.running_mean.detach().to(self.device).float()) * scale + norm.bias.detach().to(
+                self.device).float()
+            act = L.BSG_ACT_LRELU
+        elif isinstance(norm, (nn.InstanceNorm3d, nn.GroupNorm)):
+            stats = torch.zeros(self.batch, cout, 2, dtype=torch.float32, device=self.device)
+            act = L.BSG_ACT_NONE
+        else:
+            raise NotImplementedError(f"norm {type(norm).__name__}")
+        cin_pad = src.c
+        wp = P.pack_conv3_weight(w, cin_pad)
+        bp = P.pad_bias(b, cout).to(self.device)
+        self.keep += [wp, bp]
+        d, h, wd = spatial_in
+        plan = L.ConvPlan(kind=L.BSG_CONV_K3, stride=stride, N=self.batch, D=d, H=h, W=wd, cin=cin_pad,
+                          in_ptr=src.ptr(), in_ctot=src.ctot, cout=cout, out_ptr=dst.buf.data_ptr(),
+                          out_ctot=dst.ctot, out_coff=dst.coff, weights=wp.data_ptr(), bias=bp.data_ptr(), act=act,
+                          slope=slope, stats=stats.data_ptr() if stats is not None else None, use_khshift=-1,
+                          max_ctas=0)
+        self.flops += plan.info().flops
+        lib = L.lib()
+        if stats is None:
+            self.steps.append(plan.run)
+            self.launches_per_forward += 1
+            return
+        groups = norm.num_groups if isinstance(norm, nn.GroupNorm) else 0
+        gamma = norm.weight.detach().to(self.device).float().contiguous() if norm.weight is not None else None
+        beta = norm.bias.detach().to(self.device).float().contiguous() if norm.bias is not None else None
+        ss = torch.empty(self.batch, cout, 2, dtype=torch.float32, device=self.device)
+        self.keep += [stats, ss, gamma, beta]
+        so = tuple(s // stride for s in spatial_in)
+        vox = so[0] * so[1] * so[2]
+        eps = float(norm.eps)
+        gp = _ptr(gamma) if gamma is not None else None
+        bp2 = _ptr(beta) if beta is not None else None
+
+        def run(stream=None, plan=plan, stats=stats, ss=ss):
+            sp = L.stream_ptr(stream)
+            stats.zero_()
+            plan.run(stream)
+            L.check(lib.bsg_norm_finalize(_ptr(stats), self.batch, cout, groups, float(vox), eps, gp, bp2, _ptr(ss), sp))
+            L.check(lib.bsg_norm_apply_lrelu(_ptr(dst.buf), vox, self.batch, cout, dst.ctot, dst.coff, _ptr(ss), slope,
+                                             sp))
+
+        self.steps.append(run)
+        self.launches_per_forward += 4
+
+    def _add_tu(self, tu, src, dst, spatial_in):
+        w = tu.weight.detach().to(self.device, torch.float32)
+        wp = P.pack_convT2_weight(w, src.c)
+        self.keep.append(wp)
+        d, h, wd = spatial_in
+        plan = L.ConvPlan(kind=L.BSG_CONVT_K2S2, stride=1, N=self.batch, D=d, H=h, W=wd, cin=src.c, in_ptr=src.ptr(),
+                          in_ctot=src.ctot, cout=w.shape[1], out_ptr=dst.buf.data_ptr(), out_ctot=dst.ctot,
+                          out_coff=dst.coff, weights=wp.data_ptr(), bias=None, act=L.BSG_ACT_NONE, slope=0.0,
+                          stats=None, use_khshift=0, max_ctas=0)
+        self.flops += plan.info().flops
+        self.steps.append(plan.run)
+        self.launches_per_forward += 1
+
+    def _build(self):
+        net = self.net
+        num_pool = len(net.tu)
+        in_ch = net.conv_blocks_context[0].blocks[0].conv.in_channels
+        self.in_channels = in_ch
+        self.cin_pad = P.round_up(in_ch, 16)
+        self.x = _Act(self._alloc(self.patch, self.cin_pad), 0, self.cin_pad)
+        cur, spatial = self.x, self.patch
+        cats = []
+        for d in range(num_pool + 1):
+            stage = net.conv_blocks_context[d]
+            blocks = list(stage.blocks) if d < num_pool else list(stage[0].blocks) + list(stage[1].blocks)
+            for i, blk in enumerate(blocks):
+                cout, stride = blk.conv.out_channels, int(blk.conv.stride[0])
+                if cout % 16:
+                    raise NotImplementedError(f"channel width {cout} is not a multiple of 16")
+                out_spatial = tuple(s // stride for s in spatial)
+                if d < num_pool and i == len(blocks) - 1:
+                    cat = self._alloc(out_spatial, 2 * cout)  # [0,C): transposed-conv output, [C,2C): this skip
+                    cats.append(cat)
+                    dst = _Act(cat, cout, cout)
+                else:
+                    dst = _Act(self._alloc(out_spatial, cout), 0, cout)
+                self._add_block(blk, cur, dst, spatial)
+                cur, spatial = dst, out_spatial
+        for u in range(num_pool):
+            cat = cats[-(u + 1)]
+            cskip = cat.shape[-1] // 2
+            tu = net.tu[u]
+            if tu.out_channels != cskip:
+                raise NotImplementedError("transposed conv width differs from the skip width")
+            self._add_tu(tu, cur, _Act(cat, 0, cskip), spatial)
+            spatial = tuple(2 * s for s in spatial)
+            cur = _Act(cat, 0, 2 * cskip)
+            loc = net.conv_blocks_localization[u]
+            for blk in list(loc[0].blocks) + list(loc[1].blocks):
+                dst = _Act(self._alloc(spatial, blk.conv.out_channels), 0, blk.conv.out_channels)
+                self._add_block(blk, cur, dst, spatial)
+                cur = dst
+        self.features = cur
+        head = net.seg_outputs[num_pool - 1]
+        self.head_w = head.weight.detach().float().reshape(head.out_channels, -1).cpu().contiguous()
+        self.head_b = head.bias.detach().float().cpu().contiguous() if head.bias is not None else None
+        self.num_classes = head.out_channels
+        self.flops_per_item = self.flops / self.batch + 2.0 * self.num_classes * self.head_w.shape[1] * (
+            self.patch[0] * self.patch[1] * self.patch[2])
+
+    # ------------------------------------------------------------------ execution
+    def run(self, stream=None):
+        """All conv / norm launches of one forward over the resident input batch `self.x`."""
+        for step in self.steps:
+            step(stream)
+
+    def forward_logits(self, x):
+        """(n <= batch, C, D, H, W) float tensor -> (n, num_classes, D, H, W) fp32 logits (head in torch: this
+        convenience path backs `Generic_UNet.forward`; predict_3D uses the fused head kernel instead)."""
+        n = x.shape[0]
+        if n > self.batch or tuple(x.shape[2:]) != self.patch:
+            raise ValueError("input does not match the engine geometry")
+        self.x.buf.zero_()
+        self.x.buf[:n, ..., :self.in_channels] = x.to(self.device).permute(0, 2, 3, 4, 1).to(torch.bfloat16)
+        self.run()
+        f = self.features.view()[:n].float()  # (n, d, h, w, c)
+        logits = torch.einsum("ndhwc,kc->nkdhw", f, self.head_w.to(self.device))
+        if self.head_b is not None:
+            logits = logits + self.head_b.to(self.device).view(1, -1, 1, 1, 1)
+        return logits

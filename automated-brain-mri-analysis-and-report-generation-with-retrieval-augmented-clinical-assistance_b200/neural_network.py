@@ -1,0 +1,104 @@
+"""Drop-in for nnU-Net v1 `SegmentationNetwork` (UPSTREAM nnunet/network_architecture/neural_network.py; the base
+class of the reference's Generic_UNet, model_architecture/generic_UNet.py:22,171): `predict_3D` with the upstream
+signature and return convention, executed by the sm_100a engine.
+"""
+import numpy as np
+import torch
+from torch import nn
+
+from . import sliding
+
+
+class SegmentationNetwork(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.input_shape_must_be_divisible_by = None
+        self.conv_op = None
+        self.num_classes = None
+        self.inference_apply_nonlin = lambda x: x  # upstream default; trainers install sigmoid / softmax_helper
+        self._engines = {}
+        self.engine_batch = 8
+
+    # ------------------------------------------------------------------ engine cache
+    def engine_for(self, patch_size, batch=None):
+        from .engine import UNetEngine
+        batch = int(batch or self.engine_batch)
+        key = (tuple(int(p) for p in patch_size), batch, torch.cuda.current_device())
+        if key not in self._engines:
+            self._engines[key] = UNetEngine(self, key[0], batch)
+        return self._engines[key]
+
+    def invalidate_engines(self):
+        """Call after loading new weights (load_state_dict / load_checkpoint_ram): packed weights are cached."""
+        self._engines = {}
+
+    def load_state_dict(self, *a, **k):
+        self.invalidate_engines()
+        return super().load_state_dict(*a, **k)
+
+    def _nonlin_name(self):
+        f = self.inference_apply_nonlin
+        if isinstance(f, nn.Sigmoid):
+            return "sigmoid"
+        if isinstance(f, nn.Softmax) or getattr(f, "__name__", "") == "softmax_helper":
+            return "softmax"
+        probe = torch.tensor([[0.5, -1.0]])
+        if torch.equal(f(probe), probe):
+            return "identity"
+        if torch.allclose(f(probe), torch.sigmoid(probe)):
+            return "sigmoid"
+        if torch.allclose(f(probe), torch.softmax(probe, 1)):
+            return "softmax"
+        raise NotImplementedError("inference_apply_nonlin must be sigmoid, softmax over dim 1 or identity")
+
+    # ------------------------------------------------------------------ upstream API
+    def predict_3D(self, x, do_mirroring, mirror_axes=(0, 1, 2), use_sliding_window=False, step_size=0.5,
+                   patch_size=None, regions_class_order=None, use_gaussian=False, pad_border_mode="constant",
+                   pad_kwargs=None, all_in_gpu=False, verbose=True, mixed_precision=True):
+        """x: (c, z, y, x) float array.  Returns (seg, class_probabilities) as numpy arrays like upstream:
+        seg (z, y, x) — argmax int64, or float32 region labels when `regions_class_order` is given;
+        class_probabilities float32 (num_classes, z, y, x)."""
+        assert step_size <= 1, "step_size must be smaller than 1. Otherwise there will be a gap between consecutive predictions"
+        if pad_border_mode != "constant" or (pad_kwargs not in (None, {"constant_values": 0})):
+            raise NotImplementedError("only constant zero padding (the nnU-Net default used by the reference)")
+        if len(mirror_axes) and max(mirror_axes) > 2:
+            raise ValueError("mirror axes. duh")
+        x = np.asarray(x) if not torch.is_tensor(x) else x
+        assert len(x.shape) == 4, "data must have shape (c,x,y,z)"
+        if not use_sliding_window:
+            raise NotImplementedError("the reference always predicts with use_sliding_window=True")
+        assert patch_size is not None, "patch_size cannot be None for tiled prediction"
+        seg, probs = self.predict_3D_device(x, do_mirroring, mirror_axes, step_size, patch_size, regions_class_order,
+                                            use_gaussian)
+        seg = seg.cpu().numpy()
+        seg = seg.astype(np.float32) if regions_class_order is not None else seg.astype(np.int64)
+        return seg, probs.cpu().numpy()
+
+    def predict_3D_device(self, x, do_mirroring=True, mirror_axes=(0, 1, 2), step_size=0.5, patch_size=None,
+                          regions_class_order=None, use_gaussian=True, want_probs=True):
+        """predict_3D without the final device->host copies: returns (uint8 seg, fp32 probs) cuda tensors."""
+        dev = torch.device("cuda", torch.cuda.current_device())
+        vol = (torch.from_numpy(np.ascontiguousarray(x)) if not torch.is_tensor(x) else x).to(dev, torch.float32)
+        patch = tuple(int(p) for p in patch_size)
+        # pad_nd_image(x, patch, 'constant', 0): symmetric zero pad up to the patch size, floor on the low side
+        shape = tuple(vol.shape[1:])
+        new = [max(s, p) for s, p in zip(shape, patch)]
+        pads, lo = [], []
+        for s, n in zip(shape, new):
+            lo.append((n - s) // 2)
+            pads.append(((n - s) // 2, (n - s) // 2 + (n - s) % 2))
+        if any(a or b for a, b in pads):
+            vol = torch.nn.functional.pad(vol, (pads[2][0], pads[2][1], pads[1][0], pads[1][1], pads[0][0], pads[0][1]))
+        vol = vol.contiguous()
+        codes = sliding.mirror_codes_for(mirror_axes, do_mirroring)
+        pred = sliding.SlidingWindowPredictor(self.engine_for(patch), step_size, use_gaussian, codes,
+                                              self._nonlin_name())
+        acc = pred.accumulate(vol)
+        seg, probs = pred.finalize([acc], tuple(vol.shape[1:]), regions_class_order, want_probs)
+        if tuple(vol.shape[1:]) != shape:  # crop back with the slicer pad_nd_image returned
+            sl = tuple(slice(l, l + s) for l, s in zip(lo, shape))
+            seg = seg[sl].contiguous()
+            if probs is not None:
+                probs = probs[(slice(None),) + sl].contiguous()
+        self.last_kernel_launches = pred.kernel_launches
+        return seg, probs

@@ -166,14 +166,17 @@ int bsg_norm_finalize(const float* stats, int N, int C, int groups, double count
 int bsg_norm_apply_lrelu(void* x_bf16, size_t voxels_per_item, int N, int C, int ctot, int coff,
                          const float* scale_shift, float slope, void* stream);
 
-/* Fused tail of one tile: 1x1x1 segmentation head (generic_UNet.py:389-391, weights [ncls][32] + optional bias, HOST
- * pointers), inference_apply_nonlin (0 sigmoid / 1 softmax / 2 identity), un-flip of each mirror's prediction,
- * result += pred/num_mirrors, result *= gaussian, aggregated_results[:, tile] += result.
- * feat: bf16 (nmirrors, P0, P1, P2, ctot) with the 32 head inputs in channels [0,32); acc: fp32 [ncls][Z][Y][X]. */
+/* Fused tail of one tile: 1x1x1 segmentation head (generic_UNet.py:389-391, weights [ncls][cfeat] + optional bias,
+ * HOST pointers), inference_apply_nonlin (0 sigmoid / 1 softmax / 2 identity), un-flip of each mirror's prediction,
+ * result += mirror_weight * pred (mirror_weight = 1/num_results of the whole TTA), result *= gaussian,
+ * aggregated_results[:, tile] += result.
+ * feat: bf16 (nmirrors, P0, P1, P2, ctot) with the cfeat head inputs in channels [0,cfeat) (cfeat % 8 == 0, <= 64);
+ * acc: fp32 [ncls][Z][Y][X]; gauss: fp32 [P0][P1][P2] or NULL. */
 int bsg_head_tta_accumulate(const void* feat_bf16, int cfeat, int ctot, int P0, int P1, int P2,
-                            const int* mirror_codes_host, int nmirrors, const float* head_w_host,
-                            const float* head_b_host, int ncls, int nonlin, const float* gauss, float* acc, int Z, int Y,
-                            int X, int z0, int y0, int x0, void* stream);
+                            const int* mirror_codes_host, int nmirrors, float mirror_weight,
+                            const float* head_w_host, const float* head_b_host, int ncls, int nonlin,
+                            const float* gauss, float* acc, int Z, int Y, int X, int z0, int y0, int x0,
+                            void* stream);
 
 /* class_probabilities = aggregated_results / aggregated_nb_of_predictions; mean over K accumulators (np.mean over
  * folds, run_brats2021_inference_singlethread.py:128); decision: mode 0 argmax(0) (main_files/run_inference.py:150),
