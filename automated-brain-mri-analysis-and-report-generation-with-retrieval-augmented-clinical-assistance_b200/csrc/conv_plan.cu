@@ -232,6 +232,7 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
     a.slope = d->slope;
     a.act = d->act;
     a.stats = d->stats;
+    a.out_f16 = d->out_f16;
 
     const int total_tiles = a.tn * a.td * a.th * a.tw * a.n_ntiles;
     int max_ctas = d->max_ctas > 0 ? d->max_ctas : sm_count_cached();

@@ -4,6 +4,7 @@
 //   warp 0      TMA producer   (activation halo boxes + weight slabs -> swizzled smem ring)
 //   warp 1      MMA issuer     (one elected lane, tcgen05.mma kind::f16, fp32 accumulators in TMEM, 2 buffers)
 //   warps 2..5  epilogue       (tcgen05.ld -> bias / LeakyReLU / norm statistics -> bf16 channels-last stores)
+#include <cuda_fp16.h>
 #include "bsg_ptx.cuh"
 #include "conv_tc.cuh"
 
@@ -250,21 +251,37 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                         uint4* dst = reinterpret_cast<uint4*>(orow + co);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            __nv_bfloat162 p0 = __floats2bfloat162_rn(f[8 * i + 0], f[8 * i + 1]);
-                            __nv_bfloat162 p1 = __floats2bfloat162_rn(f[8 * i + 2], f[8 * i + 3]);
-                            __nv_bfloat162 p2 = __floats2bfloat162_rn(f[8 * i + 4], f[8 * i + 5]);
-                            __nv_bfloat162 p3 = __floats2bfloat162_rn(f[8 * i + 6], f[8 * i + 7]);
                             uint4 u;
-                            u.x = *reinterpret_cast<uint32_t*>(&p0);
-                            u.y = *reinterpret_cast<uint32_t*>(&p1);
-                            u.z = *reinterpret_cast<uint32_t*>(&p2);
-                            u.w = *reinterpret_cast<uint32_t*>(&p3);
+                            if (a.out_f16) {
+                                __half2 p0 = __floats2half2_rn(f[8 * i + 0], f[8 * i + 1]);
+                                __half2 p1 = __floats2half2_rn(f[8 * i + 2], f[8 * i + 3]);
+                                __half2 p2 = __floats2half2_rn(f[8 * i + 4], f[8 * i + 5]);
+                                __half2 p3 = __floats2half2_rn(f[8 * i + 6], f[8 * i + 7]);
+                                u.x = *reinterpret_cast<uint32_t*>(&p0);
+                                u.y = *reinterpret_cast<uint32_t*>(&p1);
+                                u.z = *reinterpret_cast<uint32_t*>(&p2);
+                                u.w = *reinterpret_cast<uint32_t*>(&p3);
+                            } else {
+                                __nv_bfloat162 p0 = __floats2bfloat162_rn(f[8 * i + 0], f[8 * i + 1]);
+                                __nv_bfloat162 p1 = __floats2bfloat162_rn(f[8 * i + 2], f[8 * i + 3]);
+                                __nv_bfloat162 p2 = __floats2bfloat162_rn(f[8 * i + 4], f[8 * i + 5]);
+                                __nv_bfloat162 p3 = __floats2bfloat162_rn(f[8 * i + 6], f[8 * i + 7]);
+                                u.x = *reinterpret_cast<uint32_t*>(&p0);
+                                u.y = *reinterpret_cast<uint32_t*>(&p1);
+                                u.z = *reinterpret_cast<uint32_t*>(&p2);
+                                u.w = *reinterpret_cast<uint32_t*>(&p3);
+                            }
                             dst[i] = u;
                         }
                     } else {
 #pragma unroll
                         for (int i = 0; i < 32; ++i)
-                            if (co + i < a.cout) orow[co + i] = __float2bfloat16_rn(f[i]);
+                            if (co + i < a.cout) {
+                                if (a.out_f16)
+                                    reinterpret_cast<__half*>(orow)[co + i] = __float2half_rn(f[i]);
+                                else
+                                    orow[co + i] = __float2bfloat16_rn(f[i]);
+                            }
                     }
                 }
             }

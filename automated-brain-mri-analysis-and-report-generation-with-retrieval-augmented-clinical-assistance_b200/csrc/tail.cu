@@ -7,6 +7,7 @@
 //                         accumulate into the full-volume fp32 accumulator
 //   finalize              / weight-sum, mean over folds, ordered-threshold or argmax decision -> uint8 labels
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "bsg_common.cuh"
 
 namespace bsg {
@@ -94,7 +95,8 @@ __global__ void norm_finalize_kernel(const float* __restrict__ stats, int N, int
 // in place on a channel slice [coff, coff+C) of a (N, V, ctot) bf16 buffer: x <- lrelu(x*scale + shift)
 __global__ void __launch_bounds__(kThreads) norm_apply_kernel(__nv_bfloat16* __restrict__ x, size_t V, int N, int C,
                                                               int ctot, int coff,
-                                                              const float* __restrict__ scale_shift, float slope) {
+                                                              const float* __restrict__ scale_shift, float slope,
+                                                              int in_f16) {
     const int c8n = C / 8;
     const size_t total = static_cast<size_t>(N) * V * c8n;
     const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
@@ -109,9 +111,18 @@ __global__ void __launch_bounds__(kThreads) norm_apply_kernel(__nv_bfloat16* __r
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const float4 s = __ldg(ss + k);  // (scale0, shift0, scale1, shift1)
-            __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&w[k]);
-            float a = __bfloat162float(v.x) * s.x + s.y;
-            float b = __bfloat162float(v.y) * s.z + s.w;
+            float a, b;
+            if (in_f16) {
+                const float2 v = __half22float2(*reinterpret_cast<__half2*>(&w[k]));
+                a = v.x;
+                b = v.y;
+            } else {
+                const __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&w[k]);
+                a = __bfloat162float(v.x);
+                b = __bfloat162float(v.y);
+            }
+            a = a * s.x + s.y;
+            b = b * s.z + s.w;
             a = a > 0.f ? a : a * slope;
             b = b > 0.f ? b : b * slope;
             __nv_bfloat162 o = __floats2bfloat162_rn(a, b);
@@ -307,12 +318,12 @@ int bsg_norm_finalize(const float* stats, int N, int C, int groups, double count
 }
 
 int bsg_norm_apply_lrelu(void* x_bf16, size_t voxels_per_item, int N, int C, int ctot, int coff,
-                         const float* scale_shift, float slope, void* stream) {
+                         const float* scale_shift, float slope, int in_f16, void* stream) {
     BSG_REQUIRE(x_bf16 != nullptr && scale_shift != nullptr, "null argument");
     BSG_REQUIRE(C % 8 == 0 && ctot % 8 == 0 && coff % 8 == 0, "channel counts must be multiples of 8");
     const size_t total = static_cast<size_t>(N) * voxels_per_item * (C / 8);
     norm_apply_kernel<<<grid_for(total, kThreads, 16), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<__nv_bfloat16*>(x_bf16), voxels_per_item, N, C, ctot, coff, scale_shift, slope);
+        static_cast<__nv_bfloat16*>(x_bf16), voxels_per_item, N, C, ctot, coff, scale_shift, slope, in_f16);
     BSG_CUDA_OK(cudaGetLastError());
     return BSG_OK;
 }

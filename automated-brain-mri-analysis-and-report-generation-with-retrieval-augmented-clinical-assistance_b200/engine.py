@@ -55,6 +55,7 @@ class UNetEngine:
         self.keep = []        # tensors the plans point at
         self.launches_per_forward = 0
         self.flops = 0.0
+        self.event_log = None  # bench.py: list collecting (start, end) CUDA events around each run()
         self._build()
 
     # ------------------------------------------------------------------ construction
@@ -93,7 +94,8 @@ class UNetEngine:
         plan = L.ConvPlan(kind=L.BSG_CONV_K3, stride=stride, N=self.batch, D=d, H=h, W=wd, cin=cin_pad,
                           in_ptr=src.ptr(), in_ctot=src.ctot, cout=cout, out_ptr=dst.buf.data_ptr(),
                           out_ctot=dst.ctot, out_coff=dst.coff, weights=wp.data_ptr(), bias=bp.data_ptr(), act=act,
-                          slope=slope, stats=stats.data_ptr() if stats is not None else None, use_khshift=-1,
+                          slope=slope, stats=stats.data_ptr() if stats is not None else None,
+                          out_f16=1 if stats is not None else 0, use_khshift=-1,
                           max_ctas=0)
         self.flops += plan.info().flops
         lib = L.lib()
@@ -117,7 +119,7 @@ class UNetEngine:
             stats.zero_()
             plan.run(stream)
             L.check(lib.bsg_norm_finalize(_ptr(stats), self.batch, cout, groups, float(vox), eps, gp, bp2, _ptr(ss), sp))
-            L.check(lib.bsg_norm_apply_lrelu(_ptr(dst.buf), vox, self.batch, cout, dst.ctot, dst.coff, _ptr(ss), slope,
+            L.check(lib.bsg_norm_apply_lrelu(_ptr(dst.buf), vox, self.batch, cout, dst.ctot, dst.coff, _ptr(ss), slope, 1,
                                              sp))
 
         self.steps.append(run)
@@ -186,8 +188,17 @@ class UNetEngine:
     # ------------------------------------------------------------------ execution
     def run(self, stream=None):
         """All conv / norm launches of one forward over the resident input batch `self.x`."""
+        if self.event_log is None:
+            for step in self.steps:
+                step(stream)
+            return
+        s = stream if stream is not None else torch.cuda.current_stream()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s)
         for step in self.steps:
             step(stream)
+        e1.record(s)
+        self.event_log.append((e0, e1))
 
     def forward_logits(self, x):
         """(n <= batch, C, D, H, W) float tensor -> (n, num_classes, D, H, W) fp32 logits (head in torch: this

@@ -1,0 +1,86 @@
+"""In-memory case pipeline: the hot path of run_brats2021_inference_singlethread.main (:246-322) and the voxel steps
+of run_full_pipeline.py that consume its output (convert_labels :198, evaluate :226, feature extraction :274), with
+the label volume staying on the device between stages.
+
+    model 1 -> probs -> regions (1,2,3) -> seg1        predict_case_single_threaded :81-158
+    model 2 -> probs -> regions (1,2,3) -> seg2
+    ensemble = np.round((seg1 + seg2) / 2)              main :305
+    brats    = convert_labels_to_brats2025(ensemble)    convert_labels_to_brats.py:34-43 (pipeline default format)
+    Dice vs GT, connected components, morphology        evaluate_segmentation.py, feature_extraction/step3, step4
+"""
+import numpy as np
+import torch
+
+from . import sliding
+from . import voxelops as V
+from . import convert_labels_to_brats as CL
+from . import evaluate_segmentation as EV
+from .feature_extraction import step3_multiplicity as S3
+from .feature_extraction import step4_morphology as S4
+from .feature_extraction import utils as FU
+
+
+class BratsCasePipeline:
+    def __init__(self, models, patch_size=(128, 128, 128), step_size=0.5, mirror_axes=(0, 1, 2), do_mirroring=True,
+                 use_gaussian=True, regions_class_order=(1, 2, 3), label_format="brats2025", batch=8, rank=0,
+                 world_size=1, reduce_fn=None):
+        """models: drop-in Generic_UNet instances (each may stand for one fold); `reduce_fn(acc)` sums an accumulator
+        over ranks when the (tile, mirror) work items of ONE case are sharded (latency mode)."""
+        self.models = list(models)
+        self.patch = tuple(patch_size)
+        self.regions = regions_class_order
+        self.lut = CL.LUT_BRATS2025 if label_format == "brats2025" else CL.LUT_BRATS2021
+        self.reduce_fn = reduce_fn
+        codes = sliding.mirror_codes_for(mirror_axes, do_mirroring)
+        self.predictors = []
+        for net in self.models:
+            eng = net.engine_for(self.patch, batch)
+            self.predictors.append(sliding.SlidingWindowPredictor(eng, step_size, use_gaussian, codes,
+                                                                  net._nonlin_name(), rank, world_size))
+        self.device = self.predictors[0].device
+        self.conv_events = None  # optional: list collecting (start, end, flops) CUDA-event triples per engine run
+
+    def kernel_launches(self):
+        return sum(p.kernel_launches for p in self.predictors)
+
+    def segment(self, vol):
+        """vol: fp32 cuda tensor (C, Z, Y, X), extents >= patch.  Returns the per-model uint8 label volumes."""
+        shape = tuple(vol.shape[1:])
+        segs = []
+        for pred in self.predictors:
+            acc = pred.accumulate(vol)
+            if self.reduce_fn is not None:
+                acc = self.reduce_fn(acc)
+            seg, _ = pred.finalize([acc], shape, self.regions, want_probs=False)
+            segs.append(seg)
+        return segs
+
+    def run_case(self, volume, gt=None, voxel_dims=(1.0, 1.0, 1.0), features=True):
+        """volume: (C, Z, Y, X) float32, host (numpy / pinned tensor) or device.  Returns a dict with the ensemble
+        label volume in BraTS convention (device uint8) and the scalar results of the post-processing steps."""
+        if isinstance(volume, np.ndarray):
+            volume = torch.from_numpy(volume)
+        vol = volume.to(self.device, torch.float32, non_blocking=True).contiguous()
+        segs = self.segment(vol)
+        if len(segs) == 1:
+            brats = V.label_lut(segs[0], self.lut)
+        elif len(segs) == 2:
+            brats = V.ensemble_round(segs[0], segs[1], post_lut=self.lut)  # ensemble + remap in one pass
+        else:
+            raise NotImplementedError("the reference ensembles exactly two models")
+        out = {"segmentation": brats, "model_segmentations": segs}
+        self.extra_launches = 1
+        if gt is not None:
+            out["evaluation"] = EV.evaluate_arrays(brats, gt)
+            self.extra_launches += 1
+        if features:
+            lv = FU.LabelVolume(brats)
+            masks = FU.get_tumor_masks(lv)
+            out["components"] = S3.detect_connected_components(lv, voxel_dims)
+            out["enhancing"] = S3.analyze_enhancing_components(lv, voxel_dims)
+            out["shape"] = S4.calculate_shape_descriptors(lv, masks, voxel_dims)
+            out["necrosis"] = S4.analyze_necrosis_pattern(lv, masks, np.array(voxel_dims))
+            vv = float(np.prod(voxel_dims)) / 1000.0
+            out["volumes_cm3"] = {k: FU.calculate_volume(masks[k], vv) for k in ("ncr", "ed", "et", "tc", "wt")}
+            self.extra_launches += 2 * 8 + 2
+        return out

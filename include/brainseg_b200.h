@@ -67,6 +67,8 @@ typedef struct bsg_conv_desc {
     float slope;         /* LeakyReLU negative slope (generic_UNet.py:39) */
     float* stats;        /* fp32 [N][cout][2] += (sum, sum of squares) of the pre-activation output, or NULL;
                             feeds InstanceNorm / GroupNorm (generic_UNet.py:62-65) */
+    int out_f16;         /* 1: store the output as IEEE fp16 instead of bf16 (raw pre-norm values that
+                            bsg_norm_apply_lrelu then rewrites in place as bf16) */
     int use_khshift;     /* -1 auto, 0 off, 1 on: halo reuse of the h taps inside shared memory */
     int max_ctas;        /* 0 = one CTA per SM */
 } bsg_conv_desc;
@@ -162,9 +164,10 @@ int bsg_gather_patch_tta(const float* vol, int C, int Z, int Y, int X, int z0, i
  * y = x*scale + shift == (x-mean)*rsqrt(var+eps)*gamma + beta.  groups = 0: per channel; > 0: GroupNorm. */
 int bsg_norm_finalize(const float* stats, int N, int C, int groups, double count, float eps, const float* gamma,
                       const float* beta, float* scale_shift, void* stream);
-/* In place on channels [coff, coff+C) of a (N, voxels, ctot) bf16 buffer: x <- LeakyReLU(x*scale + shift). */
-int bsg_norm_apply_lrelu(void* x_bf16, size_t voxels_per_item, int N, int C, int ctot, int coff,
-                         const float* scale_shift, float slope, void* stream);
+/* In place on channels [coff, coff+C) of a (N, voxels, ctot) 16-bit buffer: x <- bf16(LeakyReLU(x*scale + shift));
+ * in_f16 = 1 when the conv stored its raw output as fp16 (bsg_conv_desc.out_f16). */
+int bsg_norm_apply_lrelu(void* x, size_t voxels_per_item, int N, int C, int ctot, int coff,
+                         const float* scale_shift, float slope, int in_f16, void* stream);
 
 /* Fused tail of one tile: 1x1x1 segmentation head (generic_UNet.py:389-391, weights [ncls][cfeat] + optional bias,
  * HOST pointers), inference_apply_nonlin (0 sigmoid / 1 softmax / 2 identity), un-flip of each mirror's prediction,
