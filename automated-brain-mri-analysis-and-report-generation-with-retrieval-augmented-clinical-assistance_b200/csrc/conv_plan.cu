@@ -141,6 +141,10 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
     // N tiling
     a.cout = d->cout;
     a.cout_pad = static_cast<int>(round_up(d->cout, 32));
+    if (a.cout_pad > 512) {
+        delete p;
+        return set_error(BSG_EINVAL, "cout %d > 512 not supported", d->cout);
+    }
     int split = 1;
     while (a.cout_pad / split > 256 || a.cout_pad % split != 0 || (a.cout_pad / split) % 32 != 0) {
         ++split;
@@ -156,7 +160,7 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
     while (a.tmem_cols < static_cast<uint32_t>(2 * a.ntile)) a.tmem_cols *= 2;
 
     // kh halo reuse: needs the canonical 8 x 16 x 1 x 1 box, stride 1, 27 taps and >= 3 pipeline stages
-    const uint32_t budget = 227 * 1024 - 2048;
+    const uint32_t budget = 227 * 1024 - 4096;  // barriers + bias + alignment slack
     auto stage_bytes = [&](int khs, uint32_t* ab, uint32_t* bb) {
         const uint32_t rows = khs ? static_cast<uint32_t>((a.bh + 2) * 8) : 128u;
         *ab = round_up(rows * a.cc * 2, 1024);

@@ -37,6 +37,8 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvArgs& a, int tile) {
     return t;
 }
 
+// CC: channels per K chunk (16/32/64 <-> swizzle 32/64/128 B); KHS: kh halo reuse (3 kh taps per stage).
+template <int CC, bool KHS>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-B aligned carve-up (swizzle-128B atoms need it)
@@ -48,6 +50,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     uint64_t* tfull_bar = empty_bar + kMaxStages;  // [2]
     uint64_t* tempty_bar = tfull_bar + 2;          // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* sbias = reinterpret_cast<float*>(bar_area + 1024);  // [cout_pad] (<= 512), zeros when there is no bias
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -69,46 +72,44 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         tmem_alloc(tmem_slot, a.tmem_cols);
         tmem_relinquish();
     }
+    if (warp >= 2) {
+        for (int i = threadIdx.x - 64; i < a.cout_pad; i += kThreads - 64)
+            sbias[i] = (a.bias != nullptr) ? a.bias[i] : 0.f;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     const int total_tiles = a.tn * a.td * a.th * a.tw * a.n_ntiles;
-    const int ntg = a.khshift ? 9 : a.ntaps;  // pipeline steps per chunk: (kd,kw) pairs or single taps
+    const int ntg = KHS ? 9 : a.ntaps;  // pipeline steps per chunk: (kd,kw) pairs or single taps
     const int ksteps = ntg * a.nchunks;
-    const int nkh = a.khshift ? 3 : 1;
-    const uint32_t row_bytes = static_cast<uint32_t>(a.cc) * 2u;
-    const uint32_t sbo = 8u * row_bytes;
+    constexpr int NKH = KHS ? 3 : 1;
+    constexpr uint32_t kRowBytes = CC * 2u;
+    constexpr uint32_t kSbo = 8u * kRowBytes;
+    const int nstages = a.nstages;
 
     if (warp == 0) {
         // =========================================================== TMA producer
         if (elect_one()) {
-            uint32_t it = 0;
+            int stage = 0;
+            uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const TileCoord t = decode_tile(a, tile);
                 const int nrow0 = t.nt * a.ntile;
+                int kd = 0, kw = 0, kh = 0;  // tap order (kd, kw, kh): kh fastest, absent when KHS
                 for (int tg = 0; tg < ntg; ++tg) {
-                    int kd, kw, kh, tap;
+                    int cw, ch, cd, mi = 0, tap;
                     if (a.ntaps == 1) {
-                        kd = kw = kh = 1;
+                        cw = t.w0;
+                        ch = t.h0;
+                        cd = t.d0;
                         tap = 0;
-                    } else if (a.khshift) {
-                        kd = tg / 3;
-                        kw = tg % 3;
-                        kh = 0;
-                        tap = tg * 3;
-                    } else {
-                        kd = tg / 9;
-                        kw = (tg / 3) % 3;
-                        kh = tg % 3;
-                        tap = tg;
-                    }
-                    int cw, ch, cd, mi = 0;
-                    if (a.stride == 1) {
+                    } else if (a.stride == 1) {
                         cw = t.w0 + kw - 1;
                         ch = t.h0 + kh - 1;
                         cd = t.d0 + kd - 1;
+                        tap = KHS ? tg * 3 : tg;
                     } else {
                         // input index 2*o + k - 1: k=0 -> odd parity, o-1; k=1 -> even parity, o; k=2 -> odd parity, o
                         const int pw = (kw + 1) & 1, ph = (kh + 1) & 1, pd = (kd + 1) & 1;
@@ -116,16 +117,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                         cw = t.w0 - (kw == 0);
                         ch = t.h0 - (kh == 0);
                         cd = t.d0 - (kd == 0);
+                        tap = tg;
                     }
-                    for (int c = 0; c < a.nchunks; ++c, ++it) {
-                        const int s = it % a.nstages;
-                        const uint32_t ph_bit = (it / a.nstages) & 1u;
-                        mbar_wait(&empty_bar[s], ph_bit ^ 1u);
-                        uint8_t* sa = smem + static_cast<size_t>(s) * stage_bytes;
+                    const CUtensorMap* mapA = &a.mapA[mi];
+                    for (int c = 0; c < a.nchunks; ++c) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1u);
+                        uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
                         uint8_t* sb = sa + a.a_stage_bytes;
-                        mbar_expect_tx(&full_bar[s], a.stage_tx_bytes);
-                        tma_load_5d(sa, &a.mapA[mi], &full_bar[s], c * a.cc, cw, ch, cd, t.n0);
-                        tma_load_3d(sb, &a.mapW, &full_bar[s], c * a.cc, nrow0, tap);
+                        mbar_expect_tx(&full_bar[stage], a.stage_tx_bytes);
+                        tma_load_5d(sa, mapA, &full_bar[stage], c * CC, cw, ch, cd, t.n0);
+                        tma_load_3d(sb, &a.mapW, &full_bar[stage], c * CC, nrow0, tap);
+                        if (++stage == nstages) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                    if (KHS) {
+                        if (++kw == 3) {
+                            kw = 0;
+                            ++kd;
+                        }
+                    } else if (++kh == 3) {
+                        kh = 0;
+                        if (++kw == 3) {
+                            kw = 0;
+                            ++kd;
+                        }
                     }
                 }
             }
@@ -133,10 +150,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     } else if (warp == 1) {
         // =========================================================== MMA issuer
         const uint32_t idesc = make_idesc_bf16(128, static_cast<uint32_t>(a.ntile));
-        const uint32_t layout = (a.cc == 64) ? kLayoutSW128 : (a.cc == 32 ? kLayoutSW64 : kLayoutSW32);
-        const uint32_t b_tap_bytes = static_cast<uint32_t>(a.ntile) * row_bytes;
-        const int k16s = a.cc / 16;
-        uint32_t it = 0;
+        constexpr uint32_t kLayout = (CC == 64) ? kLayoutSW128 : (CC == 32 ? kLayoutSW64 : kLayoutSW32);
+        // descriptor = constant high word | (start address >> 4): only the low word moves between MMAs
+        const uint64_t desc_base = make_smem_desc(0, kSbo, kLayout);
+        const uint32_t b_tap16 = (static_cast<uint32_t>(a.ntile) * kRowBytes) >> 4;
+        const uint32_t smem0_16 = smem_u32(smem) >> 4;
+        const uint32_t stage16 = stage_bytes >> 4, a16 = a.a_stage_bytes >> 4;
+        int stage = 0;
+        uint32_t phase = 0;
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
             const uint32_t acc = tcount & 1u;
@@ -144,25 +165,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * static_cast<uint32_t>(a.ntile);
-            for (int ks = 0; ks < ksteps; ++ks, ++it) {
-                const int s = it % a.nstages;
-                const uint32_t ph_bit = (it / a.nstages) & 1u;
-                mbar_wait(&full_bar[s], ph_bit);
+            for (int ks = 0; ks < ksteps; ++ks) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t sa = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
-                    const uint32_t sb = sa + a.a_stage_bytes;
-                    for (int kh = 0; kh < nkh; ++kh) {
-                        for (int k = 0; k < k16s; ++k) {
-                            const uint64_t ad = make_smem_desc(sa + kh * sbo + k * 32, sbo, layout);
-                            const uint64_t bd = make_smem_desc(sb + kh * b_tap_bytes + k * 32, sbo, layout);
-                            umma_bf16(d_tmem, ad, bd, idesc, (ks | kh | k) != 0 ? 1u : 0u);
+                    const uint32_t sa16 = smem0_16 + static_cast<uint32_t>(stage) * stage16;
+                    const uint32_t sb16 = sa16 + a16;
+#pragma unroll
+                    for (int kh = 0; kh < NKH; ++kh) {
+#pragma unroll
+                        for (int k = 0; k < CC / 16; ++k) {
+                            const uint64_t ad = desc_base | static_cast<uint64_t>(sa16 + ((kh * kSbo + k * 32) >> 4));
+                            const uint64_t bd = desc_base | static_cast<uint64_t>(sb16 + kh * b_tap16 + ((k * 32) >> 4));
+                            umma_bf16(d_tmem, ad, bd, idesc, (kh | k) != 0 ? 1u : (ks != 0 ? 1u : 0u));
                         }
                     }
-                    umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
                     if (ks == ksteps - 1) umma_commit(&tfull_bar[acc]);
                 }
                 __syncwarp();
+                if (++stage == nstages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
             }
         }
     } else {
@@ -208,9 +233,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 float f[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    float x = __uint_as_float(v[i]);
-                    if (a.bias != nullptr) x += __ldg(&a.bias[co + i]);
-                    f[i] = x;
+                    f[i] = __uint_as_float(v[i]) + sbias[co + i];
                 }
                 if (a.stats != nullptr) {
                     // per-channel sum / sum of squares over this warp's 32 voxels: transpose-reduce (31 shuffles each)
@@ -302,18 +325,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 }  // namespace
 
 size_t conv_tc_smem_bytes(const ConvArgs& a) {
-    return static_cast<size_t>(a.nstages) * (a.a_stage_bytes + a.b_stage_bytes) + 1024 /*barriers*/ + 1024 /*align*/;
+    return static_cast<size_t>(a.nstages) * (a.a_stage_bytes + a.b_stage_bytes) + 1024 /*barriers*/ + 2048 /*bias*/ +
+           1024 /*align*/;
 }
 
-cudaError_t launch_conv_tc(const ConvArgs& a, int grid, size_t smem_bytes, cudaStream_t stream) {
-    static bool attr_set = false;
+template <int CC, bool KHS>
+static cudaError_t launch_variant(const ConvArgs& a, int grid, size_t smem_bytes, cudaStream_t stream) {
+    static bool attr_set = false;  // one process drives one device
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<CC, KHS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             232448);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    conv_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(a);
+    conv_tc_kernel<CC, KHS><<<grid, kThreads, smem_bytes, stream>>>(a);
     return cudaGetLastError();
+}
+
+cudaError_t launch_conv_tc(const ConvArgs& a, int grid, size_t smem_bytes, cudaStream_t stream) {
+    if (a.khshift) {
+        if (a.cc == 64) return launch_variant<64, true>(a, grid, smem_bytes, stream);
+        if (a.cc == 32) return launch_variant<32, true>(a, grid, smem_bytes, stream);
+        return launch_variant<16, true>(a, grid, smem_bytes, stream);
+    }
+    if (a.cc == 64) return launch_variant<64, false>(a, grid, smem_bytes, stream);
+    if (a.cc == 32) return launch_variant<32, false>(a, grid, smem_bytes, stream);
+    return launch_variant<16, false>(a, grid, smem_bytes, stream);
 }
 
 }  // namespace bsg

@@ -21,7 +21,10 @@ class SegmentationNetwork(nn.Module):
 
     # ------------------------------------------------------------------ engine cache
     def engine_for(self, patch_size, batch=None):
+        from . import _lib as L
         from .engine import UNetEngine
+        if not torch.cuda.is_available():
+            raise L.BsgError("brainseg_b200 needs a CUDA device (sm_100); there is no CPU fallback")
         batch = int(batch or self.engine_batch)
         key = (tuple(int(p) for p in patch_size), batch, torch.cuda.current_device())
         if key not in self._engines:

@@ -40,6 +40,13 @@ def mirror_codes_for(mirror_axes, do_mirroring=True):
     return [m for m in ALL_MIRROR_CODES if (m & ~allowed) == 0]
 
 
+def shard_work_items(num_tiles, mirror_codes, rank=0, world_size=1):
+    """(tile index, mirror code) pairs owned by `rank`: round-robin over the items sorted by tile, so the shares
+    differ by at most one forward and a rank's items of one tile stay adjacent (one gather / head launch per tile)."""
+    items = [(t, m) for t in range(num_tiles) for m in mirror_codes]
+    return items[rank::world_size]
+
+
 _gauss_cache = {}
 
 
@@ -107,8 +114,7 @@ class SlidingWindowPredictor:
 
     def work_items(self, tiles):
         """(tile index, mirror code) pairs owned by this rank: round-robin over items sorted by tile."""
-        items = [(t, m) for t in range(len(tiles)) for m in self.mirror_codes]
-        return items[self.rank::self.world_size]
+        return shard_work_items(len(tiles), self.mirror_codes, self.rank, self.world_size)
 
     def accumulate(self, vol, acc=None, stream=None):
         """vol: fp32 cuda tensor (C, Z, Y, X) with every extent >= patch.  Adds this rank's share of

@@ -1,0 +1,150 @@
+"""CPU tests of the host-side logic: the C ABI loads and exports what include/*.h declares, the drop-in classes keep
+the reference's checkpoint layout, the sliding-window geometry matches the oracle, and the product refuses to run
+without its CUDA path."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_c_abi_exports_every_declared_symbol():
+    import __graft_entry__ as G
+    G.build()
+    from brainseg_b200 import _lib as L
+    lib = L.lib()
+    header = open(os.path.join(ROOT, "include", "brainseg_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(bsg_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert lib.bsg_version() >= 100
+    assert lib.bsg_ccl26_workspace_bytes(240, 240, 155) >= 240 * 240 * 155 * 4
+
+
+def test_struct_layouts_match_header():
+    from brainseg_b200 import voxelops as V
+    assert V.COMP_DTYPE.itemsize == 88 and V.MOM_DTYPE.itemsize == 120
+    assert V.MOM_DTYPE.fields["surface"][1] == 80 and V.COMP_DTYPE.fields["mn0"][1] == 56
+
+
+def test_no_cpu_fallback():
+    from brainseg_b200 import _lib as L
+    from brainseg_b200 import voxelops as V
+    from tests.helpers import build_dropin_unet
+    if torch.cuda.is_available():
+        pytest.skip("this check is for CPU-only hosts")
+    with pytest.raises(L.BsgError):
+        V.as_label_volume(np.zeros((4, 4, 4), dtype=np.uint8))
+    net = build_dropin_unet("bn", base=16, num_pool=2)
+    with pytest.raises(L.BsgError):
+        net(torch.zeros(1, 4, 16, 16, 16))
+    with pytest.raises(RuntimeError):
+        net.conv_blocks_context[0].blocks[0](torch.zeros(1, 4, 8, 8, 8))  # blocks only hold parameters
+
+
+def test_dropin_unet_checkpoint_layout(golden_dir):
+    from tests.helpers import build_dropin_unet
+    keys = json.load(open(os.path.join(golden_dir, "unet_keys.json")))
+    m1 = build_dropin_unet("bn", base=32, num_pool=5)
+    m2 = build_dropin_unet("gn", base=32, num_pool=5, groups=8, encoder_scale=2, max_num_features=512)
+    for net, ref in ((m1, keys["model1_bn"]), (m2, keys["model2_gn_large"])):
+        sd = net.state_dict()
+        assert list(sd.keys()) == list(ref["keys"].keys())  # same names in the same order
+        assert all(list(sd[k].shape) == ref["keys"][k] for k in sd)
+        assert sum(p.numel() for p in net.parameters()) == ref["params"]
+    assert [int(v) for v in m1.input_shape_must_be_divisible_by] == [32, 32, 32]
+    assert m1.num_classes == 3 and m1.conv_op == torch.nn.Conv3d and m1.do_ds is False
+
+
+@pytest.mark.needs_reference
+def test_dropin_unet_loads_reference_state_dict():
+    """A state_dict produced by the REFERENCE class loads into the drop-in (strict) and vice versa."""
+    from oracle import ref_import as R
+    from tests.helpers import build_dropin_unet
+    ref = R.build_reference_unet("gn", base=16, num_pool=3, groups=4, seed=3)
+    ours = build_dropin_unet("gn", base=16, num_pool=3, groups=4, seed=99)
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    ref.load_state_dict(ours.state_dict(), strict=True)
+    # same construction order + same seed => identical random initial weights as the reference class
+    a = R.build_reference_unet("bn", base=16, num_pool=2, seed=5, randomize_norm=False).state_dict()
+    b = build_dropin_unet("bn", base=16, num_pool=2, seed=5)
+    torch.manual_seed(5)
+    from brainseg_b200 import generic_UNet as G
+    from torch import nn
+    c = G.Generic_UNet(4, 16, 3, 2, 2, 2, nn.Conv3d, nn.BatchNorm3d, {"eps": 1e-5, "affine": True}, nn.Dropout3d,
+                       {"p": 0, "inplace": True}, nn.LeakyReLU, {"negative_slope": 1e-2, "inplace": True}, True, False,
+                       lambda x: x, G.InitWeights_He(1e-2), [[2, 2, 2]] * 2, [[3, 3, 3]] * 3, False, True,
+                       True).state_dict()
+    assert all(torch.equal(a[k], c[k]) for k in a)
+    assert b is not None
+
+
+def test_unsupported_configurations_raise():
+    from brainseg_b200 import generic_UNet as G
+    from torch import nn
+    with pytest.raises(NotImplementedError):
+        G.Generic_UNet(4, 32, 3, 5)  # 2-D default conv_op
+    with pytest.raises(NotImplementedError):
+        G.Generic_UNet(4, 32, 3, 5, conv_op=nn.Conv3d, norm_op=nn.BatchNorm3d, convolutional_pooling=False,
+                       convolutional_upsampling=False)
+
+
+def test_sliding_geometry_matches_oracle():
+    from brainseg_b200 import sliding as S
+    from oracle import sliding_window as SW
+    for img, patch, step in [((155, 240, 240), (128,) * 3, 0.5), ((155, 240, 240), (128,) * 3, 0.25),
+                             ((256,) * 3, (160,) * 3, 0.5), ((137, 171, 140), (128,) * 3, 0.5),
+                             ((128, 128, 128), (128,) * 3, 0.5), ((40, 56, 48), (32,) * 3, 1.0)]:
+        assert S.compute_steps_for_sliding_window(patch, img, step) == SW.compute_steps_for_sliding_window(patch, img, step)
+    for patch in [(128, 128, 128), (32, 48, 64), (16, 16, 16)]:
+        g = S.gaussian_importance_map(patch, torch.device("cpu")).numpy()
+        assert np.array_equal(g, SW.get_gaussian(patch))  # bit-exact with the SciPy-based upstream construction
+    assert S.mirror_codes_for((0, 1, 2)) == list(range(8))
+    assert S.mirror_codes_for((0,)) == [0, 4] and S.mirror_codes_for((1, 2)) == [0, 1, 2, 3]
+    assert S.mirror_codes_for((0, 1, 2), do_mirroring=False) == [0]
+    # codes <-> upstream flip dims (App. A.6): bit0 = dim 4, bit1 = dim 3, bit2 = dim 2
+    for m, flips in enumerate(SW.MIRROR_FLIPS):
+        assert sorted(flips) == sorted(d for b, d in ((1, 4), (2, 3), (4, 2)) if m & b)
+
+
+def test_work_item_sharding_partitions_the_case():
+    from brainseg_b200 import sliding as S
+    full = S.shard_work_items(18, range(8))
+    assert len(full) == 144
+    for world in (2, 3, 4, 8):
+        shards = [S.shard_work_items(18, range(8), r, world) for r in range(world)]
+        assert sorted(sum(shards, [])) == sorted(full)
+        assert max(map(len, shards)) - min(map(len, shards)) <= 1
+
+
+def test_weight_packing_layouts():
+    from brainseg_b200 import packing as P
+    w = torch.arange(2 * 3 * 27, dtype=torch.float32).reshape(2, 3, 3, 3, 3)
+    p = P.pack_conv3_weight(w)
+    assert p.shape == (27, 32, 16) and p.dtype == torch.bfloat16
+    kd, kh, kw = 2, 0, 1
+    tap = (kd * 3 + kw) * 3 + kh  # tap order (kd, kw, kh)
+    assert p[tap, 1, 2].item() == w[1, 2, kd, kh, kw].item()
+    assert p[:, 2:, :].abs().sum() == 0 and p[:, :, 3:].abs().sum() == 0
+    wt = torch.arange(3 * 2 * 8, dtype=torch.float32).reshape(3, 2, 2, 2, 2)
+    pt = P.pack_convT2_weight(wt)
+    assert pt.shape == (1, 8 * 32, 16)
+    par = 1 * 4 + 0 * 2 + 1  # parity index (kd, kh, kw)
+    assert pt[0, par * 32 + 1, 2].item() == wt[2, 1, 1, 0, 1].item()
+    x = torch.randn(2, 4, 3, 5, 6)
+    assert torch.allclose(P.from_ndhwc(P.to_ndhwc_bf16(x), 4), x.to(torch.bfloat16).float())
+
+
+def test_remap_luts_and_dice_formulas_on_host():
+    from brainseg_b200 import convert_labels_to_brats as CL
+    from brainseg_b200 import evaluate_segmentation as EV
+    assert CL.LUT_BRATS2025[:5].tolist() == [0, 2, 1, 3, 0] and CL.LUT_BRATS2021[:5].tolist() == [0, 2, 1, 4, 0]
+    assert CL.LUT_BRATS2025[5:].sum() == 0
+    m = EV._metrics(np.float32(10), np.float32(2), np.float32(3), np.float32(100))
+    assert m["dice"].dtype == np.float32 and m["dice"] == np.float32(20) / (np.float32(20) + np.float32(2) + np.float32(3) + 1e-8)
