@@ -23,8 +23,15 @@ def detect_connected_components(seg_data, voxel_dims):
     if num_components == 0:
         return {"num_components": 0, "components": [], "is_single_lesion": True, "description": "No tumor detected"}
     vox = np.prod(voxel_dims)
-    components = []
-    for i in range(num_components):
+    # the reference builds a dict for every component and then splits at 0.1 cm³ (:63-125); only the significant ones
+    # are returned, so the split / stable volume sort run on arrays and dicts are built for the survivors only
+    counts = st["count"].astype(np.int64)
+    volumes = counts * vox / 1000
+    keep = np.flatnonzero(volumes >= MIN_LESION_VOLUME_CM3)
+    n_noise = num_components - len(keep)
+    keep = keep[np.argsort(-volumes[keep], kind="stable")]  # list.sort(reverse=True) is stable too (:128)
+    significant = []
+    for rank, i in enumerate(keep.tolist()):
         r = st[i]
         count = int(r["count"])
         centroid = {"x": float(int(r["s0"]) / count), "y": float(int(r["s1"]) / count),
@@ -32,10 +39,10 @@ def detect_connected_components(seg_data, voxel_dims):
         bbox = {"x_min": int(r["mn0"]), "x_max": int(r["mx0"]), "y_min": int(r["mn1"]), "y_max": int(r["mx1"]),
                 "z_min": int(r["mn2"]), "z_max": int(r["mx2"])}
         composition = {"ncr": int(r["n1"]), "ed": int(r["n2"]), "et": int(r["n3"])}
-        components.append({
+        significant.append({
             "id": i + 1,
             "voxel_count": count,
-            "volume_cm3": float(count * vox / 1000),
+            "volume_cm3": float(volumes[i]),
             "centroid_voxel": centroid,
             "centroid_mm": {k: centroid[k] * voxel_dims[a] for a, k in enumerate("xyz")},
             "bounding_box": bbox,
@@ -43,17 +50,13 @@ def detect_connected_components(seg_data, voxel_dims):
                                          for a, k in enumerate("xyz"))),
             "composition": composition,
             "has_enhancement": composition["et"] > 0,
+            "rank": rank + 1,
+            "classification": "Primary lesion" if rank == 0 else f"Secondary lesion #{rank}",
         })
-    significant = [c for c in components if c["volume_cm3"] >= MIN_LESION_VOLUME_CM3]
-    noise = [c for c in components if c["volume_cm3"] < MIN_LESION_VOLUME_CM3]
-    significant.sort(key=lambda c: c["volume_cm3"], reverse=True)  # stable, like the reference (:128)
-    for rank, comp in enumerate(significant):
-        comp["rank"] = rank + 1
-        comp["classification"] = "Primary lesion" if rank == 0 else f"Secondary lesion #{rank}"
     n_sig = len(significant)
-    note = f" ({len(noise)} sub-threshold fragments excluded, <{MIN_LESION_VOLUME_CM3} cm³)" if noise else ""
+    note = f" ({n_noise} sub-threshold fragments excluded, <{MIN_LESION_VOLUME_CM3} cm³)" if n_noise else ""
     return {"num_components": n_sig, "components": significant, "is_single_lesion": n_sig == 1,
-            "description": f"{n_sig} lesion(s) detected{note}", "excluded_fragments": len(noise),
+            "description": f"{n_sig} lesion(s) detected{note}", "excluded_fragments": n_noise,
             "minimum_volume_threshold_cm3": MIN_LESION_VOLUME_CM3}
 
 
@@ -65,13 +68,13 @@ def analyze_enhancing_components(seg_data, voxel_dims):
         return {"num_enhancing_foci": 0, "enhancing_components": [], "pattern": "Non-enhancing",
                 "description": "No enhancing tumor components detected"}
     vox = np.prod(voxel_dims)
-    comps = []
-    for i in range(n_et):
-        r = st[i]
-        count = int(r["count"])
-        comps.append({"id": i + 1, "volume_cm3": float(count * vox / 1000),
-                      "centroid_mm": {k: float(int(r[f"s{a}"]) / count * voxel_dims[a]) for a, k in enumerate("xyz")}})
-    comps.sort(key=lambda c: c["volume_cm3"], reverse=True)
+    counts = st["count"].astype(np.int64)
+    volumes = (counts * vox / 1000).tolist()
+    cents = [(st[f"s{a}"].astype(np.float64) / counts * voxel_dims[a]).tolist() for a in range(3)]
+    # exact: the coordinate sums are < 2**53, so float64(sum) / count == np.mean(coords)
+    order = np.argsort(-np.asarray(volumes), kind="stable").tolist()
+    comps = [{"id": i + 1, "volume_cm3": volumes[i],
+              "centroid_mm": {"x": cents[0][i], "y": cents[1][i], "z": cents[2][i]}} for i in order]
     if n_et == 1:
         pattern = "Single enhancing focus"
     elif n_et <= 3:

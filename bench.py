@@ -31,6 +31,31 @@ N_TILES = 18
 N_MIRRORS = 8
 
 
+T0 = time.time()
+
+
+def log(msg):
+    sys.stderr.write(f"[bench {time.time() - T0:7.1f}s] {msg}\n")
+    sys.stderr.flush()
+
+
+def usable_cpus():
+    """Host threads this process may really use: the cgroup CPU quota if there is one, else the visible cores."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period))))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -115,8 +140,8 @@ def cpu_reference_sample(model2, include_post=True, threads=None):
     from oracle import unet as OU
     from tests.helpers import build_dropin_unet
 
-    if threads:
-        torch.set_num_threads(threads)
+    torch.set_num_threads(threads or usable_cpus())
+    log(f"cpu baseline: {torch.get_num_threads()} threads")
     m1 = build_dropin_unet("bn", base=32, num_pool=5, seed=1)
     sd = {k: v.detach().float() for k, v in m1.state_dict().items()}
     arch = OU.arch_from_module(m1)
@@ -126,6 +151,7 @@ def cpu_reference_sample(model2, include_post=True, threads=None):
     y = OU.forward(sd, arch, x)
     torch.sigmoid(y)
     t_fwd = time.perf_counter() - t0
+    log(f"cpu baseline: one 128^3 forward {t_fwd:.2f} s")
     gf1 = OU.conv_flops(sd, arch, PATCH) / 1e9
     gf2 = 3342.2 if model2 == "large" else gf1
     t_post = 0.0
@@ -142,6 +168,7 @@ def cpu_reference_sample(model2, include_post=True, threads=None):
         OP.calculate_shape_descriptors(brats, masks, (1.0, 1.0, 1.0))
         OP.analyze_necrosis_pattern(brats, masks, np.array((1.0, 1.0, 1.0)))
         t_post = time.perf_counter() - t0
+        log(f"cpu baseline: post-processing chain {t_post:.2f} s")
     n_fwd = N_TILES * N_MIRRORS
     t_case = t_fwd * n_fwd * (1.0 + gf2 / gf1) + t_post
     return {"t_fwd": t_fwd, "t_post": t_post, "t_case": t_case, "gf1": gf1, "gf2": gf2,
@@ -221,7 +248,10 @@ def run_ours(args):
     from brainseg_b200 import pipeline as PL
     from oracle import synthetic as SY
 
+    torch.set_num_threads(usable_cpus())
+    log(f"rank {rank}/{world}: building models ({torch.get_num_threads()} host threads)")
     m1, m2 = build_models(args.model2)
+    log("models built")
     reduce_fn = None
     if args.mode == "latency" and world > 1:
         def reduce_fn(acc):
@@ -231,6 +261,8 @@ def run_ours(args):
                                 rank=rank if args.mode == "latency" else 0,
                                 world_size=world if args.mode == "latency" else 1, reduce_fn=reduce_fn)
     eng1, eng2 = pipe.predictors[0].engine, pipe.predictors[1].engine
+    log(f"engines ready: {eng1.launches_per_forward} + {eng2.launches_per_forward} launches per forward batch, "
+        f"{eng1.flops_per_item / 1e9:.1f} + {eng2.flops_per_item / 1e9:.1f} GF per tile-mirror")
 
     # synthetic inputs: pinned host volume (seeded per rank) + synthetic ground truth labels
     seed = 0 if args.mode == "latency" else rank
@@ -252,8 +284,13 @@ def run_ours(args):
         seg_host = out["segmentation"].cpu()  # D2H of the final label volume
         return out, seg_host
 
-    for _ in range(max(args.warmup, 1)):
-        step_e2e()
+    log("inputs ready; warm-up")
+    for i in range(max(args.warmup, 1)):
+        t0 = time.time()
+        out, _ = step_e2e()
+        torch.cuda.synchronize()
+        log(f"warm-up step {i}: {time.time() - t0:.2f} s, {out['components']['num_components']} significant components, "
+            f"{out['components']['excluded_fragments']} fragments, {out['enhancing']['num_enhancing_foci']} ET foci")
     barrier()
 
     sampler = ClockSampler(local) if rank == 0 else None
@@ -269,6 +306,7 @@ def run_ours(args):
     e1.record()
     barrier()
     t_res = e0.elapsed_time(e1) / 1e3
+    log(f"resident: {t_res / args.steps:.3f} s per case")
     launches = (pipe.kernel_launches() - l0) + args.steps * pipe.extra_launches
     conv_ms = [sum(a.elapsed_time(b) for a, b in e.event_log) for e in (eng1, eng2)]
     conv_runs = [len(e.event_log) for e in (eng1, eng2)]
@@ -282,6 +320,7 @@ def run_ours(args):
     e1.record()
     barrier()
     t_e2e = e0.elapsed_time(e1) / 1e3
+    log(f"e2e: {t_e2e / args.steps:.3f} s per case")
     clocks = sampler.stop() if sampler is not None else None
 
     times = torch.tensor([t_res, t_e2e], dtype=torch.float64, device=dev)

@@ -85,7 +85,8 @@ def test_predict_3d_softmax_argmax_groupnorm():
 def test_predict_3d_volume_smaller_than_patch_and_subset_mirrors():
     net = build_dropin_unet("in", base=16, num_pool=2, seed=13)
     vol = torch.randn(4, 20, 32, 27, generator=torch.Generator().manual_seed(4)).numpy()
-    _check_predict(net, vol, (32, 32, 32), (1, 2), True, 0.5, (1, 2, 3), torch.sigmoid)  # padded, single tile
+    # 4 mirrors, one padded tile, InstanceNorm over tiny (4^3) deep levels: less averaging than north_star -> 2e-2
+    _check_predict(net, vol, (32, 32, 32), (1, 2), True, 0.5, (1, 2, 3), torch.sigmoid, tol=2 * PROB_TOL)
     # 2 mirrors / no mirrors: less averaging of the bf16 noise than the north_star configuration -> 2e-2
     _check_predict(net, vol, (16, 16, 16), (0,), True, 0.25, (1, 2, 3), torch.sigmoid, tol=2 * PROB_TOL)
     _check_predict(net, vol, (16, 16, 16), (0, 1, 2), False, 1.0, None, torch.sigmoid, use_gaussian=False,
