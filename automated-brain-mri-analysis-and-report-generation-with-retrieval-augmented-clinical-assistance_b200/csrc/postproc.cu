@@ -402,10 +402,13 @@ __global__ void __launch_bounds__(kThreads) ccl_finalize_kernel(const uint8_t* _
         if (i < n) root = L[i];
         // ids of roots were written by ccl_assign_kernel before this kernel started; non-root voxels read them
         if (root >= 0) id = (root == static_cast<int>(i)) ? labels[i] : labels[root];
-        const unsigned active = __ballot_sync(0xffffffffu, id > 0);
+        // lanes that contribute statistics; ids beyond `cap` are only counted (the caller re-runs with a larger
+        // table), and must not be named in the masks of the warp collectives below
+        const bool part = st != nullptr && id > 0 && id <= cap;
+        const unsigned active = __ballot_sync(0xffffffffu, part);
         if (i < n && root != static_cast<int>(i)) labels[i] = id;  // (roots already hold their id)
-        if (st == nullptr || active == 0u) continue;
-        if (id > 0 && id <= cap) {
+        if (active == 0u) continue;
+        if (part) {
             const int i2 = static_cast<int>(i % d2), i1 = static_cast<int>((i / d2) % d1),
                       i0 = static_cast<int>(i / (static_cast<size_t>(d2) * d1));
             const uint8_t v = vol[i];

@@ -52,6 +52,7 @@ class UNetEngine:
         if any(p % d for p, d in zip(self.patch, div)):
             raise ValueError(f"patch size {self.patch} must be divisible by {div}")
         self.steps = []       # callables, in launch order
+        self.step_info = []   # per step: name, algorithmic flops, plan geometry (diagnostics / bench breakdown)
         self.keep = []        # tensors the plans point at
         self.launches_per_forward = 0
         self.flops = 0.0
@@ -98,6 +99,8 @@ class UNetEngine:
                           out_f16=1 if stats is not None else 0, use_khshift=-1,
                           max_ctas=0)
         self.flops += plan.info().flops
+        self._note(f"conv3 s{stride} {cin_pad}->{cout} @{'x'.join(map(str, spatial_in))}"
+                   f"{' +norm' if stats is not None else ''}", plan)
         lib = L.lib()
         if stats is None:
             self.steps.append(plan.run)
@@ -135,8 +138,15 @@ class UNetEngine:
                           out_coff=dst.coff, weights=wp.data_ptr(), bias=None, act=L.BSG_ACT_NONE, slope=0.0,
                           stats=None, use_khshift=0, max_ctas=0)
         self.flops += plan.info().flops
+        self._note(f"convT2 {src.c}->{w.shape[1]} @{'x'.join(map(str, spatial_in))}", plan)
         self.steps.append(plan.run)
         self.launches_per_forward += 1
+
+    def _note(self, name, plan):
+        i = plan.info()
+        self.step_info.append({"name": name, "flops": i.flops,
+                               "plan": f"box {i.bw}x{i.bh}x{i.bd}x{i.bn} ntile {i.ntile}x{i.n_ntiles} cc {i.cc} "
+                                       f"stages {i.nstages} khs {i.khshift} grid {i.grid}"})
 
     def _build(self):
         net = self.net

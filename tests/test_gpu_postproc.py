@@ -146,6 +146,23 @@ def test_component_statistics(mods, shape, vd):
     tree_equal(OP.analyze_enhancing_components(seg, vd), mods["S3"].analyze_enhancing_components(seg, vd), "enhancing")
 
 
+def test_more_components_than_the_statistics_table(mods):
+    # 4800 isolated enhancing voxels + noise: more components than ccl26's default 4096-row statistics table, so the
+    # first pass only counts and the wrapper re-runs with room for every component (this used to dead-lock)
+    rng = np.random.default_rng(7)
+    seg = np.zeros((24, 40, 40), dtype=np.int32)
+    seg[::2, ::2, ::2] = 3
+    seg[1::2, 1::2, :] = (rng.random((12, 20, 40)) < 0.05) * 2
+    vd = (1.0, 1.0, 1.0)
+    ref = OP.analyze_enhancing_components(seg, vd)
+    assert ref["num_enhancing_foci"] == 4800
+    tree_equal(ref, mods["S3"].analyze_enhancing_components(seg, vd), "enhancing")
+    tree_equal(OP.detect_connected_components(seg, vd), mods["S3"].detect_connected_components(seg, vd), "components")
+    _, n, st = mods["V"].ccl26(mods["V"].as_label_volume(seg), stats_cap=16)
+    _, nref = OP.label_components(seg > 0)
+    assert n == nref and len(st) == n and int(st["count"].sum()) == int((seg > 0).sum())
+
+
 @pytest.mark.parametrize("shape", SHAPES)
 def test_masks_volumes_morphology(mods, shape):
     pred, _ = _pair(5, shape)
