@@ -1,0 +1,299 @@
+// "Brick" tcgen05 / TMEM / TMA implicit-GEMM kernel for the stride-1 3x3x3 convs with Cout <= 64
+// (reference: model_architecture/generic_UNet.py:56,69 — the full- and half-resolution conv blocks, where the
+// activations are large and the channel counts small).
+//
+// The plain tile kernel (conv_tc.cu) re-reads every activation box 9x and the whole 27-tap weight set once per 128
+// output voxels; at Cout = 32 / 64 that L2 -> shared-memory traffic, not the tensor pipe, bounds it.  Here a CTA owns
+// a brick of P output planes whose fp32 accumulators all sit in TMEM (P x NT columns, two bricks in flight), so
+//   * one activation box (8 w x 18 h haloed rows of ONE input plane, one kw shift, one channel chunk) is loaded once
+//     and used by the nine (kd, kh) taps that touch it: 3 output planes x 3 row-shifted descriptors;
+//   * weights are staged as per-phase slabs (phase = (channel chunk, kw): 9 taps x NT x CC) that stay resident in
+//     shared memory for the whole launch when all phases fit, else stream through two buffers once per brick.
+// Roles: warp 0 activation TMA producer, warp 1 MMA issuer (one elected lane), warps 2..5 epilogue (one TMEM lane
+// quadrant each), warp 6 weight-slab TMA producer.
+#include "bsg_ptx.cuh"
+#include "conv_brick.cuh"
+#include "conv_epilogue.cuh"
+
+namespace bsg {
+
+namespace {
+
+constexpr int kMaxStages = 12;
+constexpr int kMaxSlabs = 6;
+constexpr int kMaxAcc = 16;
+
+struct Unit {
+    int w0, h0, d0, n;
+};
+
+__device__ __forceinline__ Unit decode_unit(const BrickArgs& a, int u, int P) {
+    Unit t;
+    const int b = u % a.tb;
+    int s = u / a.tb;
+    const int wt = s % a.tw;
+    s /= a.tw;
+    const int ht = s % a.th;
+    t.n = s / a.th;
+    t.w0 = wt * 8;
+    t.h0 = ht * 16;
+    t.d0 = b * P;
+    return t;
+}
+
+template <int CC, int NT>
+__global__ void __launch_bounds__(kBrickThreads, 1) conv_brick_kernel(const __grid_constant__ BrickArgs a) {
+    constexpr int P = 256 / NT;
+    constexpr uint32_t kRowBytes = CC * 2u;
+    constexpr uint32_t kAtom = 8u * kRowBytes;              // 8 rows: one swizzle atom, one h step of the 8-wide box
+    constexpr uint32_t kTapBytes = NT * kRowBytes;          // one tap of a weight slab
+    constexpr uint32_t kLayout = (CC == 64) ? kLayoutSW128 : (CC == 32 ? kLayoutSW64 : kLayoutSW32);
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* slabs = smem;
+    uint8_t* stages = slabs + static_cast<size_t>(a.nslabbuf) * a.slab_bytes;
+    uint8_t* bar_area = stages + static_cast<size_t>(a.nstages) * a.a_stage_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_area);
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* wfull_bar = empty_bar + kMaxStages;
+    uint64_t* wempty_bar = wfull_bar + kMaxSlabs;
+    uint64_t* tfull_bar = wempty_bar + kMaxSlabs;
+    uint64_t* tempty_bar = tfull_bar + kMaxAcc;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + kMaxAcc);
+    float* sbias = reinterpret_cast<float*>(bar_area + 1024);  // [NT]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&a.mapW);
+        tma_prefetch_desc(&a.mapA);
+        for (int s = 0; s < kMaxStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < kMaxSlabs; ++s) {
+            mbar_init(&wfull_bar[s], 1);
+            mbar_init(&wempty_bar[s], 1);
+        }
+        for (int i = 0; i < kMaxAcc; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    if (warp >= 2 && warp < 6) {
+        for (int i = threadIdx.x - 64; i < NT; i += 128) sbias[i] = (a.bias != nullptr) ? a.bias[i] : 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int units = a.tn * a.th * a.tw * a.tb;
+    const int nphases = a.nphases;
+    const bool resident = a.nslabbuf >= nphases;
+
+    if (warp == 0) {
+        // =========================================================== activation producer
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const Unit t = decode_unit(a, u, P);
+                for (int ph = 0; ph < nphases; ++ph) {
+                    const int c = ph / 3, kw = ph - c * 3;
+                    for (int p = 0; p < P + 2; ++p) {
+                        const int d = t.d0 + p - 1;
+                        if (d < 0 || d >= a.D) continue;  // zero plane: contributes nothing, never issued
+                        mbar_wait(&empty_bar[stage], phase ^ 1u);
+                        mbar_expect_tx(&full_bar[stage], a.a_tx_bytes);
+                        tma_load_5d(stages + static_cast<size_t>(stage) * a.a_stage_bytes, &a.mapA, &full_bar[stage],
+                                    c * CC, t.w0 + kw - 1, t.h0 - 1, d, t.n);
+                        if (++stage == a.nstages) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 6) {
+        // =========================================================== weight-slab producer
+        if (elect_one()) {
+            uint32_t su = 0;  // slab uses so far
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                if (resident && su >= static_cast<uint32_t>(nphases)) break;
+                for (int ph = 0; ph < nphases; ++ph, ++su) {
+                    uint32_t buf;
+                    if (resident) {
+                        buf = static_cast<uint32_t>(ph);
+                    } else {
+                        buf = su % static_cast<uint32_t>(a.nslabbuf);
+                        mbar_wait(&wempty_bar[buf], ((su / static_cast<uint32_t>(a.nslabbuf)) & 1u) ^ 1u);
+                    }
+                    const int c = ph / 3, kw = ph - c * 3;
+                    uint8_t* dst = slabs + static_cast<size_t>(buf) * a.slab_bytes;
+                    mbar_expect_tx(&wfull_bar[buf], a.slab_bytes);
+                    for (int kd = 0; kd < 3; ++kd)
+                        tma_load_3d(dst + kd * 3 * kTapBytes, &a.mapW, &wfull_bar[buf], c * CC, 0, (kd * 3 + kw) * 3);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================================================== MMA issuer
+        const bool leader = elect_one();
+        const uint32_t idesc = make_idesc_bf16(128, NT);
+        const uint64_t desc_base = make_smem_desc(0, kAtom, kLayout);
+        const uint32_t stages16 = smem_u32(stages) >> 4, slabs16 = smem_u32(slabs) >> 4;
+        const uint32_t stage16 = a.a_stage_bytes >> 4, slab16 = a.slab_bytes >> 4;
+        int stage = 0;
+        uint32_t phase = 0, su = 0, tcount = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x, ++tcount) {
+            const Unit t = decode_unit(a, u, P);
+            const uint32_t bb = tcount & 1u, par = (tcount >> 1) & 1u;
+            uint32_t started = 0;  // bit q: accumulator q of this brick already holds a partial sum
+            for (int ph = 0; ph < nphases; ++ph, ++su) {
+                uint32_t buf;
+                if (resident) {
+                    buf = static_cast<uint32_t>(ph);
+                    if (tcount == 0) mbar_wait(&wfull_bar[buf], 0u);
+                } else {
+                    buf = su % static_cast<uint32_t>(a.nslabbuf);
+                    mbar_wait(&wfull_bar[buf], (su / static_cast<uint32_t>(a.nslabbuf)) & 1u);
+                }
+                tc_fence_after();
+                const uint32_t sb16 = slabs16 + buf * slab16;
+                for (int p = 0; p < P + 2; ++p) {
+                    const int d = t.d0 + p - 1;
+                    if (d < 0 || d >= a.D) continue;
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa16 = stages16 + static_cast<uint32_t>(stage) * stage16;
+#pragma unroll
+                    for (int kd = 0; kd < 3; ++kd) {
+                        const int q = p - kd;  // output plane fed by input plane p through tap row kd
+                        if (q < 0 || q >= P) continue;
+                        const uint32_t slot = bb * P + static_cast<uint32_t>(q);
+                        const uint32_t have = (started >> q) & 1u;
+                        if (!have) {  // first touch of this TMEM slot in this brick: the epilogue must have drained it
+                            mbar_wait(&tempty_bar[slot], par ^ 1u);
+                            tc_fence_after();
+                        }
+                        if (leader) {
+                            const uint32_t d_tmem = tmem_base + slot * NT;
+#pragma unroll
+                            for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                                for (int k = 0; k < CC / 16; ++k) {
+                                    const uint64_t ad = desc_base | static_cast<uint64_t>(sa16 + ((kh * kAtom + k * 32) >> 4));
+                                    const uint64_t bd = desc_base | static_cast<uint64_t>(
+                                                                        sb16 + (((kd * 3 + kh) * kTapBytes + k * 32) >> 4));
+                                    umma_bf16(d_tmem, ad, bd, idesc, (kh | k) != 0 ? 1u : have);
+                                }
+                            }
+                        }
+                        started |= 1u << q;
+                    }
+                    if (leader) {
+                        umma_commit(&empty_bar[stage]);  // frees the activation slot once these MMAs have read it
+                        if (ph == nphases - 1) {
+                            // planes whose last contribution was just issued
+                            if (p >= 2 && p - 2 < P) umma_commit(&tfull_bar[bb * P + (p - 2)]);
+                            if (d + 1 >= a.D && p >= 1 && p - 1 < P) umma_commit(&tfull_bar[bb * P + (p - 1)]);
+                        }
+                    }
+                    __syncwarp();
+                    if (++stage == a.nstages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                if (!resident && leader) umma_commit(&wempty_bar[buf]);
+                __syncwarp();
+            }
+        }
+    } else {
+        // =========================================================== epilogue (4 warps, one TMEM lane quadrant each)
+        const int q4 = warp & 3;
+        const int row = q4 * 32 + lane;
+        const int iw = row & 7, ih = row >> 3;
+        EpiParams epi;
+        epi.sbias = sbias;
+        epi.stats = a.stats;
+        epi.cout = a.cout;
+        epi.No = a.tn;
+        epi.act = a.act;
+        epi.slope = a.slope;
+        epi.out_f16 = a.out_f16;
+        uint32_t tcount = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x, ++tcount) {
+            const Unit t = decode_unit(a, u, P);
+            const uint32_t bb = tcount & 1u, par = (tcount >> 1) & 1u;
+            __nv_bfloat16* obase = a.out + t.n * a.os_n + static_cast<long long>(t.h0 + ih) * a.os_h +
+                                   static_cast<long long>(t.w0 + iw) * a.os_w + a.out_c_off;
+            for (int q = 0; q < P; ++q) {
+                const uint32_t slot = bb * P + static_cast<uint32_t>(q);
+                mbar_wait(&tfull_bar[slot], par);
+                tc_fence_after();
+                __nv_bfloat16* orow = obase + static_cast<long long>(t.d0 + q) * a.os_d;
+                const uint32_t t_addr = tmem_base + slot * NT + (static_cast<uint32_t>(q4 * 32) << 16);
+#pragma unroll
+                for (int cb = 0; cb < NT; cb += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_addr + cb, v);
+                    tmem_ld_wait();
+                    epilogue_32cols(v, epi, cb, true, lane, t.n, orow);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[slot]);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+template <int CC, int NT>
+cudaError_t launch_variant(const BrickArgs& a, int grid, size_t smem_bytes, cudaStream_t stream) {
+    static bool attr_set = false;  // one process drives one device
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_brick_kernel<CC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             232448);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    conv_brick_kernel<CC, NT><<<grid, kBrickThreads, smem_bytes, stream>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+size_t conv_brick_smem_bytes(const BrickArgs& a) {
+    return static_cast<size_t>(a.nslabbuf) * a.slab_bytes + static_cast<size_t>(a.nstages) * a.a_stage_bytes +
+           1024 /*barriers*/ + 256 /*bias*/ + 1024 /*align*/;
+}
+
+cudaError_t launch_conv_brick(const BrickArgs& a, int cc, int nt, int grid, size_t smem_bytes, cudaStream_t stream) {
+    if (nt == 32) {
+        if (cc == 64) return launch_variant<64, 32>(a, grid, smem_bytes, stream);
+        if (cc == 32) return launch_variant<32, 32>(a, grid, smem_bytes, stream);
+        return launch_variant<16, 32>(a, grid, smem_bytes, stream);
+    }
+    if (cc == 64) return launch_variant<64, 64>(a, grid, smem_bytes, stream);
+    if (cc == 32) return launch_variant<32, 64>(a, grid, smem_bytes, stream);
+    return launch_variant<16, 64>(a, grid, smem_bytes, stream);
+}
+
+}  // namespace bsg

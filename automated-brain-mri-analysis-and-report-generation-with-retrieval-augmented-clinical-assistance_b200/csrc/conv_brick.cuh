@@ -1,0 +1,44 @@
+// Argument block of the "brick" variant of the tcgen05 conv kernel (conv_brick.cu) for the wide, shallow layers of
+// Generic_UNet (stride-1 Conv3d k3, Cout <= 64: the full- and half-resolution levels, where most of the time goes).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace bsg {
+
+// One work unit = a brick of P consecutive output planes (8 w x 16 h voxels each, one batch item).  All P fp32
+// accumulators of a brick live in TMEM at once (2 bricks double-buffered = 512 columns), so every activation box
+// that TMA brings in (8 x 18 haloed rows of one input plane, one kw shift, one 16/32/64-channel chunk) feeds all
+// nine (kd, kh) taps it takes part in, and the weights sit in shared memory as per-phase slabs
+// (phase = (channel chunk, kw); 9 taps x Cout x CC each) that stay resident when all of them fit.
+struct BrickArgs {
+    CUtensorMap mapA;  // 5-D (C, W, H, D, N) activations, box (CC, 8, 18, 1, 1), OOB zero fill = conv padding
+    CUtensorMap mapW;  // 3-D (Cin_pad, Cout_pad, 27 taps in (kd, kw, kh) order), box (CC, NT, 3)
+    int tw, th, tb, tn;  // unit grid: W/8, H/16, D/P, batch
+    int P;               // planes per brick = 256 / NT
+    int D;
+    int nchunks;   // Cin / CC
+    int nphases;   // 3 * nchunks, phase = chunk * 3 + kw
+    int nslabbuf;  // weight slab buffers in shared memory; >= nphases: resident for the whole launch
+    int nstages;   // activation ring depth
+    uint32_t a_stage_bytes;  // multiple of 1024
+    uint32_t a_tx_bytes;     // bytes one activation box delivers
+    uint32_t slab_bytes;     // 9 * NT * CC * 2
+    // epilogue
+    __nv_bfloat16* out;
+    long long os_n, os_d, os_h, os_w;
+    int out_c_off;
+    int cout, cout_pad;
+    const float* bias;
+    float slope;
+    int act;
+    float* stats;
+    int out_f16;
+};
+
+constexpr int kBrickThreads = 224;
+cudaError_t launch_conv_brick(const BrickArgs& a, int cc, int nt, int grid, size_t smem_bytes, cudaStream_t stream);
+size_t conv_brick_smem_bytes(const BrickArgs& a);
+
+}  // namespace bsg

@@ -4,6 +4,7 @@
 #include <string.h>
 #include <new>
 #include "bsg_common.cuh"
+#include "conv_brick.cuh"
 #include "conv_tc.cuh"
 
 namespace bsg {
@@ -59,11 +60,89 @@ uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
 }  // namespace bsg
 
 struct bsg_conv_plan {
-    bsg::ConvArgs args;
+    bsg::ConvArgs args;    // tile kernel (conv_tc.cu)
+    bsg::BrickArgs bargs;  // brick kernel (conv_brick.cu), used when brick != 0
+    int brick, brick_cc, brick_nt;
     int grid;
     size_t smem_bytes;
     double flops;
 };
+
+namespace bsg {
+namespace {
+
+// Brick kernel eligibility + geometry (see conv_brick.cuh).  Returns 1 when the plan was filled, 0 when the layer
+// does not suit the brick kernel, < 0 on error.
+int plan_brick(const bsg_conv_desc* d, bsg_conv_plan* p) {
+    if (d->kind != BSG_CONV_K3 || d->stride != 1 || d->algo == 0) return 0;
+    const int cout_pad = static_cast<int>(round_up(d->cout, 32));
+    if (cout_pad != 32 && cout_pad != 64) return 0;
+    const int P = 256 / cout_pad;
+    if (d->W % 8 != 0 || d->H % 16 != 0 || d->D % P != 0) return 0;
+    BrickArgs& a = p->bargs;
+    memset(&a, 0, sizeof(a));
+    const int cc = (d->cin % 64 == 0) ? 64 : (d->cin % 32 == 0 ? 32 : 16);
+    a.P = P;
+    a.D = d->D;
+    a.tw = d->W / 8;
+    a.th = d->H / 16;
+    a.tb = d->D / P;
+    a.tn = d->N;
+    a.nchunks = d->cin / cc;
+    a.nphases = 3 * a.nchunks;
+    a.a_tx_bytes = 8u * 18u * cc * 2u;
+    a.a_stage_bytes = round_up(a.a_tx_bytes, 1024);
+    a.slab_bytes = 9u * cout_pad * cc * 2u;
+    const uint32_t avail = 227 * 1024 - 1024 - 1280;
+    if (a.nphases <= 6 && static_cast<uint64_t>(a.nphases) * a.slab_bytes + 3ull * a.a_stage_bytes <= avail)
+        a.nslabbuf = a.nphases;  // resident
+    else if (2ull * a.slab_bytes + 2ull * a.a_stage_bytes <= avail)
+        a.nslabbuf = 2;
+    else
+        return 0;
+    a.nstages = static_cast<int>((avail - static_cast<uint32_t>(a.nslabbuf) * a.slab_bytes) / a.a_stage_bytes);
+    if (a.nstages > 12) a.nstages = 12;
+
+    const uint64_t ct = static_cast<uint64_t>(d->in_ctot);
+    uint64_t dims[5] = {static_cast<uint64_t>(d->cin), static_cast<uint64_t>(d->W), static_cast<uint64_t>(d->H),
+                        static_cast<uint64_t>(d->D), static_cast<uint64_t>(d->N)};
+    uint64_t str[4] = {ct * 2, ct * 2 * d->W, ct * 2 * d->W * d->H, ct * 2 * d->W * d->H * d->D};
+    uint32_t box[5] = {static_cast<uint32_t>(cc), 8u, 18u, 1u, 1u};
+    int rc = encode_map(&a.mapA, d->in, 5, dims, str, box, cc);
+    if (rc != BSG_OK) return rc;
+    uint64_t wdims[3] = {static_cast<uint64_t>(d->cin), static_cast<uint64_t>(cout_pad), 27ull};
+    uint64_t wstr[2] = {static_cast<uint64_t>(d->cin) * 2, static_cast<uint64_t>(d->cin) * 2 * cout_pad};
+    uint32_t wbox[3] = {static_cast<uint32_t>(cc), static_cast<uint32_t>(cout_pad), 3u};
+    rc = encode_map(&a.mapW, d->weights, 3, wdims, wstr, wbox, cc);
+    if (rc != BSG_OK) return rc;
+
+    a.out = static_cast<__nv_bfloat16*>(d->out);
+    a.os_w = d->out_ctot;
+    a.os_h = static_cast<long long>(d->out_ctot) * d->W;
+    a.os_d = a.os_h * d->H;
+    a.os_n = a.os_d * d->D;
+    a.out_c_off = d->out_coff;
+    a.cout = d->cout;
+    a.cout_pad = cout_pad;
+    a.bias = d->bias;
+    a.slope = d->slope;
+    a.act = d->act;
+    a.stats = d->stats;
+    a.out_f16 = d->out_f16;
+
+    p->brick = 1;
+    p->brick_cc = cc;
+    p->brick_nt = cout_pad;
+    const int units = a.tn * a.th * a.tw * a.tb;
+    const int max_ctas = d->max_ctas > 0 ? d->max_ctas : sm_count_cached();
+    p->grid = units < max_ctas ? units : max_ctas;
+    p->smem_bytes = conv_brick_smem_bytes(a);
+    p->flops = 2.0 * 27 * static_cast<double>(d->cin) * d->cout * (static_cast<double>(d->W) * d->H * d->D * d->N);
+    return 1;
+}
+
+}  // namespace
+}  // namespace bsg
 
 using namespace bsg;
 
@@ -107,6 +186,18 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
 
     bsg_conv_plan* p = new (std::nothrow) bsg_conv_plan();
     if (p == nullptr) return set_error(BSG_ENOMEM, "host allocation failed");
+    p->brick = 0;
+    {
+        const int br = plan_brick(d, p);
+        if (br < 0) {
+            delete p;
+            return br;
+        }
+        if (br == 1) {
+            *out_plan = p;
+            return BSG_OK;
+        }
+    }
     ConvArgs& a = p->args;
     memset(&a, 0, sizeof(a));
 
@@ -156,6 +247,14 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
     a.ntile = a.cout_pad / split;
     a.out_mul = (d->kind == BSG_CONVT_K2S2) ? 2 : 1;
     a.n_ntiles = split * (a.out_mul == 2 ? 8 : 1);
+    if (a.out_mul == 2 && split == 1) {
+        // transposed conv: the 8 output parities are extra GEMM columns; let one N tile span as many whole parities
+        // as fit 256 columns so the activation tile is read once instead of once per parity
+        int m = 1;
+        while (m < 8 && a.cout_pad * m * 2 <= 256) m *= 2;
+        a.ntile = a.cout_pad * m;
+        a.n_ntiles = 8 / m;
+    }
     a.tmem_cols = 32;
     while (a.tmem_cols < static_cast<uint32_t>(2 * a.ntile)) a.tmem_cols *= 2;
 
@@ -250,7 +349,11 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
 
 int bsg_conv_plan_run(const bsg_conv_plan* plan, void* stream) {
     BSG_REQUIRE(plan != nullptr, "null plan");
-    BSG_CUDA_OK(launch_conv_tc(plan->args, plan->grid, plan->smem_bytes, static_cast<cudaStream_t>(stream)));
+    if (plan->brick)
+        BSG_CUDA_OK(launch_conv_brick(plan->bargs, plan->brick_cc, plan->brick_nt, plan->grid, plan->smem_bytes,
+                                      static_cast<cudaStream_t>(stream)));
+    else
+        BSG_CUDA_OK(launch_conv_tc(plan->args, plan->grid, plan->smem_bytes, static_cast<cudaStream_t>(stream)));
     return BSG_OK;
 }
 
@@ -258,6 +361,22 @@ void bsg_conv_plan_destroy(bsg_conv_plan* plan) { delete plan; }
 
 int bsg_conv_plan_info(const bsg_conv_plan* plan, bsg_conv_info* info) {
     BSG_REQUIRE(plan != nullptr && info != nullptr, "null argument");
+    if (plan->brick) {
+        const BrickArgs& b = plan->bargs;
+        info->bw = 8;
+        info->bh = 16;
+        info->bd = b.P;
+        info->bn = 1;
+        info->ntile = plan->brick_nt;
+        info->n_ntiles = 1;
+        info->cc = plan->brick_cc;
+        info->nstages = b.nstages;
+        info->khshift = 2 + b.nslabbuf;  /* brick kernel marker: 2 + number of weight-slab buffers */
+        info->grid = plan->grid;
+        info->smem_bytes = plan->smem_bytes;
+        info->flops = plan->flops;
+        return BSG_OK;
+    }
     const ConvArgs& a = plan->args;
     info->bw = a.bw;
     info->bh = a.bh;

@@ -6,6 +6,7 @@
 //   warps 2..5  epilogue       (tcgen05.ld -> bias / LeakyReLU / norm statistics -> bf16 channels-last stores)
 #include <cuda_fp16.h>
 #include "bsg_ptx.cuh"
+#include "conv_epilogue.cuh"
 #include "conv_tc.cuh"
 
 namespace bsg {
@@ -202,6 +203,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int id = r % a.bd;
         r /= a.bd;
         const int in = r;
+        EpiParams epi;
+        epi.sbias = sbias;
+        epi.stats = a.stats;
+        epi.cout = a.cout;
+        epi.No = a.No;
+        epi.act = a.act;
+        epi.slope = a.slope;
+        epi.out_f16 = a.out_f16;
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
             const TileCoord t = decode_tile(a, tile);
@@ -209,18 +218,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const uint32_t acc_phase = (tcount >> 1) & 1u;
             const int w = t.w0 + iw, h = t.h0 + ih, d = t.d0 + id, n = t.n0 + in;
             const bool valid = (w < a.Wo) && (h < a.Ho) && (d < a.Do) && (n < a.No);
-            int q0 = t.nt * a.ntile;  // first GEMM column of this tile
-            int pw = 0, phh = 0, pd = 0;
-            if (a.out_mul == 2) {
-                const int par = q0 / a.cout_pad;
-                q0 -= par * a.cout_pad;
-                pw = par & 1;
-                phh = (par >> 1) & 1;
-                pd = (par >> 2) & 1;
-            }
-            __nv_bfloat16* orow = a.out + n * a.os_n + static_cast<long long>(d * a.out_mul + pd) * a.os_d +
-                                  static_cast<long long>(h * a.out_mul + phh) * a.os_h +
-                                  static_cast<long long>(w * a.out_mul + pw) * a.os_w + a.out_c_off;
+            const int q0 = t.nt * a.ntile;  // first GEMM column of this tile
+            __nv_bfloat16* obase = a.out + n * a.os_n + a.out_c_off;
+            __nv_bfloat16* orow = obase + static_cast<long long>(d) * a.os_d + static_cast<long long>(h) * a.os_h +
+                                  static_cast<long long>(w) * a.os_w;
 
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
@@ -229,84 +230,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 uint32_t v[32];
                 tmem_ld_32x32(t_addr + cb, v);
                 tmem_ld_wait();
-                const int co = q0 + cb;
-                float f[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    f[i] = __uint_as_float(v[i]) + sbias[co + i];
+                int co = q0 + cb;
+                if (a.out_mul == 2) {
+                    // transposed conv: GEMM columns enumerate (parity (pd, ph, pw), channel); an N tile may span
+                    // several parities, so the output voxel is re-derived per 32-column chunk
+                    const int par = co / a.cout_pad;
+                    co -= par * a.cout_pad;
+                    orow = obase + static_cast<long long>(2 * d + ((par >> 2) & 1)) * a.os_d +
+                           static_cast<long long>(2 * h + ((par >> 1) & 1)) * a.os_h +
+                           static_cast<long long>(2 * w + (par & 1)) * a.os_w;
                 }
-                if (a.stats != nullptr) {
-                    // per-channel sum / sum of squares over this warp's 32 voxels: transpose-reduce (31 shuffles each)
-                    float s1[32], s2[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float x = valid ? f[i] : 0.f;
-                        s1[i] = x;
-                        s2[i] = x * x;
-                    }
-#pragma unroll
-                    for (int off = 16; off >= 1; off >>= 1) {
-                        const bool up = (lane & off) != 0;
-#pragma unroll
-                        for (int i = 0; i < off; ++i) {
-                            const float send1 = up ? s1[i] : s1[i + off];
-                            const float keep1 = up ? s1[i + off] : s1[i];
-                            s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, off);
-                            const float send2 = up ? s2[i] : s2[i + off];
-                            const float keep2 = up ? s2[i + off] : s2[i];
-                            s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
-                        }
-                    }
-                    // lane l now owns channel co + l; rows of one warp always share the batch index n
-                    const int nn = __shfl_sync(0xffffffffu, n, 0);
-                    if (co + lane < a.cout && nn < a.No) {
-                        float* sp = a.stats + (static_cast<long long>(nn) * a.cout + co + lane) * 2;
-                        atomicAdd(sp, s1[0]);
-                        atomicAdd(sp + 1, s2[0]);
-                    }
-                }
-                if (a.act == 1) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) f[i] = f[i] > 0.f ? f[i] : f[i] * a.slope;
-                }
-                if (valid) {
-                    if (co + 32 <= a.cout) {
-                        uint4* dst = reinterpret_cast<uint4*>(orow + co);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            uint4 u;
-                            if (a.out_f16) {
-                                __half2 p0 = __floats2half2_rn(f[8 * i + 0], f[8 * i + 1]);
-                                __half2 p1 = __floats2half2_rn(f[8 * i + 2], f[8 * i + 3]);
-                                __half2 p2 = __floats2half2_rn(f[8 * i + 4], f[8 * i + 5]);
-                                __half2 p3 = __floats2half2_rn(f[8 * i + 6], f[8 * i + 7]);
-                                u.x = *reinterpret_cast<uint32_t*>(&p0);
-                                u.y = *reinterpret_cast<uint32_t*>(&p1);
-                                u.z = *reinterpret_cast<uint32_t*>(&p2);
-                                u.w = *reinterpret_cast<uint32_t*>(&p3);
-                            } else {
-                                __nv_bfloat162 p0 = __floats2bfloat162_rn(f[8 * i + 0], f[8 * i + 1]);
-                                __nv_bfloat162 p1 = __floats2bfloat162_rn(f[8 * i + 2], f[8 * i + 3]);
-                                __nv_bfloat162 p2 = __floats2bfloat162_rn(f[8 * i + 4], f[8 * i + 5]);
-                                __nv_bfloat162 p3 = __floats2bfloat162_rn(f[8 * i + 6], f[8 * i + 7]);
-                                u.x = *reinterpret_cast<uint32_t*>(&p0);
-                                u.y = *reinterpret_cast<uint32_t*>(&p1);
-                                u.z = *reinterpret_cast<uint32_t*>(&p2);
-                                u.w = *reinterpret_cast<uint32_t*>(&p3);
-                            }
-                            dst[i] = u;
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (co + i < a.cout) {
-                                if (a.out_f16)
-                                    reinterpret_cast<__half*>(orow)[co + i] = __float2half_rn(f[i]);
-                                else
-                                    orow[co + i] = __float2bfloat16_rn(f[i]);
-                            }
-                    }
-                }
+                epilogue_32cols(v, epi, co, valid, lane, n, orow);
             }
             tc_fence_before();
             __syncwarp();

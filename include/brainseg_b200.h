@@ -71,6 +71,8 @@ typedef struct bsg_conv_desc {
                             bsg_norm_apply_lrelu then rewrites in place as bf16) */
     int use_khshift;     /* -1 auto, 0 off, 1 on: halo reuse of the h taps inside shared memory */
     int max_ctas;        /* 0 = one CTA per SM */
+    int algo;            /* -1 auto, 0 tile kernel (one 128-voxel tile per accumulator), 1 brick kernel when the layer
+                            suits it (stride-1 k3, Cout <= 64, W % 8 == 0, H % 16 == 0, D % (256/Cout_pad) == 0) */
 } bsg_conv_desc;
 
 typedef struct bsg_conv_plan bsg_conv_plan;

@@ -19,7 +19,7 @@ dev = torch.device("cuda:0")
 
 
 def run_case(name, kind, N, D, H, W, cin, cout, stride=1, khshift=-1, act=0, stats=False, in_extra=0, out_extra=0,
-             out_coff=0, seed=0, bias=True, time_it=False):
+             out_coff=0, seed=0, bias=True, time_it=False, algo=-1):
     g = torch.Generator(device="cpu").manual_seed(seed)
     cin_pad = P.round_up(cin, 16)
     x = torch.randn(N, cin, D, H, W, generator=g)
@@ -53,7 +53,7 @@ def run_case(name, kind, N, D, H, W, cin, cout, stride=1, khshift=-1, act=0, sta
     plan = L.ConvPlan(kind=kind, stride=stride, N=N, D=D, H=H, W=W, cin=cin_pad, in_ptr=xb.data_ptr(),
                       in_ctot=in_ctot, cout=cout, out_ptr=out.data_ptr(), out_ctot=out_ctot, out_coff=out_coff,
                       weights=wp.data_ptr(), bias=bp.data_ptr() if bp is not None else None, act=act, slope=0.01,
-                      stats=st.data_ptr() if st is not None else None, use_khshift=khshift, max_ctas=0)
+                      stats=st.data_ptr() if st is not None else None, use_khshift=khshift, max_ctas=0, algo=algo)
     inf = plan.info()
     plan.run()
     torch.cuda.synchronize()
@@ -123,10 +123,32 @@ CASES = [
     ("convT", dict(kind=1, N=1, D=4, H=16, W=8, cin=64, cout=32)),
     ("convT_big", dict(kind=1, N=2, D=4, H=4, W=4, cin=320, cout=320, out_extra=320)),
     ("k1", dict(kind=2, N=1, D=4, H=16, W=16, cin=32, cout=32)),
-    ("perf_32_32_128", dict(kind=0, N=1, D=128, H=128, W=128, cin=32, cout=32, act=1, time_it=True)),
-    ("perf_32_32_128_nokhs", dict(kind=0, N=1, D=128, H=128, W=128, cin=32, cout=32, act=1, khshift=0, time_it=True)),
-    ("perf_64_32_128", dict(kind=0, N=1, D=128, H=128, W=128, cin=64, cout=32, act=1, time_it=True)),
-    ("perf_64_64_64", dict(kind=0, N=1, D=64, H=64, W=64, cin=64, cout=64, act=1, time_it=True)),
+    ("brick_c32_32", dict(kind=0, N=1, D=8, H=16, W=8, cin=32, cout=32)),
+    ("brick_c32_32_multi", dict(kind=0, N=2, D=16, H=32, W=16, cin=32, cout=32, act=1)),
+    ("brick_c64_32", dict(kind=0, N=1, D=8, H=16, W=16, cin=64, cout=32)),
+    ("brick_c64_64_stream", dict(kind=0, N=2, D=8, H=32, W=16, cin=64, cout=64, act=1)),
+    ("brick_c128_64_stream", dict(kind=0, N=1, D=8, H=16, W=16, cin=128, cout=64)),
+    ("brick_c4_32", dict(kind=0, N=1, D=8, H=16, W=16, cin=4, cout=32)),
+    ("brick_c4_64", dict(kind=0, N=1, D=8, H=16, W=16, cin=4, cout=64, act=1)),
+    ("brick_c32_24", dict(kind=0, N=1, D=8, H=16, W=8, cin=32, cout=24)),
+    ("brick_stats", dict(kind=0, N=2, D=8, H=16, W=16, cin=32, cout=64, stats=True)),
+    ("brick_slices", dict(kind=0, N=1, D=8, H=16, W=16, cin=32, cout=32, in_extra=32, out_extra=32, out_coff=32)),
+    ("brick_many_units", dict(kind=0, N=3, D=32, H=48, W=40, cin=32, cout=32, act=1)),
+    ("brick_many_units_stream", dict(kind=0, N=3, D=16, H=48, W=40, cin=64, cout=64, act=1)),
+    ("perfb_4_32_128", dict(kind=0, N=2, D=128, H=128, W=128, cin=4, cout=32, act=1, time_it=True)),
+    ("perfb_32_32_128", dict(kind=0, N=2, D=128, H=128, W=128, cin=32, cout=32, act=1, time_it=True)),
+    ("perfb_64_32_128", dict(kind=0, N=2, D=128, H=128, W=128, cin=64, cout=32, act=1, time_it=True)),
+    ("perfb_64_64_128", dict(kind=0, N=2, D=128, H=128, W=128, cin=64, cout=64, act=1, time_it=True)),
+    ("perfb_128_64_128", dict(kind=0, N=1, D=128, H=128, W=128, cin=128, cout=64, act=1, time_it=True)),
+    ("perfb_64_64_64", dict(kind=0, N=8, D=64, H=64, W=64, cin=64, cout=64, act=1, time_it=True)),
+    ("perfb_128_64_64", dict(kind=0, N=8, D=64, H=64, W=64, cin=128, cout=64, act=1, time_it=True)),
+    ("perft_32_32_128", dict(kind=0, N=2, D=128, H=128, W=128, cin=32, cout=32, act=1, time_it=True, algo=0)),
+    ("perft_64_64_128", dict(kind=0, N=2, D=128, H=128, W=128, cin=64, cout=64, act=1, time_it=True, algo=0)),
+    ("perft_128_64_128", dict(kind=0, N=1, D=128, H=128, W=128, cin=128, cout=64, act=1, time_it=True, algo=0)),
+    ("perf_32_32_128", dict(kind=0, N=1, D=128, H=128, W=128, cin=32, cout=32, act=1, time_it=True, algo=0)),
+    ("perf_32_32_128_nokhs", dict(kind=0, N=1, D=128, H=128, W=128, cin=32, cout=32, act=1, khshift=0, time_it=True, algo=0)),
+    ("perf_64_32_128", dict(kind=0, N=1, D=128, H=128, W=128, cin=64, cout=32, act=1, time_it=True, algo=0)),
+    ("perf_64_64_64", dict(kind=0, N=1, D=64, H=64, W=64, cin=64, cout=64, act=1, time_it=True, algo=0)),
     ("perf_128_128_32", dict(kind=0, N=1, D=32, H=32, W=32, cin=128, cout=128, act=1, time_it=True)),
     ("perf_256_256_16", dict(kind=0, N=1, D=16, H=16, W=16, cin=256, cout=256, act=1, time_it=True)),
     ("perf_320_320_8_b8", dict(kind=0, N=8, D=8, H=8, W=8, cin=320, cout=320, act=1, time_it=True)),
