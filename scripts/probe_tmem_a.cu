@@ -126,6 +126,103 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const __grid_constant__ P
     }
 }
 
+
+// Straight-line issue: GROUP MMAs (or cp + MMAs) per iteration, fully unrolled, one thread, descriptors derived from
+// two bases by compile-time offsets.  MODE 0: SS; 1: TS (one cp feeds NACC MMAs); 2: SS, commit + mbarrier wait after
+// every group (exposes the drain / refill cost of the issue queue).
+template <int N, int MODE, int NACC, int GROUP>
+__global__ void __launch_bounds__(128, 1) unrolled_kernel(const __grid_constant__ Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + 16 * 1024;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 48 * 1024);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 4);
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *slot;
+    const uint32_t tmemA = tmem + 448;
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar[0], 16 * 1024 + 32 * 1024);
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
+                         smem_u32(sA)),
+                     "l"(reinterpret_cast<uint64_t>(&p.mapA)), "r"(smem_u32(&bar[0])), "r"(0), "r"(0)
+                     : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
+                         smem_u32(sB)),
+                     "l"(reinterpret_cast<uint64_t>(&p.mapB)), "r"(smem_u32(&bar[0])), "r"(0), "r"(0)
+                     : "memory");
+        mbar_wait(&bar[0], 0);
+        tc_fence_after();
+        const uint32_t idesc = make_idesc_bf16(128, N);
+        const uint64_t dbase = make_smem_desc(0, 1024, kLayoutSW128);
+        const uint64_t abase = dbase | static_cast<uint64_t>(smem_u32(sA) >> 4);
+        const uint64_t bbase = dbase | static_cast<uint64_t>(smem_u32(sB) >> 4);
+        uint32_t parity = 0;
+        const long long t0 = clock64();
+        for (int it = 0; it < p.iters; ++it) {
+#pragma unroll
+            for (int g = 0; g < GROUP; ++g) {
+                const int k = g % 4;
+                const uint64_t ad = abase + 2 * k;
+                const uint64_t bd = bbase + 2 * k;
+                if (MODE == 1) {
+                    utccp_128x256b(tmemA + 8 * k, ad);
+#pragma unroll
+                    for (int j = 0; j < NACC; ++j) umma_bf16_ts(tmem + j * N, tmemA + 8 * k, bd, idesc, 1u);
+                } else {
+                    umma_bf16(tmem + (g % NACC) * N, ad, bd, idesc, 1u);
+                }
+            }
+            if (MODE == 2) {
+                umma_commit(&bar[1]);
+                mbar_wait(&bar[1], parity);
+                parity ^= 1u;
+            }
+        }
+        if (MODE != 2) {
+            umma_commit(&bar[1]);
+            mbar_wait(&bar[1], 0);
+        }
+        const long long t1 = clock64();
+        p.cycles[blockIdx.x] = t1 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+template <int N, int MODE, int NACC, int GROUP>
+static void run_unrolled(Params p, const char* name, long long* dcyc) {
+    CK(cudaFuncSetAttribute(unrolled_kernel<N, MODE, NACC, GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    for (int grid : {1, 148}) {
+        p.iters = 300;
+        unrolled_kernel<N, MODE, NACC, GROUP><<<grid, 128, 64 * 1024>>>(p);
+        CK(cudaDeviceSynchronize());
+        std::vector<long long> cyc(grid);
+        CK(cudaMemcpy(cyc.data(), dcyc, grid * 8, cudaMemcpyDeviceToHost));
+        long long mx = 0;
+        for (long long v : cyc) mx = v > mx ? v : mx;
+        const int mmas = MODE == 1 ? GROUP * NACC : GROUP;
+        printf("unrolled grid %3d %-28s: %7.1f cycles per MMA (ideal tensor %5.1f)%s\n", grid, name,
+               (double)mx / p.iters / mmas, N / 2.0, MODE == 1 ? " [+1 cp per NACC MMAs]" : "");
+    }
+}
+
 static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
     void* fp = nullptr;
     cudaDriverEntryPointQueryResult q;
@@ -194,7 +291,25 @@ int main() {
                 }
             printf("correctness %s N=%d: max err %g %s\n", mode ? "TS(cp)" : "SS", N, maxerr, maxerr < 1e-3 ? "ok" : "MISMATCH");
         }
-    // ---- timing
+
+    // ---- straight-line issue
+    run_unrolled<16, 0, 1, 24>(p, "SS N=16 1acc x24", dcyc);
+    run_unrolled<32, 0, 1, 24>(p, "SS N=32 1acc x24", dcyc);
+    run_unrolled<32, 0, 3, 24>(p, "SS N=32 3acc x24", dcyc);
+    run_unrolled<64, 0, 1, 24>(p, "SS N=64 1acc x24", dcyc);
+    run_unrolled<96, 0, 1, 24>(p, "SS N=96 1acc x24", dcyc);
+    run_unrolled<128, 0, 1, 24>(p, "SS N=128 1acc x24", dcyc);
+    run_unrolled<256, 0, 1, 24>(p, "SS N=256 1acc x24", dcyc);
+    run_unrolled<32, 1, 3, 8>(p, "TS N=32 cp+3 x8", dcyc);
+    run_unrolled<32, 1, 6, 4>(p, "TS N=32 cp+6 x4", dcyc);
+    run_unrolled<32, 1, 1, 24>(p, "TS N=32 cp+1 x24", dcyc);
+    run_unrolled<64, 1, 3, 8>(p, "TS N=64 cp+3 x8", dcyc);
+    run_unrolled<128, 1, 3, 8>(p, "TS N=128 cp+3 x8", dcyc);
+    run_unrolled<32, 2, 1, 6>(p, "SS N=32 commit+wait every 6", dcyc);
+    run_unrolled<32, 2, 1, 18>(p, "SS N=32 commit+wait every 18", dcyc);
+    run_unrolled<64, 2, 1, 12>(p, "SS N=64 commit+wait every 12", dcyc);
+    run_unrolled<256, 2, 1, 4>(p, "SS N=256 commit+wait every 4", dcyc);
+    // ---- timing (rolled loop)
     struct Cfg {
         const char* name;
         int mode, N, nacc;
