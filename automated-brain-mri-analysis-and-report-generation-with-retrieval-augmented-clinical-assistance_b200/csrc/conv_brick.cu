@@ -2,15 +2,19 @@
 // (reference: model_architecture/generic_UNet.py:56,69 — the full- and half-resolution conv blocks, where the
 // activations are large and the channel counts small).
 //
-// The plain tile kernel (conv_tc.cu) re-reads every activation box 9x and the whole 27-tap weight set once per 128
-// output voxels; at Cout = 32 / 64 that L2 -> shared-memory traffic, not the tensor pipe, bounds it.  Here a CTA owns
-// a brick of P output planes whose fp32 accumulators all sit in TMEM (P x NT columns, two bricks in flight), so
+// Measured on B200 (profiles/r01_probe_umma_issue_rates.log): a tcgen05.mma with M = 128 costs max(N/2, ~45) cycles,
+// whether A comes from shared memory or TMEM — at N = Cout = 32 the tensor pipe can never be more than 36 % busy, and
+// the plain tile kernel (conv_tc.cu) additionally re-reads every activation box 9x and all 27 weight taps per 128
+// output voxels.  Here a CTA owns a brick of P output planes (8 w x 16 h voxels each) whose fp32 accumulators sit side
+// by side in TMEM, plane q at column (P-1-q)*NT, so that
+//   * the three kd taps of one (kh, kw, channel step) become ONE MMA of N = 3*NT: input plane p feeds output planes
+//     p, p-1, p-2 through weights [W(kd=0) | W(kd=1) | W(kd=2)] — N = 96 / 192 instead of 32 / 64;
 //   * one activation box (8 w x 18 h haloed rows of ONE input plane, one kw shift, one channel chunk) is loaded once
-//     and used by the nine (kd, kh) taps that touch it: 3 output planes x 3 row-shifted descriptors;
-//   * weights are staged as per-phase slabs (phase = (channel chunk, kw): 9 taps x NT x CC) that stay resident in
-//     shared memory for the whole launch when all phases fit, else stream through two buffers once per brick.
-// Roles: warp 0 activation TMA producer, warp 1 MMA issuer (one elected lane), warps 2..5 epilogue (one TMEM lane
-// quadrant each), warp 6 weight-slab TMA producer.
+//     and serves the nine (kd, kh) taps it takes part in (kh through row-shifted descriptors);
+//   * weights are staged as per-phase slabs (phase = (channel chunk, kw): 9 taps x NT x CC, laid out [kh][kd][NT][CC])
+//     that stay resident in shared memory for the whole launch when all phases fit, else stream through two buffers.
+// Roles: warp 0 activation TMA producer, warp 1 MMA issuer (one thread), warps 2..5 epilogue (one TMEM lane quadrant
+// each), warp 6 weight-slab TMA producer.
 #include "bsg_ptx.cuh"
 #include "conv_brick.cuh"
 #include "conv_epilogue.cuh"
@@ -109,8 +113,7 @@ __global__ void __launch_bounds__(kBrickThreads, 1) conv_brick_kernel(const __gr
                 for (int ph = 0; ph < nphases; ++ph) {
                     const int c = ph / 3, kw = ph - c * 3;
                     for (int p = 0; p < P + 2; ++p) {
-                        const int d = t.d0 + p - 1;
-                        if (d < 0 || d >= a.D) continue;  // zero plane: contributes nothing, never issued
+                        const int d = t.d0 + p - 1;  // d = -1 / D: the box is all out of bounds -> zeros (conv padding)
                         mbar_wait(&empty_bar[stage], phase ^ 1u);
                         mbar_expect_tx(&full_bar[stage], a.a_tx_bytes);
                         tma_load_5d(stages + static_cast<size_t>(stage) * a.a_stage_bytes, &a.mapA, &full_bar[stage],
@@ -140,84 +143,78 @@ __global__ void __launch_bounds__(kBrickThreads, 1) conv_brick_kernel(const __gr
                     const int c = ph / 3, kw = ph - c * 3;
                     uint8_t* dst = slabs + static_cast<size_t>(buf) * a.slab_bytes;
                     mbar_expect_tx(&wfull_bar[buf], a.slab_bytes);
-                    for (int kd = 0; kd < 3; ++kd)
-                        tma_load_3d(dst + kd * 3 * kTapBytes, &a.mapW, &wfull_bar[buf], c * CC, 0, (kd * 3 + kw) * 3);
+                    for (int kh = 0; kh < 3; ++kh)  // box (CC, NT, 1, 1, 3 kd) -> [kd][NT][CC] behind each kh
+                        tma_load_5d(dst + kh * 3 * kTapBytes, &a.mapW, &wfull_bar[buf], c * CC, 0, kh, kw, 0);
                 }
             }
         }
     } else if (warp == 1) {
-        // =========================================================== MMA issuer
-        const bool leader = elect_one();
-        const uint32_t idesc = make_idesc_bf16(128, NT);
-        const uint64_t desc_base = make_smem_desc(0, kAtom, kLayout);
-        const uint32_t stages16 = smem_u32(stages) >> 4, slabs16 = smem_u32(slabs) >> 4;
-        const uint32_t stage16 = a.a_stage_bytes >> 4, slab16 = a.slab_bytes >> 4;
-        int stage = 0;
-        uint32_t phase = 0, su = 0, tcount = 0;
-        for (int u = blockIdx.x; u < units; u += gridDim.x, ++tcount) {
-            const Unit t = decode_unit(a, u, P);
-            const uint32_t bb = tcount & 1u, par = (tcount >> 1) & 1u;
-            uint32_t started = 0;  // bit q: accumulator q of this brick already holds a partial sum
-            for (int ph = 0; ph < nphases; ++ph, ++su) {
-                uint32_t buf;
-                if (resident) {
-                    buf = static_cast<uint32_t>(ph);
-                    if (tcount == 0) mbar_wait(&wfull_bar[buf], 0u);
-                } else {
-                    buf = su % static_cast<uint32_t>(a.nslabbuf);
-                    mbar_wait(&wfull_bar[buf], (su / static_cast<uint32_t>(a.nslabbuf)) & 1u);
-                }
-                tc_fence_after();
-                const uint32_t sb16 = slabs16 + buf * slab16;
-                for (int p = 0; p < P + 2; ++p) {
-                    const int d = t.d0 + p - 1;
-                    if (d < 0 || d >= a.D) continue;
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t sa16 = stages16 + static_cast<uint32_t>(stage) * stage16;
+        // =========================================================== MMA issuer (one elected thread runs the whole
+        // role: inside elect.sync the compiler knows the code is warp-uniform and emits straight UTCHMMA sequences)
+        if (elect_one()) {
+            const uint32_t idesc1 = make_idesc_bf16(128, NT), idesc2 = make_idesc_bf16(128, 2 * NT),
+                           idesc3 = make_idesc_bf16(128, 3 * NT);
+            const uint64_t desc_base = make_smem_desc(0, kAtom, kLayout);
+            const uint32_t stages16 = smem_u32(stages) >> 4, slabs16 = smem_u32(slabs) >> 4;
+            const uint32_t stage16 = a.a_stage_bytes >> 4, slab16 = a.slab_bytes >> 4;
+            constexpr uint32_t kTap16 = kTapBytes >> 4, kAtom16 = kAtom >> 4;
+            int stage = 0;
+            uint32_t phase = 0, su = 0, tcount = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x, ++tcount) {
+                const uint32_t bb = tcount & 1u, par = (tcount >> 1) & 1u;
+                const uint32_t tm_brick = tmem_base + bb * (P * NT);
+                for (int ph = 0; ph < nphases; ++ph, ++su) {
+                    uint32_t buf;
+                    if (resident) {
+                        buf = static_cast<uint32_t>(ph);
+                        if (tcount == 0) mbar_wait(&wfull_bar[buf], 0u);
+                    } else {
+                        buf = su % static_cast<uint32_t>(a.nslabbuf);
+                        mbar_wait(&wfull_bar[buf], (su / static_cast<uint32_t>(a.nslabbuf)) & 1u);
+                    }
+                    const uint32_t sb16 = slabs16 + buf * slab16;
+                    for (int p = 0; p < P + 2; ++p) {
+                        // input plane p feeds output planes q = p - kd, kd in [kd_lo, kd_hi]; their accumulators are
+                        // adjacent TMEM column blocks in ascending kd order starting at plane q_hi = p - kd_lo
+                        const int kd_lo = p > P - 1 ? p - (P - 1) : 0;
+                        const int kd_hi = p < 2 ? p : 2;
+                        const int nblk = kd_hi - kd_lo + 1;
+                        const uint32_t d_tmem = tm_brick + static_cast<uint32_t>(P - 1 - (p - kd_lo)) * NT;
+                        const uint32_t idesc = nblk == 3 ? idesc3 : (nblk == 2 ? idesc2 : idesc1);
+                        const bool fresh = (ph == 0) && (p < P);  // plane q = p receives its first contribution here
+                        if (fresh) mbar_wait(&tempty_bar[bb * P + p], par ^ 1u);  // epilogue has drained the slot
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sa16 = stages16 + static_cast<uint32_t>(stage) * stage16;
+                        const uint32_t sbk16 = sb16 + static_cast<uint32_t>(kd_lo) * kTap16;
 #pragma unroll
-                    for (int kd = 0; kd < 3; ++kd) {
-                        const int q = p - kd;  // output plane fed by input plane p through tap row kd
-                        if (q < 0 || q >= P) continue;
-                        const uint32_t slot = bb * P + static_cast<uint32_t>(q);
-                        const uint32_t have = (started >> q) & 1u;
-                        if (!have) {  // first touch of this TMEM slot in this brick: the epilogue must have drained it
-                            mbar_wait(&tempty_bar[slot], par ^ 1u);
-                            tc_fence_after();
-                        }
-                        if (leader) {
-                            const uint32_t d_tmem = tmem_base + slot * NT;
+                        for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
-                            for (int kh = 0; kh < 3; ++kh) {
-#pragma unroll
-                                for (int k = 0; k < CC / 16; ++k) {
-                                    const uint64_t ad = desc_base | static_cast<uint64_t>(sa16 + ((kh * kAtom + k * 32) >> 4));
-                                    const uint64_t bd = desc_base | static_cast<uint64_t>(
-                                                                        sb16 + (((kd * 3 + kh) * kTapBytes + k * 32) >> 4));
-                                    umma_bf16(d_tmem, ad, bd, idesc, (kh | k) != 0 ? 1u : have);
+                            for (int k = 0; k < CC / 16; ++k) {
+                                const uint64_t ad = desc_base | static_cast<uint64_t>(sa16 + kh * kAtom16 + 2 * k);
+                                const uint64_t bd = desc_base | static_cast<uint64_t>(sbk16 + kh * 3 * kTap16 + 2 * k);
+                                if (kh == 0 && k == 0 && fresh) {
+                                    // the new plane's block must overwrite, the older planes' blocks accumulate: split
+                                    umma_bf16(d_tmem, ad, bd, idesc1, 0u);
+                                    if (nblk > 1)
+                                        umma_bf16(d_tmem + NT, ad, bd + kTap16, nblk == 3 ? idesc2 : idesc1, 1u);
+                                } else {
+                                    umma_bf16(d_tmem, ad, bd, idesc, 1u);
                                 }
                             }
                         }
-                        started |= 1u << q;
-                    }
-                    if (leader) {
                         umma_commit(&empty_bar[stage]);  // frees the activation slot once these MMAs have read it
-                        if (ph == nphases - 1) {
-                            // planes whose last contribution was just issued
-                            if (p >= 2 && p - 2 < P) umma_commit(&tfull_bar[bb * P + (p - 2)]);
-                            if (d + 1 >= a.D && p >= 1 && p - 1 < P) umma_commit(&tfull_bar[bb * P + (p - 1)]);
+                        if (ph == nphases - 1 && p >= 2) umma_commit(&tfull_bar[bb * P + (p - 2)]);  // plane p-2 done
+                        if (++stage == a.nstages) {
+                            stage = 0;
+                            phase ^= 1u;
                         }
                     }
-                    __syncwarp();
-                    if (++stage == a.nstages) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
+                    if (!resident) umma_commit(&wempty_bar[buf]);
                 }
-                if (!resident && leader) umma_commit(&wempty_bar[buf]);
-                __syncwarp();
             }
         }
+        __syncwarp();
     } else {
         // =========================================================== epilogue (4 warps, one TMEM lane quadrant each)
         const int q4 = warp & 3;
@@ -231,10 +228,19 @@ __global__ void __launch_bounds__(kBrickThreads, 1) conv_brick_kernel(const __gr
         epi.act = a.act;
         epi.slope = a.slope;
         epi.out_f16 = a.out_f16;
+        StatAcc sacc[NT / 32];
+#pragma unroll
+        for (int j = 0; j < NT / 32; ++j) sacc[j].s1 = sacc[j].s2 = 0.f;
+        int stat_n = -1;  // batch item the running statistics belong to
         uint32_t tcount = 0;
         for (int u = blockIdx.x; u < units; u += gridDim.x, ++tcount) {
             const Unit t = decode_unit(a, u, P);
             const uint32_t bb = tcount & 1u, par = (tcount >> 1) & 1u;
+            if (a.stats != nullptr && t.n != stat_n) {
+#pragma unroll
+                for (int j = 0; j < NT / 32; ++j) flush_stats(epi, sacc[j], j * 32, lane, stat_n);
+                stat_n = t.n;
+            }
             __nv_bfloat16* obase = a.out + t.n * a.os_n + static_cast<long long>(t.h0 + ih) * a.os_h +
                                    static_cast<long long>(t.w0 + iw) * a.os_w + a.out_c_off;
             for (int q = 0; q < P; ++q) {
@@ -242,18 +248,22 @@ __global__ void __launch_bounds__(kBrickThreads, 1) conv_brick_kernel(const __gr
                 mbar_wait(&tfull_bar[slot], par);
                 tc_fence_after();
                 __nv_bfloat16* orow = obase + static_cast<long long>(t.d0 + q) * a.os_d;
-                const uint32_t t_addr = tmem_base + slot * NT + (static_cast<uint32_t>(q4 * 32) << 16);
+                const uint32_t t_addr = tmem_base + (bb * P + static_cast<uint32_t>(P - 1 - q)) * NT + (static_cast<uint32_t>(q4 * 32) << 16);
 #pragma unroll
                 for (int cb = 0; cb < NT; cb += 32) {
                     uint32_t v[32];
                     tmem_ld_32x32(t_addr + cb, v);
                     tmem_ld_wait();
-                    epilogue_32cols(v, epi, cb, true, lane, t.n, orow);
+                    epilogue_32cols(v, epi, cb, true, lane, sacc[cb / 32], orow);
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[slot]);
             }
+        }
+        if (a.stats != nullptr) {
+#pragma unroll
+            for (int j = 0; j < NT / 32; ++j) flush_stats(epi, sacc[j], j * 32, lane, stat_n);
         }
     }
 

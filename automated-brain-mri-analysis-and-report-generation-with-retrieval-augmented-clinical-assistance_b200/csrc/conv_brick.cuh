@@ -8,13 +8,14 @@
 namespace bsg {
 
 // One work unit = a brick of P consecutive output planes (8 w x 16 h voxels each, one batch item).  All P fp32
-// accumulators of a brick live in TMEM at once (2 bricks double-buffered = 512 columns), so every activation box
-// that TMA brings in (8 x 18 haloed rows of one input plane, one kw shift, one 16/32/64-channel chunk) feeds all
-// nine (kd, kh) taps it takes part in, and the weights sit in shared memory as per-phase slabs
-// (phase = (channel chunk, kw); 9 taps x Cout x CC each) that stay resident when all of them fit.
+// accumulators of a brick live side by side in TMEM (2 bricks double-buffered = 512 columns), so every activation
+// box that TMA brings in (8 x 18 haloed rows of one input plane, one kw shift, one 16/32/64-channel chunk) feeds all
+// nine (kd, kh) taps it takes part in — the three kd taps as ONE MMA of N = 3*NT over adjacent accumulators — and
+// the weights sit in shared memory as per-phase slabs (phase = (channel chunk, kw); 9 taps x Cout x CC each) that
+// stay resident when all of them fit.
 struct BrickArgs {
     CUtensorMap mapA;  // 5-D (C, W, H, D, N) activations, box (CC, 8, 18, 1, 1), OOB zero fill = conv padding
-    CUtensorMap mapW;  // 3-D (Cin_pad, Cout_pad, 27 taps in (kd, kw, kh) order), box (CC, NT, 3)
+    CUtensorMap mapW;  // 5-D (Cin_pad, Cout_pad, kh, kw, kd) view of the 27-tap weights, box (CC, NT, 1, 1, 3)
     int tw, th, tb, tn;  // unit grid: W/8, H/16, D/P, batch
     int P;               // planes per brick = 256 / NT
     int D;

@@ -18,10 +18,28 @@ struct EpiParams {
     int out_f16;         // 1: store IEEE fp16 instead of bf16
 };
 
+// Per-lane running norm statistics of one 32-column chunk: after the transpose-reduce lane l owns channel co + l.
+// They stay in registers across tiles and go to global memory (one atomicAdd pair per lane) only when the batch item
+// or the channel block changes: per-tile atomics on the [N][C][2] table serialise in L2 (measured: +2.5..4.8 ms per
+// full-resolution layer).
+struct StatAcc {
+    float s1, s2;
+};
+
+__device__ __forceinline__ void flush_stats(const EpiParams& e, StatAcc& acc, int co, int lane, int n) {
+    if (co + lane < e.cout && n >= 0 && n < e.No && (acc.s1 != 0.f || acc.s2 != 0.f)) {
+        float* sp = e.stats + (static_cast<long long>(n) * e.cout + co + lane) * 2;
+        atomicAdd(sp, acc.s1);
+        atomicAdd(sp + 1, acc.s2);
+    }
+    acc.s1 = 0.f;
+    acc.s2 = 0.f;
+}
+
 // v: the 32 accumulator columns [co, co+32) of this thread's voxel; orow: the voxel's first output channel;
-// n: batch index of the voxel (shared by the whole warp); valid: voxel inside the tensor.
+// valid: voxel inside the tensor; acc: this lane's running statistics for the chunk (used when e.stats != null).
 __device__ __forceinline__ void epilogue_32cols(const uint32_t (&v)[32], const EpiParams& e, int co, bool valid, int lane,
-                                                int n, __nv_bfloat16* orow) {
+                                                StatAcc& acc, __nv_bfloat16* orow) {
     float f[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + e.sbias[co + i];
@@ -47,13 +65,8 @@ __device__ __forceinline__ void epilogue_32cols(const uint32_t (&v)[32], const E
                 s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
             }
         }
-        // lane l now owns channel co + l; rows of one warp always share the batch index n
-        const int nn = __shfl_sync(0xffffffffu, n, 0);
-        if (co + lane < e.cout && nn < e.No) {
-            float* sp = e.stats + (static_cast<long long>(nn) * e.cout + co + lane) * 2;
-            atomicAdd(sp, s1[0]);
-            atomicAdd(sp + 1, s2[0]);
-        }
+        acc.s1 += s1[0];
+        acc.s2 += s2[0];
     }
     if (e.act == 1) {
 #pragma unroll

@@ -110,10 +110,13 @@ int plan_brick(const bsg_conv_desc* d, bsg_conv_plan* p) {
     uint32_t box[5] = {static_cast<uint32_t>(cc), 8u, 18u, 1u, 1u};
     int rc = encode_map(&a.mapA, d->in, 5, dims, str, box, cc);
     if (rc != BSG_OK) return rc;
-    uint64_t wdims[3] = {static_cast<uint64_t>(d->cin), static_cast<uint64_t>(cout_pad), 27ull};
-    uint64_t wstr[2] = {static_cast<uint64_t>(d->cin) * 2, static_cast<uint64_t>(d->cin) * 2 * cout_pad};
-    uint32_t wbox[3] = {static_cast<uint32_t>(cc), static_cast<uint32_t>(cout_pad), 3u};
-    rc = encode_map(&a.mapW, d->weights, 3, wdims, wstr, wbox, cc);
+    // weights [27 taps (kd, kw, kh)][cout_pad][cin] seen as (cin, row, kh, kw, kd): a box of the 3 kd taps of one
+    // (kh, kw) lands as [kd][cout_pad][cc] = the B operand of one N = 3*cout_pad MMA
+    const uint64_t tap_bytes = static_cast<uint64_t>(d->cin) * 2 * cout_pad;
+    uint64_t wdims[5] = {static_cast<uint64_t>(d->cin), static_cast<uint64_t>(cout_pad), 3ull, 3ull, 3ull};
+    uint64_t wstr[4] = {static_cast<uint64_t>(d->cin) * 2, tap_bytes, tap_bytes * 3, tap_bytes * 9};
+    uint32_t wbox[5] = {static_cast<uint32_t>(cc), static_cast<uint32_t>(cout_pad), 1u, 1u, 3u};
+    rc = encode_map(&a.mapW, d->weights, 5, wdims, wstr, wbox, cc);
     if (rc != BSG_OK) return rc;
 
     a.out = static_cast<__nv_bfloat16*>(d->out);

@@ -211,12 +211,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         epi.act = a.act;
         epi.slope = a.slope;
         epi.out_f16 = a.out_f16;
+        // running norm statistics of the (up to 8) 32-column chunks of the current N tile, flushed when the batch item
+        // of this warp's rows or the N tile changes (rows of one warp always share the batch index)
+        StatAcc sacc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sacc[j].s1 = sacc[j].s2 = 0.f;
+        int stat_n = -1, stat_nt = 0;
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
             const TileCoord t = decode_tile(a, tile);
             const uint32_t acc = tcount & 1u;
             const uint32_t acc_phase = (tcount >> 1) & 1u;
             const int w = t.w0 + iw, h = t.h0 + ih, d = t.d0 + id, n = t.n0 + in;
+            if (a.stats != nullptr) {
+                const int n_warp = __shfl_sync(0xffffffffu, n, 0);
+                if (n_warp != stat_n || t.nt != stat_nt) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) flush_stats(epi, sacc[j], stat_nt * a.ntile + j * 32, lane, stat_n);
+                    stat_n = n_warp;
+                    stat_nt = t.nt;
+                }
+            }
             const bool valid = (w < a.Wo) && (h < a.Ho) && (d < a.Do) && (n < a.No);
             const int q0 = t.nt * a.ntile;  // first GEMM column of this tile
             __nv_bfloat16* obase = a.out + n * a.os_n + a.out_c_off;
@@ -226,7 +241,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + acc * static_cast<uint32_t>(a.ntile) + (static_cast<uint32_t>(q * 32) << 16);
-            for (int cb = 0; cb < a.ntile; cb += 32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int cb = j * 32;
+                if (cb >= a.ntile) break;
                 uint32_t v[32];
                 tmem_ld_32x32(t_addr + cb, v);
                 tmem_ld_wait();
@@ -240,11 +258,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                            static_cast<long long>(2 * h + ((par >> 1) & 1)) * a.os_h +
                            static_cast<long long>(2 * w + (par & 1)) * a.os_w;
                 }
-                epilogue_32cols(v, epi, co, valid, lane, n, orow);
+                epilogue_32cols(v, epi, co, valid, lane, sacc[j], orow);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+        if (a.stats != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) flush_stats(epi, sacc[j], stat_nt * a.ntile + j * 32, lane, stat_n);
         }
     }
 

@@ -50,9 +50,6 @@ def simulate(P, D, nchunks, nslabbuf, nstages, units_of_cta, seed, async_commit=
         for (ui, d0) in units_of_cta:
             for ph in range(nphases):
                 for p in range(P + 2):
-                    d = d0 + p - 1
-                    if d < 0 or d >= D:
-                        continue
                     yield from wait(empty[stage], phase ^ 1)
                     assert stage_data[stage] is None, "activation stage overwritten while in use"
                     stage_data[stage] = (ui, ph, p)
@@ -89,7 +86,6 @@ def simulate(P, D, nchunks, nslabbuf, nstages, units_of_cta, seed, async_commit=
         stage, phase, su, tcount = 0, 0, 0, 0
         for (ui, d0) in units_of_cta:
             bb, par = tcount & 1, (tcount >> 1) & 1
-            started = 0
             for ph in range(nphases):
                 if resident:
                     buf = ph
@@ -100,35 +96,29 @@ def simulate(P, D, nchunks, nslabbuf, nstages, units_of_cta, seed, async_commit=
                     yield from wait(wfull[buf], (su // nslabbuf) & 1)
                 assert slab_data[buf] == ph, f"slab {slab_data[buf]} != phase {ph}"
                 for p in range(P + 2):
-                    d = d0 + p - 1
-                    if d < 0 or d >= D:
-                        continue
+                    kd_lo, kd_hi = max(0, p - (P - 1)), min(2, p)
+                    fresh = ph == 0 and p < P
+                    if fresh:
+                        slot = bb * P + p
+                        yield from wait(tempty[slot], par ^ 1)
+                        assert acc[slot] is None, "TMEM slot reused before the epilogue drained it"
+                        acc[slot] = set()
                     yield from wait(full[stage], phase)
                     assert stage_data[stage] == (ui, ph, p), f"stage holds {stage_data[stage]}, want {(ui, ph, p)}"
-                    for kd in range(3):
-                        q = p - kd
-                        if q < 0 or q >= P:
-                            continue
-                        slot = bb * P + q
-                        if not (started >> q) & 1:
-                            yield from wait(tempty[slot], par ^ 1)
-                            assert acc[slot] is None, "TMEM slot reused before the epilogue drained it"
-                            acc[slot] = set()
+                    for kd in range(kd_lo, kd_hi + 1):  # one wide-N MMA per (kh, k): column blocks kd_lo..kd_hi
+                        slot = bb * P + (p - kd)
+                        assert acc[slot] is not None, "accumulating into a slot that was never started"
                         for kh in range(3):
                             key = (ph, kd, kh)
                             assert key not in acc[slot]
                             acc[slot].add(key)
-                        started |= 1 << q
 
                     def free_stage(s=stage):
                         stage_data[s] = None
                         empty[s].arrive()
                     commit(free_stage)
-                    if ph == nphases - 1:
-                        if 0 <= p - 2 < P:
-                            commit(lambda s=bb * P + p - 2: tfull[s].arrive())
-                        if d + 1 >= D and 0 <= p - 1 < P:
-                            commit(lambda s=bb * P + p - 1: tfull[s].arrive())
+                    if ph == nphases - 1 and p >= 2:
+                        commit(lambda s=bb * P + p - 2: tfull[s].arrive())
                     stage += 1
                     if stage == nstages:
                         stage, phase = 0, phase ^ 1
@@ -148,8 +138,7 @@ def simulate(P, D, nchunks, nslabbuf, nstages, units_of_cta, seed, async_commit=
             for q in range(P):
                 slot = bb * P + q
                 yield from wait(tfull[slot], par)
-                want = {(ph, kd, kh) for ph in range(nphases) for kd in range(3) for kh in range(3)
-                        if 0 <= d0 + q + kd - 1 < D}
+                want = {(ph, kd, kh) for ph in range(nphases) for kd in range(3) for kh in range(3)}
                 assert acc[slot] == want, f"unit {ui} plane {q}: {len(acc[slot] or ())} of {len(want)} contributions"
                 if widx == 0:
                     done_planes.append((ui, q))
