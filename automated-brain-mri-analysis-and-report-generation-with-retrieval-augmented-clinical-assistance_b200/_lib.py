@@ -24,7 +24,7 @@ class ConvDesc(C.Structure):
         ("cout", C.c_int), ("out_ptr", C.c_void_p), ("out_ctot", C.c_int), ("out_coff", C.c_int),
         ("weights", C.c_void_p), ("bias", C.c_void_p),
         ("act", C.c_int), ("slope", C.c_float), ("stats", C.c_void_p), ("out_f16", C.c_int),
-        ("use_khshift", C.c_int), ("max_ctas", C.c_int), ("algo", C.c_int),
+        ("use_khshift", C.c_int), ("max_ctas", C.c_int), ("in_f16", C.c_int), ("algo", C.c_int),
     ]
 
 
@@ -71,10 +71,10 @@ _EXTRA_SIGS = {
     "bsg_joint_hist_u8": [_vp, _vp, _sz, _vp, _vp, _vp],
     "bsg_ccl26_stats": [_vp, _i, _i, _i, _u32, _vp, _vp, _vp, _i, _vp, _sz, _vp],
     "bsg_masked_moments": [_vp, _i, _i, _i, C.POINTER(_u32), _i, _u32, _vp, _vp],
-    "bsg_gather_patch_tta": [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(_i), _i, _vp, _i, _vp],
+    "bsg_gather_patch_tta": [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(_i), _i, _vp, _i, _i, _vp],
     "bsg_norm_finalize": [_vp, _i, _i, _i, _d, _f, _vp, _vp, _vp, _vp],
-    "bsg_norm_apply_lrelu": [_vp, _sz, _i, _i, _i, _i, _vp, _f, _i, _vp],
-    "bsg_head_tta_accumulate": [_vp, _i, _i, _i, _i, _i, C.POINTER(_i), _i, _f, C.POINTER(_f), C.POINTER(_f), _i, _i,
+    "bsg_norm_apply_lrelu": [_vp, _sz, _i, _i, _i, _i, _vp, _f, _i, _i, _vp],
+    "bsg_head_tta_accumulate": [_vp, _i, _i, _i, _i, _i, _i, C.POINTER(_i), _i, _f, C.POINTER(_f), C.POINTER(_f), _i, _i,
                                 _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "bsg_finalize": [C.POINTER(_vp), _i, _vp, _i, _sz, _i, C.POINTER(_i), _vp, _vp, _vp],
 }

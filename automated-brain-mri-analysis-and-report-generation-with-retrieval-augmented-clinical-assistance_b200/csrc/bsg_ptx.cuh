@@ -146,15 +146,18 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 // layout type codes
 constexpr uint32_t kLayoutSW128 = 2, kLayoutSW64 = 4, kLayoutSW32 = 6;
 
-// Instruction descriptor, kind::f16: bf16 x bf16 -> fp32, both operands K-major.
-__host__ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
+// Instruction descriptor, kind::f16: (bf16 | fp16) x (same) -> fp32, both operands K-major.
+// f16 = 0: operands are bf16; 1: IEEE fp16 (same tensor-pipe rate, 10-bit mantissa, narrower range).
+__host__ __device__ __forceinline__ uint32_t make_idesc_16(uint32_t M, uint32_t N, int f16) {
+    const uint32_t fmt = f16 ? 0u : 1u;
     uint32_t d = 0;
     d |= 1u << 4;          // C format: F32
-    d |= 1u << 7;          // A format: BF16
-    d |= 1u << 10;         // B format: BF16
+    d |= fmt << 7;         // A format: 0 F16, 1 BF16
+    d |= fmt << 10;        // B format
     d |= (N >> 3) << 17;   // N, 3 LSBs dropped
     d |= (M >> 4) << 24;   // M, 4 LSBs dropped
     return d;
 }
+__host__ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t M, uint32_t N) { return make_idesc_16(M, N, 0); }
 
 }  // namespace bsg

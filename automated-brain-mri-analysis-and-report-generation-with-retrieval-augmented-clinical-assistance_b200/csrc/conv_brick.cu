@@ -13,8 +13,10 @@
 //     and serves the nine (kd, kh) taps it takes part in (kh through row-shifted descriptors);
 //   * weights are staged as per-phase slabs (phase = (channel chunk, kw): 9 taps x NT x CC, laid out [kh][kd][NT][CC])
 //     that stay resident in shared memory for the whole launch when all phases fit, else stream through two buffers.
-// Roles: warp 0 activation TMA producer, warp 1 MMA issuer (one thread), warps 2..5 epilogue (one TMEM lane quadrant
-// each), warp 6 weight-slab TMA producer.
+// Roles: warps 0..3 epilogue (TMEM lane quadrant = warp id), warp 4 activation TMA producer, warp 5 weight-slab TMA
+// producer, warp 6 MMA issuer (one thread).  The issuer is the highest warp id of its scheduler partition: the
+// warp arbiter favours the highest id, so the latency-critical tcgen05.mma stream is never queued behind the
+// instruction-heavy epilogue warp it shares the partition with.
 #include "bsg_ptx.cuh"
 #include "conv_brick.cuh"
 #include "conv_epilogue.cuh"
@@ -70,7 +72,7 @@ __global__ void __launch_bounds__(kBrickThreads, 1) conv_brick_kernel(const __gr
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 4 && lane == 0) {
         tma_prefetch_desc(&a.mapW);
         tma_prefetch_desc(&a.mapA);
         for (int s = 0; s < kMaxStages; ++s) {
@@ -87,12 +89,12 @@ __global__ void __launch_bounds__(kBrickThreads, 1) conv_brick_kernel(const __gr
         }
         fence_barrier_init();
     }
-    if (warp == 1) {
+    if (warp == 6) {
         tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
     }
-    if (warp >= 2 && warp < 6) {
-        for (int i = threadIdx.x - 64; i < NT; i += 128) sbias[i] = (a.bias != nullptr) ? a.bias[i] : 0.f;
+    if (warp < 4) {
+        for (int i = threadIdx.x; i < NT; i += 128) sbias[i] = (a.bias != nullptr) ? a.bias[i] : 0.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__(kBrickThreads, 1) conv_brick_kernel(const __gr
     const int nphases = a.nphases;
     const bool resident = a.nslabbuf >= nphases;
 
-    if (warp == 0) {
+    if (warp == 4) {
         // =========================================================== activation producer
         if (elect_one()) {
             int stage = 0;
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(kBrickThreads, 1) conv_brick_kernel(const __gr
                 }
             }
         }
-    } else if (warp == 6) {
+    } else if (warp == 5) {
         // =========================================================== weight-slab producer
         if (elect_one()) {
             uint32_t su = 0;  // slab uses so far
@@ -148,12 +150,12 @@ __global__ void __launch_bounds__(kBrickThreads, 1) conv_brick_kernel(const __gr
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 6) {
         // =========================================================== MMA issuer (one elected thread runs the whole
         // role: inside elect.sync the compiler knows the code is warp-uniform and emits straight UTCHMMA sequences)
         if (elect_one()) {
-            const uint32_t idesc1 = make_idesc_bf16(128, NT), idesc2 = make_idesc_bf16(128, 2 * NT),
-                           idesc3 = make_idesc_bf16(128, 3 * NT);
+            const uint32_t idesc1 = make_idesc_16(128, NT, a.in_f16), idesc2 = make_idesc_16(128, 2 * NT, a.in_f16),
+                           idesc3 = make_idesc_16(128, 3 * NT, a.in_f16);
             const uint64_t desc_base = make_smem_desc(0, kAtom, kLayout);
             const uint32_t stages16 = smem_u32(stages) >> 4, slabs16 = smem_u32(slabs) >> 4;
             const uint32_t stage16 = a.a_stage_bytes >> 4, slab16 = a.slab_bytes >> 4;
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(kBrickThreads, 1) conv_brick_kernel(const __gr
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 6) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }

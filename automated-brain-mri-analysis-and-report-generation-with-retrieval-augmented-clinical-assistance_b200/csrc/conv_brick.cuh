@@ -36,6 +36,7 @@ struct BrickArgs {
     int act;
     float* stats;
     int out_f16;
+    int in_f16;  // 1: activations and weights are IEEE fp16 instead of bf16
 };
 
 constexpr int kBrickThreads = 224;

@@ -93,7 +93,9 @@ int plan_brick(const bsg_conv_desc* d, bsg_conv_plan* p) {
     a.a_tx_bytes = 8u * 18u * cc * 2u;
     a.a_stage_bytes = round_up(a.a_tx_bytes, 1024);
     a.slab_bytes = 9u * cout_pad * cc * 2u;
-    const uint32_t avail = 227 * 1024 - 1024 - 1280;
+    // leave ~8 KB of the SM's shared memory unclaimed: the HBM-bound elementwise kernels of the other stream lane
+    // (norm apply, gather, head) need their 1 KB system reservation each to become co-resident with this CTA
+    const uint32_t avail = 227 * 1024 - 1024 - 1280 - 8192;
     if (a.nphases <= 6 && static_cast<uint64_t>(a.nphases) * a.slab_bytes + 3ull * a.a_stage_bytes <= avail)
         a.nslabbuf = a.nphases;  // resident
     else if (2ull * a.slab_bytes + 2ull * a.a_stage_bytes <= avail)
@@ -132,6 +134,7 @@ int plan_brick(const bsg_conv_desc* d, bsg_conv_plan* p) {
     a.act = d->act;
     a.stats = d->stats;
     a.out_f16 = d->out_f16;
+    a.in_f16 = d->in_f16;
 
     p->brick = 1;
     p->brick_cc = cc;
@@ -262,7 +265,7 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
     while (a.tmem_cols < static_cast<uint32_t>(2 * a.ntile)) a.tmem_cols *= 2;
 
     // kh halo reuse: needs the canonical 8 x 16 x 1 x 1 box, stride 1, 27 taps and >= 3 pipeline stages
-    const uint32_t budget = 227 * 1024 - 4096;  // barriers + bias + alignment slack
+    const uint32_t budget = 227 * 1024 - 4096 - 6144;  // barriers + bias + alignment slack + room for co-resident CTAs
     auto stage_bytes = [&](int khs, uint32_t* ab, uint32_t* bb) {
         const uint32_t rows = khs ? static_cast<uint32_t>((a.bh + 2) * 8) : 128u;
         *ab = round_up(rows * a.cc * 2, 1024);
@@ -339,6 +342,7 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
     a.act = d->act;
     a.stats = d->stats;
     a.out_f16 = d->out_f16;
+    a.in_f16 = d->in_f16;
 
     const int total_tiles = a.tn * a.td * a.th * a.tw * a.n_ntiles;
     int max_ctas = d->max_ctas > 0 ? d->max_ctas : sm_count_cached();

@@ -1,9 +1,12 @@
 // tcgen05 / TMEM / TMA implicit-GEMM kernel for the 3-D conv stacks of Generic_UNet
 // (reference: model_architecture/generic_UNet.py:56,69 Conv3d k3; :285-288 stride-2 conv pooling; :363-364
 // ConvTranspose3d k2 s2).  Persistent, warp-specialised:
-//   warp 0      TMA producer   (activation halo boxes + weight slabs -> swizzled smem ring)
-//   warp 1      MMA issuer     (one elected lane, tcgen05.mma kind::f16, fp32 accumulators in TMEM, 2 buffers)
-//   warps 2..5  epilogue       (tcgen05.ld -> bias / LeakyReLU / norm statistics -> bf16 channels-last stores)
+//   warps 0..3  epilogue       (tcgen05.ld -> bias / LeakyReLU / norm statistics -> 16-bit channels-last stores;
+//                               TMEM lane quadrant = warp id)
+//   warp 4      TMA producer   (activation halo boxes + weight slabs -> swizzled smem ring)
+//   warp 5      MMA issuer     (one elected lane, tcgen05.mma kind::f16, fp32 accumulators in TMEM, 2 buffers); the
+//                               highest warp id of its scheduler partition, which the warp arbiter favours over the
+//                               instruction-heavy epilogue warp sharing it
 #include <cuda_fp16.h>
 #include "bsg_ptx.cuh"
 #include "conv_epilogue.cuh"
@@ -56,7 +59,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 4 && lane == 0) {
         tma_prefetch_desc(&a.mapW);
         tma_prefetch_desc(&a.mapA[0]);
         for (int s = 0; s < a.nstages; ++s) {
@@ -69,13 +72,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
         fence_barrier_init();
     }
-    if (warp == 1) {
+    if (warp == 5) {
         tmem_alloc(tmem_slot, a.tmem_cols);
         tmem_relinquish();
     }
-    if (warp >= 2) {
-        for (int i = threadIdx.x - 64; i < a.cout_pad; i += kThreads - 64)
-            sbias[i] = (a.bias != nullptr) ? a.bias[i] : 0.f;
+    if (warp < 4) {
+        for (int i = threadIdx.x; i < a.cout_pad; i += 128) sbias[i] = (a.bias != nullptr) ? a.bias[i] : 0.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     constexpr uint32_t kSbo = 8u * kRowBytes;
     const int nstages = a.nstages;
 
-    if (warp == 0) {
+    if (warp == 4) {
         // =========================================================== TMA producer
         if (elect_one()) {
             int stage = 0;
@@ -148,28 +150,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 }
             }
         }
-    } else if (warp == 1) {
-        // =========================================================== MMA issuer
-        const uint32_t idesc = make_idesc_bf16(128, static_cast<uint32_t>(a.ntile));
-        constexpr uint32_t kLayout = (CC == 64) ? kLayoutSW128 : (CC == 32 ? kLayoutSW64 : kLayoutSW32);
-        // descriptor = constant high word | (start address >> 4): only the low word moves between MMAs
-        const uint64_t desc_base = make_smem_desc(0, kSbo, kLayout);
-        const uint32_t b_tap16 = (static_cast<uint32_t>(a.ntile) * kRowBytes) >> 4;
-        const uint32_t smem0_16 = smem_u32(smem) >> 4;
-        const uint32_t stage16 = stage_bytes >> 4, a16 = a.a_stage_bytes >> 4;
-        int stage = 0;
-        uint32_t phase = 0;
-        uint32_t tcount = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-            const uint32_t acc = tcount & 1u;
-            const uint32_t acc_phase = (tcount >> 1) & 1u;
-            mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * static_cast<uint32_t>(a.ntile);
-            for (int ks = 0; ks < ksteps; ++ks) {
-                mbar_wait(&full_bar[stage], phase);
+    } else if (warp == 5) {
+        // =========================================================== MMA issuer (one elected thread runs the whole
+        // role: inside elect.sync the compiler emits straight UTCHMMA sequences without per-stage reconvergence waits)
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_16(128, static_cast<uint32_t>(a.ntile), a.in_f16);
+            constexpr uint32_t kLayout = (CC == 64) ? kLayoutSW128 : (CC == 32 ? kLayoutSW64 : kLayoutSW32);
+            // descriptor = constant high word | (start address >> 4): only the low word moves between MMAs
+            const uint64_t desc_base = make_smem_desc(0, kSbo, kLayout);
+            const uint32_t b_tap16 = (static_cast<uint32_t>(a.ntile) * kRowBytes) >> 4;
+            const uint32_t smem0_16 = smem_u32(smem) >> 4;
+            const uint32_t stage16 = stage_bytes >> 4, a16 = a.a_stage_bytes >> 4;
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t tcount = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+                const uint32_t acc = tcount & 1u;
+                const uint32_t acc_phase = (tcount >> 1) & 1u;
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
                 tc_fence_after();
-                if (elect_one()) {
+                const uint32_t d_tmem = tmem_base + acc * static_cast<uint32_t>(a.ntile);
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
                     const uint32_t sa16 = smem0_16 + static_cast<uint32_t>(stage) * stage16;
                     const uint32_t sb16 = sa16 + a16;
 #pragma unroll
@@ -183,14 +186,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     }
                     umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
                     if (ks == ksteps - 1) umma_commit(&tfull_bar[acc]);
-                }
-                __syncwarp();
-                if (++stage == nstages) {
-                    stage = 0;
-                    phase ^= 1u;
+                    if (++stage == nstages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
                 }
             }
         }
+        __syncwarp();
     } else {
         // =========================================================== epilogue (4 warps, one TMEM lane quadrant each)
         const int q = warp & 3;
@@ -272,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 5) {
         tc_fence_after();
         tmem_dealloc(tmem_base, a.tmem_cols);
     }

@@ -26,7 +26,7 @@ struct MirrorSet {
 __global__ void __launch_bounds__(kThreads) gather_patch_kernel(const float* __restrict__ vol, int C, int Z, int Y,
                                                                 int X, int z0, int y0, int x0, int P0, int P1, int P2,
                                                                 const MirrorSet ms, __nv_bfloat16* __restrict__ out,
-                                                                int cpad) {
+                                                                int cpad, int out_f16) {
     const size_t pv = static_cast<size_t>(P0) * P1 * P2;
     const size_t total = pv * ms.n;
     const size_t plane = static_cast<size_t>(Z) * Y * X;
@@ -52,8 +52,13 @@ __global__ void __launch_bounds__(kThreads) gather_patch_kernel(const float* __r
                 const int ca = c0 + 2 * k, cb = ca + 1;
                 const float fa = ca < C ? __ldg(src + ca * plane) : 0.f;
                 const float fb = cb < C ? __ldg(src + cb * plane) : 0.f;
-                __nv_bfloat162 p = __floats2bfloat162_rn(fa, fb);
-                pk[k] = *reinterpret_cast<uint32_t*>(&p);
+                if (out_f16) {
+                    __half2 p = __floats2half2_rn(fa, fb);
+                    pk[k] = *reinterpret_cast<uint32_t*>(&p);
+                } else {
+                    __nv_bfloat162 p = __floats2bfloat162_rn(fa, fb);
+                    pk[k] = *reinterpret_cast<uint32_t*>(&p);
+                }
             }
             *reinterpret_cast<uint4*>(dst + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
@@ -92,41 +97,59 @@ __global__ void norm_finalize_kernel(const float* __restrict__ stats, int N, int
     scale_shift[static_cast<size_t>(i) * 2 + 1] = static_cast<float>(be - mean * ga * rstd);
 }
 
-// in place on a channel slice [coff, coff+C) of a (N, V, ctot) bf16 buffer: x <- lrelu(x*scale + shift)
-__global__ void __launch_bounds__(kThreads) norm_apply_kernel(__nv_bfloat16* __restrict__ x, size_t V, int N, int C,
-                                                              int ctot, int coff,
-                                                              const float* __restrict__ scale_shift, float slope,
-                                                              int in_f16) {
+// in place on a channel slice [coff, coff+C) of a (N, V, ctot) 16-bit buffer: x <- lrelu(x*scale + shift).
+// One 16-byte group (8 channels) per thread and step.  The launch makes the thread stride a multiple of the groups
+// per voxel, so a thread keeps the SAME 8 channels of the SAME batch item (blockIdx.y) for its whole run: its 16
+// scale/shift values live in registers and the loop body is one load, 8 FMAs, one store — no index division.
+template <bool IN_F16, bool OUT_F16>
+__global__ void __launch_bounds__(kThreads) norm_apply_kernel(__nv_bfloat16* __restrict__ x, size_t V, int C, int ctot,
+                                                              int coff, const float* __restrict__ scale_shift,
+                                                              float slope) {
     const int c8n = C / 8;
-    const size_t total = static_cast<size_t>(N) * V * c8n;
-    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const int c8 = static_cast<int>(i % c8n);
-        const size_t nv = i / c8n;
-        const int n = static_cast<int>(nv / V);
-        uint4* p = reinterpret_cast<uint4*>(x + nv * ctot + coff + c8 * 8);
+    const int n = blockIdx.y;
+    const size_t j0 = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;  // multiple of c8n (host guarantees it)
+    const int c8 = static_cast<int>(j0 % c8n);
+    size_t v = j0 / c8n;
+    const size_t vstep = stride / c8n;
+    float sc[8], sh[8];
+    {
+        const float2* ss = reinterpret_cast<const float2*>(scale_shift + (static_cast<size_t>(n) * C + c8 * 8) * 2);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float2 t = __ldg(ss + k);
+            sc[k] = t.x;
+            sh[k] = t.y;
+        }
+    }
+    uint4* p = reinterpret_cast<uint4*>(x + (static_cast<size_t>(n) * V + v) * ctot + coff + c8 * 8);
+    const size_t pstep = vstep * ctot / 8;  // uint4 units
+    for (; v < V; v += vstep, p += pstep) {
         uint4 u = *p;
         uint32_t w[4] = {u.x, u.y, u.z, u.w};
-        const float4* ss = reinterpret_cast<const float4*>(scale_shift + (static_cast<size_t>(n) * C + c8 * 8) * 2);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const float4 s = __ldg(ss + k);  // (scale0, shift0, scale1, shift1)
             float a, b;
-            if (in_f16) {
-                const float2 v = __half22float2(*reinterpret_cast<__half2*>(&w[k]));
-                a = v.x;
-                b = v.y;
+            if (IN_F16) {
+                const float2 t = __half22float2(*reinterpret_cast<__half2*>(&w[k]));
+                a = t.x;
+                b = t.y;
             } else {
-                const __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&w[k]);
-                a = __bfloat162float(v.x);
-                b = __bfloat162float(v.y);
+                const __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&w[k]);
+                a = __bfloat162float(t.x);
+                b = __bfloat162float(t.y);
             }
-            a = a * s.x + s.y;
-            b = b * s.z + s.w;
+            a = fmaf(a, sc[2 * k], sh[2 * k]);
+            b = fmaf(b, sc[2 * k + 1], sh[2 * k + 1]);
             a = a > 0.f ? a : a * slope;
             b = b > 0.f ? b : b * slope;
-            __nv_bfloat162 o = __floats2bfloat162_rn(a, b);
-            w[k] = *reinterpret_cast<uint32_t*>(&o);
+            if (OUT_F16) {
+                __half2 o = __floats2half2_rn(a, b);
+                w[k] = *reinterpret_cast<uint32_t*>(&o);
+            } else {
+                __nv_bfloat162 o = __floats2bfloat162_rn(a, b);
+                w[k] = *reinterpret_cast<uint32_t*>(&o);
+            }
         }
         *p = make_uint4(w[0], w[1], w[2], w[3]);
     }
@@ -145,7 +168,7 @@ struct HeadParams {
 
 __global__ void __launch_bounds__(kThreads) head_tta_accumulate_kernel(
     const __nv_bfloat16* __restrict__ feat, int ctot, int P0, int P1, int P2, const MirrorSet ms,
-    const __grid_constant__ HeadParams hp, const float* __restrict__ gauss, float* __restrict__ acc, int Z, int Y, int X,
+    const __grid_constant__ HeadParams hp, const int feat_f16, const float* __restrict__ gauss, float* __restrict__ acc, int Z, int Y, int X,
     int z0, int y0, int x0) {
     const size_t pv = static_cast<size_t>(P0) * P1 * P2;
     const size_t plane = static_cast<size_t>(Z) * Y * X;
@@ -177,9 +200,15 @@ __global__ void __launch_bounds__(kThreads) head_tta_accumulate_kernel(
                 float f[8];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&ww[k]);
-                    f[2 * k] = __bfloat162float(b2.x);
-                    f[2 * k + 1] = __bfloat162float(b2.y);
+                    if (feat_f16) {
+                        const float2 h2 = __half22float2(*reinterpret_cast<const __half2*>(&ww[k]));
+                        f[2 * k] = h2.x;
+                        f[2 * k + 1] = h2.y;
+                    } else {
+                        const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&ww[k]);
+                        f[2 * k] = __bfloat162float(b2.x);
+                        f[2 * k + 1] = __bfloat162float(b2.y);
+                    }
                 }
 #pragma unroll
                 for (int k = 0; k < kMaxClasses; ++k) {
@@ -292,7 +321,7 @@ using namespace bsg;
 extern "C" {
 
 int bsg_gather_patch_tta(const float* vol, int C, int Z, int Y, int X, int z0, int y0, int x0, int P0, int P1, int P2,
-                         const int* mirror_codes_host, int nmirrors, void* out_bf16, int cpad, void* stream) {
+                         const int* mirror_codes_host, int nmirrors, void* out_bf16, int cpad, int out_f16, void* stream) {
     BSG_REQUIRE(vol != nullptr && out_bf16 != nullptr, "null argument");
     BSG_REQUIRE(cpad % 8 == 0 && cpad >= C, "cpad %d must be a multiple of 8 and >= C=%d", cpad, C);
     BSG_REQUIRE(z0 >= 0 && y0 >= 0 && x0 >= 0 && z0 + P0 <= Z && y0 + P1 <= Y && x0 + P2 <= X,
@@ -302,7 +331,7 @@ int bsg_gather_patch_tta(const float* vol, int C, int Z, int Y, int X, int z0, i
     if (rc != BSG_OK) return rc;
     const size_t total = static_cast<size_t>(P0) * P1 * P2 * nmirrors;
     gather_patch_kernel<<<grid_for(total, kThreads, 16), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        vol, C, Z, Y, X, z0, y0, x0, P0, P1, P2, ms, static_cast<__nv_bfloat16*>(out_bf16), cpad);
+        vol, C, Z, Y, X, z0, y0, x0, P0, P1, P2, ms, static_cast<__nv_bfloat16*>(out_bf16), cpad, out_f16);
     BSG_CUDA_OK(cudaGetLastError());
     return BSG_OK;
 }
@@ -318,17 +347,39 @@ int bsg_norm_finalize(const float* stats, int N, int C, int groups, double count
 }
 
 int bsg_norm_apply_lrelu(void* x_bf16, size_t voxels_per_item, int N, int C, int ctot, int coff,
-                         const float* scale_shift, float slope, int in_f16, void* stream) {
+                         const float* scale_shift, float slope, int in_f16, int out_f16, void* stream) {
     BSG_REQUIRE(x_bf16 != nullptr && scale_shift != nullptr, "null argument");
     BSG_REQUIRE(C % 8 == 0 && ctot % 8 == 0 && coff % 8 == 0, "channel counts must be multiples of 8");
-    const size_t total = static_cast<size_t>(N) * voxels_per_item * (C / 8);
-    norm_apply_kernel<<<grid_for(total, kThreads, 16), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<__nv_bfloat16*>(x_bf16), voxels_per_item, N, C, ctot, coff, scale_shift, slope, in_f16);
+    // thread stride = blocks * 256 must be a multiple of the 16-byte groups per voxel (C / 8)
+    const int c8n = C / 8;
+    int g = c8n, r = kThreads;  // gcd(c8n, 256)
+    while (r != 0) {
+        const int t = g % r;
+        g = r;
+        r = t;
+    }
+    const int unit = c8n / g;  // smallest block count whose thread total is a multiple of c8n
+    const size_t groups = voxels_per_item * static_cast<size_t>(c8n);
+    size_t blocks = (groups + kThreads - 1) / kThreads;
+    const size_t cap = static_cast<size_t>(sm_count_cached()) * 16 / (N > 0 ? N : 1) + 1;
+    if (blocks > cap) blocks = cap;
+    blocks = (blocks + unit - 1) / unit * unit;
+    dim3 grid(static_cast<unsigned>(blocks), static_cast<unsigned>(N));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    __nv_bfloat16* xp = static_cast<__nv_bfloat16*>(x_bf16);
+    if (in_f16 && out_f16)
+        norm_apply_kernel<true, true><<<grid, kThreads, 0, st>>>(xp, voxels_per_item, C, ctot, coff, scale_shift, slope);
+    else if (in_f16)
+        norm_apply_kernel<true, false><<<grid, kThreads, 0, st>>>(xp, voxels_per_item, C, ctot, coff, scale_shift, slope);
+    else if (out_f16)
+        norm_apply_kernel<false, true><<<grid, kThreads, 0, st>>>(xp, voxels_per_item, C, ctot, coff, scale_shift, slope);
+    else
+        norm_apply_kernel<false, false><<<grid, kThreads, 0, st>>>(xp, voxels_per_item, C, ctot, coff, scale_shift, slope);
     BSG_CUDA_OK(cudaGetLastError());
     return BSG_OK;
 }
 
-int bsg_head_tta_accumulate(const void* feat_bf16, int cfeat, int ctot, int P0, int P1, int P2,
+int bsg_head_tta_accumulate(const void* feat_bf16, int feat_f16, int cfeat, int ctot, int P0, int P1, int P2,
                             const int* mirror_codes_host, int nmirrors, float mirror_weight,
                             const float* head_w_host, const float* head_b_host, int ncls, int nonlin,
                             const float* gauss, float* acc, int Z, int Y, int X, int z0, int y0, int x0,
@@ -356,7 +407,7 @@ int bsg_head_tta_accumulate(const void* feat_bf16, int cfeat, int ctot, int P0, 
     }
     const size_t pv = static_cast<size_t>(P0) * P1 * P2;
     head_tta_accumulate_kernel<<<grid_for(pv, kThreads, 64), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(feat_bf16), ctot, P0, P1, P2, ms, hp, gauss, acc, Z, Y, X, z0, y0, x0);
+        static_cast<const __nv_bfloat16*>(feat_bf16), ctot, P0, P1, P2, ms, hp, feat_f16, gauss, acc, Z, Y, X, z0, y0, x0);
     BSG_CUDA_OK(cudaGetLastError());
     return BSG_OK;
 }

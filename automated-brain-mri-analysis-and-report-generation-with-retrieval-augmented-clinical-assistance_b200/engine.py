@@ -1,12 +1,16 @@
 """B200 execution engine for Generic_UNet: turns the module tree into a fixed sequence of sm_100a kernel launches.
 
-Data layout in HBM: every activation is a channels-last (N, D, H, W, C) bf16 tensor.  The skip connection of level d
+Data layout in HBM: every activation is a channels-last (N, D, H, W, C) 16-bit tensor — bf16 when the norms are
+eval-mode BatchNorm folded into the conv weights (unbounded range), IEEE fp16 for the InstanceNorm / GroupNorm stacks
+(activations bounded by the normalisation; same tensor-pipe rate and bytes, 3 more mantissa bits: the type the
+reference's own CUDA path computes in under torch.cuda.amp.autocast).  The skip connection of level d
 and the transposed-conv output that is concatenated with it (generic_UNet.py:435-438) share one buffer of 2*C
 channels — the encoder conv writes channels [C, 2C), the transposed conv writes [0, C) — so `torch.cat` never runs and
 the first decoder conv reads one tensor.  Eval-mode BatchNorm is folded into the conv weights; InstanceNorm / GroupNorm
 use per-(n, c) sums produced by the conv epilogue and one in-place normalise + LeakyReLU pass.
 """
 import ctypes as C
+import os
 
 import torch
 from torch import nn
@@ -51,17 +55,24 @@ class UNetEngine:
         div = [int(v) for v in net.input_shape_must_be_divisible_by]
         if any(p % d for p, d in zip(self.patch, div)):
             raise ValueError(f"patch size {self.patch} must be divisible by {div}")
+        norms = [m for m in net.modules() if isinstance(m, (nn.InstanceNorm3d, nn.GroupNorm))]
+        mode = os.environ.get("BSG_ACT_DTYPE", "auto").lower()  # auto | bf16 | fp16
+        if mode not in ("auto", "bf16", "fp16"):
+            raise ValueError(f"BSG_ACT_DTYPE={mode!r}: expected auto, bf16 or fp16")
+        self.f16 = (1 if norms else 0) if mode == "auto" else int(mode == "fp16")
+        self.act_dtype = torch.float16 if self.f16 else torch.bfloat16
         self.steps = []       # callables, in launch order
         self.step_info = []   # per step: name, algorithmic flops, plan geometry (diagnostics / bench breakdown)
         self.keep = []        # tensors the plans point at
         self.launches_per_forward = 0
         self.flops = 0.0
+        self.sub_events = None  # scripts/diag_case.py: events recorded between a conv and its norm passes
         self.event_log = None  # bench.py: list collecting (start, end) CUDA events around each run()
         self._build()
 
     # ------------------------------------------------------------------ construction
     def _alloc(self, spatial, c):
-        t = torch.zeros((self.batch,) + tuple(spatial) + (c,), dtype=torch.bfloat16, device=self.device)
+        t = torch.zeros((self.batch,) + tuple(spatial) + (c,), dtype=self.act_dtype, device=self.device)
         self.keep.append(t)
         return t
 
@@ -88,7 +99,7 @@ class UNetEngine:
         else:
             raise NotImplementedError(f"norm {type(norm).__name__}")
         cin_pad = src.c
-        wp = P.pack_conv3_weight(w, cin_pad)
+        wp = P.pack_conv3_weight(w, cin_pad, self.act_dtype)
         bp = P.pad_bias(b, cout).to(self.device)
         self.keep += [wp, bp]
         d, h, wd = spatial_in
@@ -96,7 +107,7 @@ class UNetEngine:
                           in_ptr=src.ptr(), in_ctot=src.ctot, cout=cout, out_ptr=dst.buf.data_ptr(),
                           out_ctot=dst.ctot, out_coff=dst.coff, weights=wp.data_ptr(), bias=bp.data_ptr(), act=act,
                           slope=slope, stats=stats.data_ptr() if stats is not None else None,
-                          out_f16=1 if stats is not None else 0, use_khshift=-1,
+                          out_f16=1 if (stats is not None or self.f16) else 0, in_f16=self.f16, use_khshift=-1,
                           max_ctas=0)
         self.flops += plan.info().flops
         self._note(f"conv3 s{stride} {cin_pad}->{cout} @{'x'.join(map(str, spatial_in))}"
@@ -121,22 +132,26 @@ class UNetEngine:
             sp = L.stream_ptr(stream)
             stats.zero_()
             plan.run(stream)
+            if self.sub_events is not None:  # diagnostics: split the step into conv | norm passes
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                self.sub_events.append(ev)
             L.check(lib.bsg_norm_finalize(_ptr(stats), self.batch, cout, groups, float(vox), eps, gp, bp2, _ptr(ss), sp))
             L.check(lib.bsg_norm_apply_lrelu(_ptr(dst.buf), vox, self.batch, cout, dst.ctot, dst.coff, _ptr(ss), slope, 1,
-                                             sp))
+                                             self.f16, sp))
 
         self.steps.append(run)
         self.launches_per_forward += 4
 
     def _add_tu(self, tu, src, dst, spatial_in):
         w = tu.weight.detach().to(self.device, torch.float32)
-        wp = P.pack_convT2_weight(w, src.c)
+        wp = P.pack_convT2_weight(w, src.c, self.act_dtype)
         self.keep.append(wp)
         d, h, wd = spatial_in
         plan = L.ConvPlan(kind=L.BSG_CONVT_K2S2, stride=1, N=self.batch, D=d, H=h, W=wd, cin=src.c, in_ptr=src.ptr(),
                           in_ctot=src.ctot, cout=w.shape[1], out_ptr=dst.buf.data_ptr(), out_ctot=dst.ctot,
                           out_coff=dst.coff, weights=wp.data_ptr(), bias=None, act=L.BSG_ACT_NONE, slope=0.0,
-                          stats=None, use_khshift=0, max_ctas=0)
+                          stats=None, out_f16=self.f16, in_f16=self.f16, use_khshift=0, max_ctas=0)
         self.flops += plan.info().flops
         self._note(f"convT2 {src.c}->{w.shape[1]} @{'x'.join(map(str, spatial_in))}", plan)
         self.steps.append(plan.run)
@@ -217,7 +232,7 @@ class UNetEngine:
         if n > self.batch or tuple(x.shape[2:]) != self.patch:
             raise ValueError("input does not match the engine geometry")
         self.x.buf.zero_()
-        self.x.buf[:n, ..., :self.in_channels] = x.to(self.device).permute(0, 2, 3, 4, 1).to(torch.bfloat16)
+        self.x.buf[:n, ..., :self.in_channels] = x.to(self.device).permute(0, 2, 3, 4, 1).to(self.act_dtype)
         self.run()
         f = self.features.view()[:n].float()  # (n, d, h, w, c)
         logits = torch.einsum("ndhwc,kc->nkdhw", f, self.head_w.to(self.device))

@@ -17,19 +17,28 @@ class SegmentationNetwork(nn.Module):
         self.num_classes = None
         self.inference_apply_nonlin = lambda x: x  # upstream default; trainers install sigmoid / softmax_helper
         self._engines = {}
-        self.engine_batch = 8
+        self.engine_batch = 8  # (tile, mirror) forwards in flight, split evenly over `engine_lanes` CUDA streams
+        self.engine_lanes = 2  # >1: HBM-bound passes of one lane overlap the tensor-bound convs of the other
 
     # ------------------------------------------------------------------ engine cache
-    def engine_for(self, patch_size, batch=None):
+    def engine_for(self, patch_size, batch=None, slot=0):
+        """Cached UNetEngine for a patch size / batch; `slot` distinguishes the engines of concurrent stream lanes."""
         from . import _lib as L
         from .engine import UNetEngine
         if not torch.cuda.is_available():
             raise L.BsgError("brainseg_b200 needs a CUDA device (sm_100); there is no CPU fallback")
         batch = int(batch or self.engine_batch)
-        key = (tuple(int(p) for p in patch_size), batch, torch.cuda.current_device())
+        key = (tuple(int(p) for p in patch_size), batch, torch.cuda.current_device(), int(slot))
         if key not in self._engines:
             self._engines[key] = UNetEngine(self, key[0], batch)
         return self._engines[key]
+
+    def engines_for(self, patch_size, batch=None, lanes=None):
+        """The lane engines of the sliding-window driver: `lanes` engines of batch/lanes forwards each."""
+        batch = int(batch or self.engine_batch)
+        lanes = max(1, min(int(lanes or self.engine_lanes), batch))
+        per = -(-batch // lanes)
+        return [self.engine_for(patch_size, per, slot) for slot in range(lanes)]
 
     def invalidate_engines(self):
         """Call after loading new weights (load_state_dict / load_checkpoint_ram): packed weights are cached."""
@@ -94,7 +103,7 @@ class SegmentationNetwork(nn.Module):
             vol = torch.nn.functional.pad(vol, (pads[2][0], pads[2][1], pads[1][0], pads[1][1], pads[0][0], pads[0][1]))
         vol = vol.contiguous()
         codes = sliding.mirror_codes_for(mirror_axes, do_mirroring)
-        pred = sliding.SlidingWindowPredictor(self.engine_for(patch), step_size, use_gaussian, codes,
+        pred = sliding.SlidingWindowPredictor(self.engines_for(patch), step_size, use_gaussian, codes,
                                               self._nonlin_name())
         acc = pred.accumulate(vol)
         seg, probs = pred.finalize([acc], tuple(vol.shape[1:]), regions_class_order, want_probs)

@@ -6,34 +6,34 @@ def round_up(x, m):
     return (x + m - 1) // m * m
 
 
-def pack_conv3_weight(w, cin_pad=None):
-    """nn.Conv3d weight (Cout, Cin, kd, kh, kw) -> bf16 [27 taps (kd,kw,kh)][cout_pad][cin_pad]."""
+def pack_conv3_weight(w, cin_pad=None, dtype=torch.bfloat16):
+    """nn.Conv3d weight (Cout, Cin, kd, kh, kw) -> 16-bit [27 taps (kd,kw,kh)][cout_pad][cin_pad]."""
     cout, cin = w.shape[0], w.shape[1]
     cin_pad = cin_pad or round_up(cin, 16)
     cout_pad = round_up(cout, 32)
     p = torch.zeros(27, cout_pad, cin_pad, dtype=torch.float32, device=w.device)
     p[:, :cout, :cin] = w.float().permute(2, 4, 3, 0, 1).reshape(27, cout, cin)
-    return p.to(torch.bfloat16).contiguous()
+    return p.to(dtype).contiguous()
 
 
-def pack_conv1_weight(w, cin_pad=None):
-    """1x1x1 conv weight (Cout, Cin, 1, 1, 1) -> bf16 [1][cout_pad][cin_pad]."""
+def pack_conv1_weight(w, cin_pad=None, dtype=torch.bfloat16):
+    """1x1x1 conv weight (Cout, Cin, 1, 1, 1) -> 16-bit [1][cout_pad][cin_pad]."""
     cout, cin = w.shape[0], w.shape[1]
     cin_pad = cin_pad or round_up(cin, 16)
     cout_pad = round_up(cout, 32)
     p = torch.zeros(1, cout_pad, cin_pad, dtype=torch.float32, device=w.device)
     p[0, :cout, :cin] = w.float().reshape(cout, cin)
-    return p.to(torch.bfloat16).contiguous()
+    return p.to(dtype).contiguous()
 
 
-def pack_convT2_weight(w, cin_pad=None):
-    """nn.ConvTranspose3d k2 s2 weight (Cin, Cout, kd, kh, kw) -> bf16 [1][8 parities (kd,kh,kw) * cout_pad][cin_pad]."""
+def pack_convT2_weight(w, cin_pad=None, dtype=torch.bfloat16):
+    """nn.ConvTranspose3d k2 s2 weight (Cin, Cout, kd, kh, kw) -> 16-bit [1][8 parities (kd,kh,kw) * cout_pad][cin_pad]."""
     cin, cout = w.shape[0], w.shape[1]
     cin_pad = cin_pad or round_up(cin, 16)
     cout_pad = round_up(cout, 32)
     p = torch.zeros(8, cout_pad, cin_pad, dtype=torch.float32, device=w.device)
     p[:, :cout, :cin] = w.float().permute(2, 3, 4, 1, 0).reshape(8, cout, cin)
-    return p.reshape(1, 8 * cout_pad, cin_pad).to(torch.bfloat16).contiguous()
+    return p.reshape(1, 8 * cout_pad, cin_pad).to(dtype).contiguous()
 
 
 def pad_bias(b, cout):

@@ -23,7 +23,7 @@ from .feature_extraction import utils as FU
 class BratsCasePipeline:
     def __init__(self, models, patch_size=(128, 128, 128), step_size=0.5, mirror_axes=(0, 1, 2), do_mirroring=True,
                  use_gaussian=True, regions_class_order=(1, 2, 3), label_format="brats2025", batch=8, rank=0,
-                 world_size=1, reduce_fn=None):
+                 world_size=1, reduce_fn=None, lanes=None):
         """models: drop-in Generic_UNet instances (each may stand for one fold); `reduce_fn(acc)` sums an accumulator
         over ranks when the (tile, mirror) work items of ONE case are sharded (latency mode)."""
         self.models = list(models)
@@ -34,8 +34,8 @@ class BratsCasePipeline:
         codes = sliding.mirror_codes_for(mirror_axes, do_mirroring)
         self.predictors = []
         for net in self.models:
-            eng = net.engine_for(self.patch, batch)
-            self.predictors.append(sliding.SlidingWindowPredictor(eng, step_size, use_gaussian, codes,
+            engs = net.engines_for(self.patch, batch, lanes)
+            self.predictors.append(sliding.SlidingWindowPredictor(engs, step_size, use_gaussian, codes,
                                                                   net._nonlin_name(), rank, world_size))
         self.device = self.predictors[0].device
         self.conv_events = None  # optional: list collecting (start, end, flops) CUDA-event triples per engine run

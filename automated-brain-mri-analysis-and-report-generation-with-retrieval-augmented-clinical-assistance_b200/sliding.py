@@ -81,11 +81,20 @@ def gaussian_importance_map(patch_size, device, sigma_scale=1.0 / 8):
 
 
 class SlidingWindowPredictor:
-    """Tiled prediction of one (C, Z, Y, X) volume with one or more UNetEngines sharing a geometry."""
+    """Tiled prediction of one (C, Z, Y, X) volume.
 
-    def __init__(self, engine, step_size=0.5, use_gaussian=True, mirror_codes=ALL_MIRROR_CODES, nonlin="sigmoid",
+    `engines`: one UNetEngine or a list of them ("lanes") sharing geometry and weights.  Every lane owns a CUDA stream:
+    a chunk of work items is dealt over the lanes, whose gather / conv / norm launches then run concurrently — the
+    HBM-bound passes of one lane (gather, norm apply, head) fill the gaps of the tensor-bound convs of the other.
+    The accumulator updates (head kernels) are chained with events in a fixed order, so the fp32 sums are the same
+    from run to run."""
+
+    def __init__(self, engines, step_size=0.5, use_gaussian=True, mirror_codes=ALL_MIRROR_CODES, nonlin="sigmoid",
                  rank=0, world_size=1):
-        self.engine = engine
+        self.engines = list(engines) if isinstance(engines, (list, tuple)) else [engines]
+        self.engine = self.engines[0]
+        engine = self.engine
+        assert all(e.patch == engine.patch and e.device == engine.device for e in self.engines)
         self.patch = engine.patch
         self.step_size, self.use_gaussian = step_size, use_gaussian
         self.mirror_codes = list(mirror_codes)
@@ -93,7 +102,13 @@ class SlidingWindowPredictor:
         self.rank, self.world_size = rank, world_size
         self.device = engine.device
         self._geom = {}
+        self._streams = None
         self.kernel_launches = 0
+
+    def _lane_streams(self):
+        if self._streams is None:
+            self._streams = [torch.cuda.Stream(self.device) for _ in self.engines] if len(self.engines) > 1 else [None]
+        return self._streams
 
     def geometry(self, shape):
         """Step grid, Gaussian map and the (geometry-only) weight-sum volume for a padded volume shape."""
@@ -119,45 +134,74 @@ class SlidingWindowPredictor:
     def accumulate(self, vol, acc=None, stream=None):
         """vol: fp32 cuda tensor (C, Z, Y, X) with every extent >= patch.  Adds this rank's share of
         sum_tiles gauss * mean_mirrors(nonlin(net(flip(tile)))) into `acc` (fp32 [num_classes, Z, Y, X])."""
-        eng, lib = self.engine, L.lib()
+        eng0, lib = self.engine, L.lib()
         Cn, Z, Y, X = vol.shape
         tiles, gauss, _ = self.geometry((Z, Y, X))
         if acc is None:
-            acc = torch.zeros((eng.num_classes, Z, Y, X), dtype=torch.float32, device=self.device)
-        sp = L.stream_ptr(stream)
+            acc = torch.zeros((eng0.num_classes, Z, Y, X), dtype=torch.float32, device=self.device)
         p0, p1, p2 = self.patch
         pv = p0 * p1 * p2
         items = self.work_items(tiles)
-        B = eng.batch
         weight = 1.0 / len(self.mirror_codes)
-        hw = eng.head_w.numpy().ctypes.data_as(C.POINTER(C.c_float))
-        hb = eng.head_b.numpy().ctypes.data_as(C.POINTER(C.c_float)) if eng.head_b is not None else None
-        cfeat = eng.head_w.shape[1]
-        feat = eng.features
-        for b0 in range(0, len(items), B):
-            chunk = items[b0:b0 + B]
-            # group consecutive items of the same tile: one gather / one head launch per group
-            groups, start = [], 0
+        hw = eng0.head_w.numpy().ctypes.data_as(C.POINTER(C.c_float))
+        hb = eng0.head_b.numpy().ctypes.data_as(C.POINTER(C.c_float)) if eng0.head_b is not None else None
+        cfeat = eng0.head_w.shape[1]
+        gptr = _ptr(gauss) if gauss is not None else None
+
+        def groups_of(chunk):
+            # consecutive items of the same tile: one gather / one head launch per group
+            out, start = [], 0
             for i in range(1, len(chunk) + 1):
                 if i == len(chunk) or chunk[i][0] != chunk[start][0]:
-                    groups.append((start, i))
+                    out.append((start, i))
                     start = i
-            for (s, e) in groups:
-                z, y, x = tiles[chunk[s][0]]
-                codes = (C.c_int * (e - s))(*[m for _, m in chunk[s:e]])
-                out = eng.x.buf.data_ptr() + 2 * s * pv * eng.x.ctot
-                L.check(lib.bsg_gather_patch_tta(_ptr(vol), Cn, Z, Y, X, z, y, x, p0, p1, p2, codes, e - s,
-                                                 C.c_void_p(out), eng.x.ctot, sp))
-            eng.run(stream)
-            for (s, e) in groups:
-                z, y, x = tiles[chunk[s][0]]
-                codes = (C.c_int * (e - s))(*[m for _, m in chunk[s:e]])
-                fptr = feat.buf.data_ptr() + 2 * (s * pv * feat.ctot + feat.coff)
-                L.check(lib.bsg_head_tta_accumulate(C.c_void_p(fptr), cfeat, feat.ctot, p0, p1, p2, codes, e - s,
-                                                    weight, hw, hb, eng.num_classes, self.nonlin,
-                                                    _ptr(gauss) if gauss is not None else None, _ptr(acc), Z, Y, X,
-                                                    z, y, x, sp))
-            self.kernel_launches += 2 * len(groups) + eng.launches_per_forward
+            return out
+
+        main = stream if stream is not None else torch.cuda.current_stream(self.device)
+        lanes = list(zip(self.engines, self._lane_streams()))
+        multi = len(lanes) > 1
+        if multi:
+            ready = torch.cuda.Event()
+            ready.record(main)
+            for _, s in lanes:
+                s.wait_event(ready)  # vol / acc / geometry were produced on the caller's stream
+        head_done = None  # event after the latest accumulator update: the head kernels form one ordered chain
+        pos = 0
+        while pos < len(items):
+            for eng, s in lanes:
+                chunk = items[pos:pos + eng.batch]
+                pos += len(chunk)
+                if not chunk:
+                    break
+                groups = groups_of(chunk)
+                feat = eng.features
+                with torch.cuda.stream(s if multi else main):
+                    sp = L.stream_ptr(None)
+                    for (a, b) in groups:
+                        z, y, x = tiles[chunk[a][0]]
+                        codes = (C.c_int * (b - a))(*[m for _, m in chunk[a:b]])
+                        out = eng.x.buf.data_ptr() + 2 * a * pv * eng.x.ctot
+                        L.check(lib.bsg_gather_patch_tta(_ptr(vol), Cn, Z, Y, X, z, y, x, p0, p1, p2, codes, b - a,
+                                                         C.c_void_p(out), eng.x.ctot, eng.f16, sp))
+                    eng.run(None)
+                    if multi and head_done is not None:
+                        s.wait_event(head_done)
+                    for (a, b) in groups:
+                        z, y, x = tiles[chunk[a][0]]
+                        codes = (C.c_int * (b - a))(*[m for _, m in chunk[a:b]])
+                        fptr = feat.buf.data_ptr() + 2 * (a * pv * feat.ctot + feat.coff)
+                        L.check(lib.bsg_head_tta_accumulate(C.c_void_p(fptr), eng.f16, cfeat, feat.ctot, p0, p1, p2, codes, b - a,
+                                                            weight, hw, hb, eng.num_classes, self.nonlin, gptr,
+                                                            _ptr(acc), Z, Y, X, z, y, x, sp))
+                    if multi:
+                        head_done = torch.cuda.Event()
+                        head_done.record(s)
+                self.kernel_launches += 2 * len(groups) + eng.launches_per_forward
+        if multi:
+            for _, s in lanes:  # join: everything the lanes did is ordered before what the caller does next
+                done = torch.cuda.Event()
+                done.record(s)
+                main.wait_event(done)
         return acc
 
     def finalize(self, accs, shape, regions_class_order=None, want_probs=True, stream=None):

@@ -93,7 +93,7 @@ def joint_hist(pred, gt):
     return h[:256].reshape(16, 16).copy()
 
 
-def ccl26(vol, maskbits=MASK_GT0, stats_cap=4096, want_labels=True):
+def ccl26(vol, maskbits=MASK_GT0, stats_cap=1 << 17, want_labels=True):
     """26-connected labelling in SciPy order.  Returns (labels int32 cuda tensor, ncomp, stats structured array)."""
     assert vol.dim() == 3 and vol.dtype == torch.uint8
     d0, d1, d2 = vol.shape

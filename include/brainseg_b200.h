@@ -71,6 +71,8 @@ typedef struct bsg_conv_desc {
                             bsg_norm_apply_lrelu then rewrites in place as bf16) */
     int use_khshift;     /* -1 auto, 0 off, 1 on: halo reuse of the h taps inside shared memory */
     int max_ctas;        /* 0 = one CTA per SM */
+    int in_f16;          /* 1: activations AND weights are IEEE fp16 instead of bf16 (same tensor-pipe rate; used for the
+                            InstanceNorm / GroupNorm stacks, whose activations are bounded by construction) */
     int algo;            /* -1 auto, 0 tile kernel (one 128-voxel tile per accumulator), 1 brick kernel when the layer
                             suits it (stride-1 k3, Cout <= 64, W % 8 == 0, H % 16 == 0, D % (256/Cout_pad) == 0) */
 } bsg_conv_desc;
@@ -156,28 +158,30 @@ int bsg_masked_moments(const uint8_t* vol, int d0, int d1, int d2, const uint32_
 /* Mirror codes: bit0 = flip x (tensor dim 4), bit1 = flip y (dim 3), bit2 = flip z (dim 2); the upstream order of the
  * 8 TTA passes is codes 0..7. */
 
-/* out[m][d][h][w][c] (bf16, cpad channels, zero padded) = vol[c][z0+fz(d)][y0+fy(h)][x0+fx(w)]: the tile crop
- * data[None, :, lb_x:ub_x, ...] plus torch.flip(x, axes) for every mirror m, written as one channels-last batch. */
+/* out[m][d][h][w][c] (bf16, or fp16 when out_f16 = 1; cpad channels, zero padded) =
+ * vol[c][z0+fz(d)][y0+fy(h)][x0+fx(w)]: the tile crop data[None, :, lb_x:ub_x, ...] plus torch.flip(x, axes) for every
+ * mirror m, written as one channels-last batch. */
 int bsg_gather_patch_tta(const float* vol, int C, int Z, int Y, int X, int z0, int y0, int x0, int P0, int P1, int P2,
-                         const int* mirror_codes_host, int nmirrors, void* out_bf16, int cpad, void* stream);
+                         const int* mirror_codes_host, int nmirrors, void* out16, int cpad, int out_f16, void* stream);
 
 /* InstanceNorm3d / GroupNorm (generic_UNet.py:62-65,72) from the statistics the conv epilogue accumulated:
  * stats [N][C][2] = (sum, sum of squares) over `count` voxels -> scale_shift [N][C][2] with
  * y = x*scale + shift == (x-mean)*rsqrt(var+eps)*gamma + beta.  groups = 0: per channel; > 0: GroupNorm. */
 int bsg_norm_finalize(const float* stats, int N, int C, int groups, double count, float eps, const float* gamma,
                       const float* beta, float* scale_shift, void* stream);
-/* In place on channels [coff, coff+C) of a (N, voxels, ctot) 16-bit buffer: x <- bf16(LeakyReLU(x*scale + shift));
- * in_f16 = 1 when the conv stored its raw output as fp16 (bsg_conv_desc.out_f16). */
+/* In place on channels [coff, coff+C) of a (N, voxels, ctot) 16-bit buffer: x <- LeakyReLU(x*scale + shift), read as
+ * fp16 when in_f16 = 1 (the conv stored its raw output as fp16, bsg_conv_desc.out_f16) else bf16, written back as fp16
+ * when out_f16 = 1 else bf16. */
 int bsg_norm_apply_lrelu(void* x, size_t voxels_per_item, int N, int C, int ctot, int coff,
-                         const float* scale_shift, float slope, int in_f16, void* stream);
+                         const float* scale_shift, float slope, int in_f16, int out_f16, void* stream);
 
 /* Fused tail of one tile: 1x1x1 segmentation head (generic_UNet.py:389-391, weights [ncls][cfeat] + optional bias,
  * HOST pointers), inference_apply_nonlin (0 sigmoid / 1 softmax / 2 identity), un-flip of each mirror's prediction,
  * result += mirror_weight * pred (mirror_weight = 1/num_results of the whole TTA), result *= gaussian,
  * aggregated_results[:, tile] += result.
- * feat: bf16 (nmirrors, P0, P1, P2, ctot) with the cfeat head inputs in channels [0,cfeat) (cfeat % 8 == 0, <= 64);
+ * feat: bf16 (fp16 when feat_f16 = 1) (nmirrors, P0, P1, P2, ctot) with the cfeat head inputs in channels [0,cfeat) (cfeat % 8 == 0, <= 64);
  * acc: fp32 [ncls][Z][Y][X]; gauss: fp32 [P0][P1][P2] or NULL. */
-int bsg_head_tta_accumulate(const void* feat_bf16, int cfeat, int ctot, int P0, int P1, int P2,
+int bsg_head_tta_accumulate(const void* feat16, int feat_f16, int cfeat, int ctot, int P0, int P1, int P2,
                             const int* mirror_codes_host, int nmirrors, float mirror_weight,
                             const float* head_w_host, const float* head_b_host, int ncls, int nonlin,
                             const float* gauss, float* acc, int Z, int Y, int X, int z0, int y0, int x0,

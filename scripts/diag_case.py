@@ -27,16 +27,21 @@ def time_steps(eng, reps=3):
         best = 1e30
         for _ in range(reps):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            eng.sub_events = []
             e0.record()
             step(None)
             e1.record()
             torch.cuda.synchronize()
-            best = min(best, e0.elapsed_time(e1))
+            if e0.elapsed_time(e1) < best:
+                best = e0.elapsed_time(e1)
+                split = f" [conv {e0.elapsed_time(eng.sub_events[0]):.3f} + norm {eng.sub_events[0].elapsed_time(e1):.3f}]" \
+                    if eng.sub_events else ""
+            eng.sub_events = None
         out.append(best)
         info = eng.step_info[i] if hasattr(eng, "step_info") else {}
         fl = info.get("flops", 0.0)
         log(f"  step {i:3d} {info.get('name', ''):40s} {best:8.3f} ms  {fl / best / 1e9 if best > 0 else 0:8.1f} TFLOP/s  "
-            f"{info.get('plan', '')}")
+            f"{info.get('plan', '')}{split}")
     return out
 
 
@@ -117,6 +122,20 @@ def main():
         out = pipe.run_case(vol, gt=gt)
         torch.cuda.synchronize()
         log(f"run_case {i}: {time.time() - t:.3f} s")
+    for lanes in (1, 2):
+        pl = PL.BratsCasePipeline([m1, m2], B.PATCH, 0.5, (0, 1, 2), True, True, (1, 2, 3), "brats2025", batch=batch,
+                                  lanes=lanes)
+        pl.run_case(vol, gt=gt, features=False)
+        torch.cuda.synchronize()
+        for i in range(2):
+            t = time.time()
+            segs = pl.segment(vol)
+            torch.cuda.synchronize()
+            log(f"lanes={lanes}: segment (both models) {time.time() - t:.3f} s")
+        del pl
+        m1.invalidate_engines()
+        m2.invalidate_engines()
+        torch.cuda.empty_cache()
     log("done")
 
 
