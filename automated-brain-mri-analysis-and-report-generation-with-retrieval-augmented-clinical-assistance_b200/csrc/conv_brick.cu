@@ -47,7 +47,9 @@ __device__ __forceinline__ Unit decode_unit(const BrickArgs& a, int u, int P) {
     return t;
 }
 
-template <int CC, int NT>
+// STATS: the epilogue also accumulates the norm statistics (a.stats != null) — a separate instantiation because the
+// per-thread sums cost 2 * NT registers.
+template <int CC, int NT, bool STATS>
 __global__ void __launch_bounds__(kBrickThreads, 1) conv_brick_kernel(const __grid_constant__ BrickArgs a) {
     constexpr int P = 256 / NT;
     constexpr uint32_t kRowBytes = CC * 2u;
@@ -230,15 +232,21 @@ __global__ void __launch_bounds__(kBrickThreads, 1) conv_brick_kernel(const __gr
         epi.act = a.act;
         epi.slope = a.slope;
         epi.out_f16 = a.out_f16;
+        epi.stats = STATS ? a.stats : nullptr;
         StatAcc sacc[NT / 32];
+        float t1[NT / 32][32], t2[NT / 32][32];  // per-thread sums over the planes of one brick (STATS only)
 #pragma unroll
-        for (int j = 0; j < NT / 32; ++j) sacc[j].s1 = sacc[j].s2 = 0.f;
+        for (int j = 0; j < NT / 32; ++j) {
+            sacc[j].s1 = sacc[j].s2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t1[j][i] = t2[j][i] = 0.f;
+        }
         int stat_n = -1;  // batch item the running statistics belong to
         uint32_t tcount = 0;
         for (int u = blockIdx.x; u < units; u += gridDim.x, ++tcount) {
             const Unit t = decode_unit(a, u, P);
             const uint32_t bb = tcount & 1u, par = (tcount >> 1) & 1u;
-            if (a.stats != nullptr && t.n != stat_n) {
+            if (STATS && t.n != stat_n) {
 #pragma unroll
                 for (int j = 0; j < NT / 32; ++j) flush_stats(epi, sacc[j], j * 32, lane, stat_n);
                 stat_n = t.n;
@@ -256,14 +264,22 @@ __global__ void __launch_bounds__(kBrickThreads, 1) conv_brick_kernel(const __gr
                     uint32_t v[32];
                     tmem_ld_32x32(t_addr + cb, v);
                     tmem_ld_wait();
-                    epilogue_32cols(v, epi, cb, true, lane, sacc[cb / 32], orow);
+                    epilogue_32cols<true>(v, epi, cb, true, lane, sacc[cb / 32], orow, t1[cb / 32], t2[cb / 32]);
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[slot]);
             }
+            if (STATS) {  // one warp reduction per brick instead of one per plane
+#pragma unroll
+                for (int j = 0; j < NT / 32; ++j) {
+                    stats_transpose_reduce(t1[j], t2[j], lane, sacc[j]);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) t1[j][i] = t2[j][i] = 0.f;
+                }
+            }
         }
-        if (a.stats != nullptr) {
+        if (STATS) {
 #pragma unroll
             for (int j = 0; j < NT / 32; ++j) flush_stats(epi, sacc[j], j * 32, lane, stat_n);
         }
@@ -277,17 +293,23 @@ __global__ void __launch_bounds__(kBrickThreads, 1) conv_brick_kernel(const __gr
     }
 }
 
-template <int CC, int NT>
+template <int CC, int NT, bool STATS>
 cudaError_t launch_variant(const BrickArgs& a, int grid, size_t smem_bytes, cudaStream_t stream) {
     static bool attr_set = false;  // one process drives one device
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_brick_kernel<CC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             232448);
+        cudaError_t e = cudaFuncSetAttribute(conv_brick_kernel<CC, NT, STATS>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    conv_brick_kernel<CC, NT><<<grid, kBrickThreads, smem_bytes, stream>>>(a);
+    conv_brick_kernel<CC, NT, STATS><<<grid, kBrickThreads, smem_bytes, stream>>>(a);
     return cudaGetLastError();
+}
+
+template <int CC, int NT>
+cudaError_t launch_stats(const BrickArgs& a, int grid, size_t smem_bytes, cudaStream_t stream) {
+    return a.stats != nullptr ? launch_variant<CC, NT, true>(a, grid, smem_bytes, stream)
+                              : launch_variant<CC, NT, false>(a, grid, smem_bytes, stream);
 }
 
 }  // namespace
@@ -299,13 +321,13 @@ size_t conv_brick_smem_bytes(const BrickArgs& a) {
 
 cudaError_t launch_conv_brick(const BrickArgs& a, int cc, int nt, int grid, size_t smem_bytes, cudaStream_t stream) {
     if (nt == 32) {
-        if (cc == 64) return launch_variant<64, 32>(a, grid, smem_bytes, stream);
-        if (cc == 32) return launch_variant<32, 32>(a, grid, smem_bytes, stream);
-        return launch_variant<16, 32>(a, grid, smem_bytes, stream);
+        if (cc == 64) return launch_stats<64, 32>(a, grid, smem_bytes, stream);
+        if (cc == 32) return launch_stats<32, 32>(a, grid, smem_bytes, stream);
+        return launch_stats<16, 32>(a, grid, smem_bytes, stream);
     }
-    if (cc == 64) return launch_variant<64, 64>(a, grid, smem_bytes, stream);
-    if (cc == 32) return launch_variant<32, 64>(a, grid, smem_bytes, stream);
-    return launch_variant<16, 64>(a, grid, smem_bytes, stream);
+    if (cc == 64) return launch_stats<64, 64>(a, grid, smem_bytes, stream);
+    if (cc == 32) return launch_stats<32, 64>(a, grid, smem_bytes, stream);
+    return launch_stats<16, 64>(a, grid, smem_bytes, stream);
 }
 
 }  // namespace bsg

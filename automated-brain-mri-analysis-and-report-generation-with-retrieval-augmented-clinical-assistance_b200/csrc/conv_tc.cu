@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
         for (int j = 0; j < 8; ++j) sacc[j].s1 = sacc[j].s2 = 0.f;
         int stat_n = -1, stat_nt = 0;
+        float unused1[32], unused2[32];  // per-thread statistic sums: brick kernel only
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
             const TileCoord t = decode_tile(a, tile);
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                            static_cast<long long>(2 * h + ((par >> 1) & 1)) * a.os_h +
                            static_cast<long long>(2 * w + (par & 1)) * a.os_w;
                 }
-                epilogue_32cols(v, epi, co, valid, lane, sacc[j], orow);
+                epilogue_32cols<false>(v, epi, co, valid, lane, sacc[j], orow, unused1, unused2);
             }
             tc_fence_before();
             __syncwarp();
