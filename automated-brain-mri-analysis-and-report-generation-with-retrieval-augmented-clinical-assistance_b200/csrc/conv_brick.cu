@@ -13,6 +13,11 @@
 //     and serves the nine (kd, kh) taps it takes part in (kh through row-shifted descriptors);
 //   * weights are staged as per-phase slabs (phase = (channel chunk, kw): 9 taps x NT x CC, laid out [kh][kd][NT][CC])
 //     that stay resident in shared memory for the whole launch when all phases fit, else stream through two buffers.
+// kw-fused variant (KWF, used whenever the slabs are resident): the box is 10 w x 18 h and every (kh, kw) tap reads it
+// through a descriptor that starts at row kh*10 + kw with a 10-row group pitch — start addresses that are not
+// aligned to the 8-row swizzle atom are fine because the tensor core applies the swizzle to absolute shared-memory
+// address bits (profiles/r01_probe_umma_shift.log).  One TMA box then feeds 27 taps instead of 9, which matters
+// because the box fill and the MMA operand reads share the same 128 B/clk shared-memory port.
 // Roles: warps 0..3 epilogue (TMEM lane quadrant = warp id), warp 4 activation TMA producer, warp 5 weight-slab TMA
 // producer, warp 6 MMA issuer (one thread).  The issuer is the highest warp id of its scheduler partition: the
 // warp arbiter favours the highest id, so the latency-critical tcgen05.mma stream is never queued behind the
@@ -49,7 +54,7 @@ __device__ __forceinline__ Unit decode_unit(const BrickArgs& a, int u, int P) {
 
 // STATS: the epilogue also accumulates the norm statistics (a.stats != null) — a separate instantiation because the
 // per-thread sums cost 2 * NT registers.
-template <int CC, int NT, bool STATS>
+template <int CC, int NT, bool STATS, bool KWF>
 __global__ void __launch_bounds__(kBrickThreads, 1) conv_brick_kernel(const __grid_constant__ BrickArgs a) {
     constexpr int P = 256 / NT;
     constexpr uint32_t kRowBytes = CC * 2u;
@@ -114,14 +119,15 @@ __global__ void __launch_bounds__(kBrickThreads, 1) conv_brick_kernel(const __gr
             uint32_t phase = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
                 const Unit t = decode_unit(a, u, P);
-                for (int ph = 0; ph < nphases; ++ph) {
-                    const int c = ph / 3, kw = ph - c * 3;
+                const int nloads = KWF ? a.nchunks : nphases;  // KWF: one haloed box per (chunk, plane) for all kw
+                for (int ph = 0; ph < nloads; ++ph) {
+                    const int c = KWF ? ph : ph / 3, kw = KWF ? 1 : ph - c * 3;
                     for (int p = 0; p < P + 2; ++p) {
                         const int d = t.d0 + p - 1;  // d = -1 / D: the box is all out of bounds -> zeros (conv padding)
                         mbar_wait(&empty_bar[stage], phase ^ 1u);
                         mbar_expect_tx(&full_bar[stage], a.a_tx_bytes);
                         tma_load_5d(stages + static_cast<size_t>(stage) * a.a_stage_bytes, &a.mapA, &full_bar[stage],
-                                    c * CC, t.w0 + kw - 1, t.h0 - 1, d, t.n);
+                                    c * CC, t.w0 + kw - 1 - (KWF ? 1 : 0), t.h0 - 1, d, t.n);
                         if (++stage == a.nstages) {
                             stage = 0;
                             phase ^= 1u;
@@ -159,14 +165,72 @@ __global__ void __launch_bounds__(kBrickThreads, 1) conv_brick_kernel(const __gr
             const uint32_t idesc1 = make_idesc_16(128, NT, a.in_f16), idesc2 = make_idesc_16(128, 2 * NT, a.in_f16),
                            idesc3 = make_idesc_16(128, 3 * NT, a.in_f16);
             const uint64_t desc_base = make_smem_desc(0, kAtom, kLayout);
-            const uint32_t stages16 = smem_u32(stages) >> 4, slabs16 = smem_u32(slabs) >> 4;
+            const uint32_t desc_hi = static_cast<uint32_t>(desc_base >> 32);
+            const uint32_t desc_lo0 = static_cast<uint32_t>(desc_base);  // LBO field; the start address is added to it
+            const uint32_t stages16 = desc_lo0 + (smem_u32(stages) >> 4), slabs16 = desc_lo0 + (smem_u32(slabs) >> 4);
             const uint32_t stage16 = a.a_stage_bytes >> 4, slab16 = a.slab_bytes >> 4;
             constexpr uint32_t kTap16 = kTapBytes >> 4, kAtom16 = kAtom >> 4;
             int stage = 0;
             uint32_t phase = 0, su = 0, tcount = 0;
+            // `ready`: the full barrier of the current stage was already seen complete.  It is probed (one non-blocking
+            // try_wait) in the middle of the previous stage's MMAs, so its ~100-cycle latency overlaps queued tensor
+            // work instead of draining the MMA queue at every stage boundary.
+            bool ready = false;
             for (int u = blockIdx.x; u < units; u += gridDim.x, ++tcount) {
                 const uint32_t bb = tcount & 1u, par = (tcount >> 1) & 1u;
                 const uint32_t tm_brick = tmem_base + bb * (P * NT);
+                if (KWF) {
+                    // ---- kw-fused: slabs are resident (slab index = chunk * 3 + kw), one stage = (chunk, input plane)
+                    if (tcount == 0)
+                        for (int ph = 0; ph < nphases; ++ph) mbar_wait(&wfull_bar[ph], 0u);
+                    constexpr uint32_t kRow16 = kRowBytes >> 4;
+                    const uint32_t a_hi = static_cast<uint32_t>(make_smem_desc(0, 10u * kRowBytes, kLayout) >> 32);
+                    for (int c = 0; c < a.nchunks; ++c) {
+                        const uint32_t sb16 = slabs16 + static_cast<uint32_t>(c) * 3u * slab16;
+                        const bool first_phase = (c == 0), last_phase = (c == a.nchunks - 1);
+                        auto issue_plane = [&](const int p, const int nblk, const int kd_lo, const bool fresh) {
+                            const uint32_t d_tmem = tm_brick + static_cast<uint32_t>(P - 1 - (p - kd_lo)) * NT;
+                            const uint32_t idesc = nblk == 3 ? idesc3 : (nblk == 2 ? idesc2 : idesc1);
+                            if (fresh) mbar_wait(&tempty_bar[bb * P + p], par ^ 1u);
+                            if (!ready) mbar_wait(&full_bar[stage], phase);
+                            tc_fence_after();
+                            const uint32_t sa16 = stages16 + static_cast<uint32_t>(stage) * stage16;
+                            const uint32_t sbk16 = sb16 + static_cast<uint32_t>(kd_lo) * kTap16;
+                            const int nstage = (stage + 1 == a.nstages) ? 0 : stage + 1;
+                            const uint32_t nphase = (stage + 1 == a.nstages) ? (phase ^ 1u) : phase;
+#pragma unroll
+                            for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+                                for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                                    for (int k = 0; k < CC / 16; ++k) {
+                                        const uint32_t ad = sa16 + (kh * 10 + kw) * kRow16 + 2 * k;
+                                        const uint32_t bd = sbk16 + kw * slab16 + kh * 3 * kTap16 + 2 * k;
+                                        if (kw == 0 && kh == 0 && k == 0 && fresh) {
+                                            umma_bf16_lo2(d_tmem, ad, a_hi, bd, desc_hi, idesc1, 0u);
+                                            if (nblk > 1)
+                                                umma_bf16_lo2(d_tmem + NT, ad, a_hi, bd + kTap16, desc_hi,
+                                                              nblk == 3 ? idesc2 : idesc1, 1u);
+                                        } else {
+                                            umma_bf16_lo2(d_tmem, ad, a_hi, bd, desc_hi, idesc, 1u);
+                                        }
+                                    }
+                                }
+                                if (kw == 0) ready = mbar_try_wait(&full_bar[nstage], nphase);  // probe the next stage
+                            }
+                            umma_commit(&empty_bar[stage]);
+                            if (last_phase && p >= 2) umma_commit(&tfull_bar[bb * P + (p - 2)]);  // plane p-2 is complete
+                            stage = nstage;
+                            phase = nphase;
+                        };
+                        issue_plane(0, 1, 0, first_phase);
+                        issue_plane(1, 2, 0, first_phase);
+                        for (int p = 2; p < P; ++p) issue_plane(p, 3, 0, first_phase);
+                        issue_plane(P, 2, 1, false);
+                        issue_plane(P + 1, 1, 2, false);
+                    }
+                    continue;
+                }
                 for (int ph = 0; ph < nphases; ++ph, ++su) {
                     uint32_t buf;
                     if (resident) {
@@ -177,43 +241,47 @@ __global__ void __launch_bounds__(kBrickThreads, 1) conv_brick_kernel(const __gr
                         mbar_wait(&wfull_bar[buf], (su / static_cast<uint32_t>(a.nslabbuf)) & 1u);
                     }
                     const uint32_t sb16 = slabs16 + buf * slab16;
-                    for (int p = 0; p < P + 2; ++p) {
-                        // input plane p feeds output planes q = p - kd, kd in [kd_lo, kd_hi]; their accumulators are
-                        // adjacent TMEM column blocks in ascending kd order starting at plane q_hi = p - kd_lo
-                        const int kd_lo = p > P - 1 ? p - (P - 1) : 0;
-                        const int kd_hi = p < 2 ? p : 2;
-                        const int nblk = kd_hi - kd_lo + 1;
+                    const bool first_phase = (ph == 0), last_phase = (ph == nphases - 1);
+                    // One stage = input plane p.  It feeds output planes q = p - kd, kd in [kd_lo, kd_lo + nblk): their
+                    // accumulators are adjacent TMEM column blocks in ascending kd order starting at plane p - kd_lo.
+                    // nblk / kd_lo are literals at every call site, so each call compiles to a straight MMA sequence.
+                    auto issue_plane = [&](const int p, const int nblk, const int kd_lo, const bool fresh) {
                         const uint32_t d_tmem = tm_brick + static_cast<uint32_t>(P - 1 - (p - kd_lo)) * NT;
                         const uint32_t idesc = nblk == 3 ? idesc3 : (nblk == 2 ? idesc2 : idesc1);
-                        const bool fresh = (ph == 0) && (p < P);  // plane q = p receives its first contribution here
-                        if (fresh) mbar_wait(&tempty_bar[bb * P + p], par ^ 1u);  // epilogue has drained the slot
-                        mbar_wait(&full_bar[stage], phase);
+                        if (fresh) mbar_wait(&tempty_bar[bb * P + p], par ^ 1u);  // epilogue has drained plane p's slot
+                        if (!ready) mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
                         const uint32_t sa16 = stages16 + static_cast<uint32_t>(stage) * stage16;
                         const uint32_t sbk16 = sb16 + static_cast<uint32_t>(kd_lo) * kTap16;
+                        const int nstage = (stage + 1 == a.nstages) ? 0 : stage + 1;
+                        const uint32_t nphase = (stage + 1 == a.nstages) ? (phase ^ 1u) : phase;
 #pragma unroll
                         for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
                             for (int k = 0; k < CC / 16; ++k) {
-                                const uint64_t ad = desc_base | static_cast<uint64_t>(sa16 + kh * kAtom16 + 2 * k);
-                                const uint64_t bd = desc_base | static_cast<uint64_t>(sbk16 + kh * 3 * kTap16 + 2 * k);
+                                const uint32_t ad = sa16 + kh * kAtom16 + 2 * k;
+                                const uint32_t bd = sbk16 + kh * 3 * kTap16 + 2 * k;
                                 if (kh == 0 && k == 0 && fresh) {
                                     // the new plane's block must overwrite, the older planes' blocks accumulate: split
-                                    umma_bf16(d_tmem, ad, bd, idesc1, 0u);
+                                    umma_bf16_lo(d_tmem, ad, bd, desc_hi, idesc1, 0u);
                                     if (nblk > 1)
-                                        umma_bf16(d_tmem + NT, ad, bd + kTap16, nblk == 3 ? idesc2 : idesc1, 1u);
+                                        umma_bf16_lo(d_tmem + NT, ad, bd + kTap16, desc_hi, nblk == 3 ? idesc2 : idesc1, 1u);
                                 } else {
-                                    umma_bf16(d_tmem, ad, bd, idesc, 1u);
+                                    umma_bf16_lo(d_tmem, ad, bd, desc_hi, idesc, 1u);
                                 }
                             }
+                            if (kh == 0) ready = mbar_try_wait(&full_bar[nstage], nphase);  // probe the next stage early
                         }
                         umma_commit(&empty_bar[stage]);  // frees the activation slot once these MMAs have read it
-                        if (ph == nphases - 1 && p >= 2) umma_commit(&tfull_bar[bb * P + (p - 2)]);  // plane p-2 done
-                        if (++stage == a.nstages) {
-                            stage = 0;
-                            phase ^= 1u;
-                        }
-                    }
+                        if (last_phase && p >= 2) umma_commit(&tfull_bar[bb * P + (p - 2)]);  // plane p-2 is complete
+                        stage = nstage;
+                        phase = nphase;
+                    };
+                    issue_plane(0, 1, 0, first_phase);
+                    issue_plane(1, 2, 0, first_phase);
+                    for (int p = 2; p < P; ++p) issue_plane(p, 3, 0, first_phase);
+                    issue_plane(P, 2, 1, false);
+                    issue_plane(P + 1, 1, 2, false);
                     if (!resident) umma_commit(&wempty_bar[buf]);
                 }
             }
@@ -293,23 +361,26 @@ __global__ void __launch_bounds__(kBrickThreads, 1) conv_brick_kernel(const __gr
     }
 }
 
-template <int CC, int NT, bool STATS>
+template <int CC, int NT, bool STATS, bool KWF>
 cudaError_t launch_variant(const BrickArgs& a, int grid, size_t smem_bytes, cudaStream_t stream) {
     static bool attr_set = false;  // one process drives one device
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_brick_kernel<CC, NT, STATS>,
+        cudaError_t e = cudaFuncSetAttribute(conv_brick_kernel<CC, NT, STATS, KWF>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    conv_brick_kernel<CC, NT, STATS><<<grid, kBrickThreads, smem_bytes, stream>>>(a);
+    conv_brick_kernel<CC, NT, STATS, KWF><<<grid, kBrickThreads, smem_bytes, stream>>>(a);
     return cudaGetLastError();
 }
 
 template <int CC, int NT>
 cudaError_t launch_stats(const BrickArgs& a, int grid, size_t smem_bytes, cudaStream_t stream) {
-    return a.stats != nullptr ? launch_variant<CC, NT, true>(a, grid, smem_bytes, stream)
-                              : launch_variant<CC, NT, false>(a, grid, smem_bytes, stream);
+    if (a.kwf)
+        return a.stats != nullptr ? launch_variant<CC, NT, true, true>(a, grid, smem_bytes, stream)
+                                  : launch_variant<CC, NT, false, true>(a, grid, smem_bytes, stream);
+    return a.stats != nullptr ? launch_variant<CC, NT, true, false>(a, grid, smem_bytes, stream)
+                              : launch_variant<CC, NT, false, false>(a, grid, smem_bytes, stream);
 }
 
 }  // namespace

@@ -14,7 +14,7 @@ namespace bsg {
 // the weights sit in shared memory as per-phase slabs (phase = (channel chunk, kw); 9 taps x Cout x CC each) that
 // stay resident when all of them fit.
 struct BrickArgs {
-    CUtensorMap mapA;  // 5-D (C, W, H, D, N) activations, box (CC, 8, 18, 1, 1), OOB zero fill = conv padding
+    CUtensorMap mapA;  // 5-D (C, W, H, D, N) activations, box (CC, 8 | 10, 18, 1, 1), OOB zero fill = conv padding
     CUtensorMap mapW;  // 5-D (Cin_pad, Cout_pad, kh, kw, kd) view of the 27-tap weights, box (CC, NT, 1, 1, 3)
     int tw, th, tb, tn;  // unit grid: W/8, H/16, D/P, batch
     int P;               // planes per brick = 256 / NT
@@ -22,6 +22,7 @@ struct BrickArgs {
     int nchunks;   // Cin / CC
     int nphases;   // 3 * nchunks, phase = chunk * 3 + kw
     int nslabbuf;  // weight slab buffers in shared memory; >= nphases: resident for the whole launch
+    int kwf;       // 1: kw-fused — one haloed 10 w x 18 h box per (plane, chunk) serves all 27 taps (needs resident slabs)
     int nstages;   // activation ring depth
     uint32_t a_stage_bytes;  // multiple of 1024
     uint32_t a_tx_bytes;     // bytes one activation box delivers

@@ -72,8 +72,22 @@ template <bool THREAD_ACC>
 __device__ __forceinline__ void epilogue_32cols(const uint32_t (&v)[32], const EpiParams& e, int co, bool valid, int lane,
                                                 StatAcc& acc, __nv_bfloat16* orow, float (&t1)[32], float (&t2)[32]) {
     float f[32];
+    {
+        // bias: 8 x ld.shared.v4 (warp-wide broadcast); `e.sbias` is a generic pointer, which would compile to 32
+        // generic loads per chunk
+        const uint32_t baddr = static_cast<uint32_t>(__cvta_generic_to_shared(e.sbias + co));
 #pragma unroll
-    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + e.sbias[co + i];
+        for (int i = 0; i < 8; ++i) {
+            float b0, b1, b2, b3;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n"
+                         : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3)
+                         : "r"(baddr + 16u * i));
+            f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b0;
+            f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b1;
+            f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b2;
+            f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b3;
+        }
+    }
     if (e.stats != nullptr) {
         if (THREAD_ACC) {
 #pragma unroll

@@ -90,18 +90,23 @@ int plan_brick(const bsg_conv_desc* d, bsg_conv_plan* p) {
     a.tn = d->N;
     a.nchunks = d->cin / cc;
     a.nphases = 3 * a.nchunks;
-    a.a_tx_bytes = 8u * 18u * cc * 2u;
-    a.a_stage_bytes = round_up(a.a_tx_bytes, 1024);
     a.slab_bytes = 9u * cout_pad * cc * 2u;
     // leave ~8 KB of the SM's shared memory unclaimed: the HBM-bound elementwise kernels of the other stream lane
     // (norm apply, gather, head) need their 1 KB system reservation each to become co-resident with this CTA
     const uint32_t avail = 227 * 1024 - 1024 - 1280 - 8192;
-    if (a.nphases <= 6 && static_cast<uint64_t>(a.nphases) * a.slab_bytes + 3ull * a.a_stage_bytes <= avail)
-        a.nslabbuf = a.nphases;  // resident
-    else if (2ull * a.slab_bytes + 2ull * a.a_stage_bytes <= avail)
+    const uint32_t stage_kwf = round_up(10u * 18u * cc * 2u, 1024), stage_3x = round_up(8u * 18u * cc * 2u, 1024);
+    if (a.nphases <= 6 && static_cast<uint64_t>(a.nphases) * a.slab_bytes + 3ull * stage_kwf <= avail) {
+        a.nslabbuf = a.nphases;  // resident slabs -> kw-fused activation boxes
+        a.kwf = 1;
+    } else if (2ull * a.slab_bytes + 2ull * stage_3x <= avail) {
         a.nslabbuf = 2;
-    else
+        a.kwf = 0;
+    } else {
         return 0;
+    }
+    const uint32_t box_w = a.kwf ? 10u : 8u;
+    a.a_tx_bytes = box_w * 18u * cc * 2u;
+    a.a_stage_bytes = a.kwf ? stage_kwf : stage_3x;
     a.nstages = static_cast<int>((avail - static_cast<uint32_t>(a.nslabbuf) * a.slab_bytes) / a.a_stage_bytes);
     if (a.nstages > 12) a.nstages = 12;
 
@@ -109,7 +114,7 @@ int plan_brick(const bsg_conv_desc* d, bsg_conv_plan* p) {
     uint64_t dims[5] = {static_cast<uint64_t>(d->cin), static_cast<uint64_t>(d->W), static_cast<uint64_t>(d->H),
                         static_cast<uint64_t>(d->D), static_cast<uint64_t>(d->N)};
     uint64_t str[4] = {ct * 2, ct * 2 * d->W, ct * 2 * d->W * d->H, ct * 2 * d->W * d->H * d->D};
-    uint32_t box[5] = {static_cast<uint32_t>(cc), 8u, 18u, 1u, 1u};
+    uint32_t box[5] = {static_cast<uint32_t>(cc), box_w, 18u, 1u, 1u};
     int rc = encode_map(&a.mapA, d->in, 5, dims, str, box, cc);
     if (rc != BSG_OK) return rc;
     // weights [27 taps (kd, kw, kh)][cout_pad][cin] seen as (cin, row, kh, kw, kd): a box of the 3 kd taps of one
@@ -378,7 +383,7 @@ int bsg_conv_plan_info(const bsg_conv_plan* plan, bsg_conv_info* info) {
         info->n_ntiles = 1;
         info->cc = plan->brick_cc;
         info->nstages = b.nstages;
-        info->khshift = 2 + b.nslabbuf;  /* brick kernel marker: 2 + number of weight-slab buffers */
+        info->khshift = 2 + b.nslabbuf + (b.kwf ? 10 : 0);  /* brick marker: 2 + slab buffers (+10: kw-fused) */
         info->grid = plan->grid;
         info->smem_bytes = plan->smem_bytes;
         info->flops = plan->flops;

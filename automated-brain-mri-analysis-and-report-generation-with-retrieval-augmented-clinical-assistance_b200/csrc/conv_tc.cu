@@ -158,12 +158,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             constexpr uint32_t kLayout = (CC == 64) ? kLayoutSW128 : (CC == 32 ? kLayoutSW64 : kLayoutSW32);
             // descriptor = constant high word | (start address >> 4): only the low word moves between MMAs
             const uint64_t desc_base = make_smem_desc(0, kSbo, kLayout);
+            const uint32_t desc_hi = static_cast<uint32_t>(desc_base >> 32);
             const uint32_t b_tap16 = (static_cast<uint32_t>(a.ntile) * kRowBytes) >> 4;
-            const uint32_t smem0_16 = smem_u32(smem) >> 4;
+            const uint32_t smem0_16 = static_cast<uint32_t>(desc_base) + (smem_u32(smem) >> 4);  // LBO field + address
             const uint32_t stage16 = stage_bytes >> 4, a16 = a.a_stage_bytes >> 4;
             int stage = 0;
             uint32_t phase = 0;
             uint32_t tcount = 0;
+            bool ready = false;  // next stage's full barrier already seen complete (probed early, see below)
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
                 const uint32_t acc = tcount & 1u;
                 const uint32_t acc_phase = (tcount >> 1) & 1u;
@@ -171,25 +173,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * static_cast<uint32_t>(a.ntile);
                 for (int ks = 0; ks < ksteps; ++ks) {
-                    mbar_wait(&full_bar[stage], phase);
+                    if (!ready) mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t sa16 = smem0_16 + static_cast<uint32_t>(stage) * stage16;
                     const uint32_t sb16 = sa16 + a16;
+                    const int nstage = (stage + 1 == nstages) ? 0 : stage + 1;
+                    const uint32_t nphase = (stage + 1 == nstages) ? (phase ^ 1u) : phase;
 #pragma unroll
                     for (int kh = 0; kh < NKH; ++kh) {
 #pragma unroll
                         for (int k = 0; k < CC / 16; ++k) {
-                            const uint64_t ad = desc_base | static_cast<uint64_t>(sa16 + ((kh * kSbo + k * 32) >> 4));
-                            const uint64_t bd = desc_base | static_cast<uint64_t>(sb16 + kh * b_tap16 + ((k * 32) >> 4));
-                            umma_bf16(d_tmem, ad, bd, idesc, (kh | k) != 0 ? 1u : (ks != 0 ? 1u : 0u));
+                            const uint32_t ad = sa16 + ((kh * kSbo + k * 32) >> 4);
+                            const uint32_t bd = sb16 + kh * b_tap16 + ((k * 32) >> 4);
+                            umma_bf16_lo(d_tmem, ad, bd, desc_hi, idesc, (kh | k) != 0 ? 1u : (ks != 0 ? 1u : 0u));
+                            // probe the next stage's barrier behind the first MMA: its latency overlaps queued work
+                            if (kh == 0 && k == 0) ready = mbar_try_wait(&full_bar[nstage], nphase);
                         }
                     }
                     umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
                     if (ks == ksteps - 1) umma_commit(&tfull_bar[acc]);
-                    if (++stage == nstages) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
+                    stage = nstage;
+                    phase = nphase;
                 }
             }
         }

@@ -25,10 +25,12 @@ class Bar:
         return self.phase != parity
 
 
-def simulate(P, D, nchunks, nslabbuf, nstages, units_of_cta, seed, async_commit=True):
+def simulate(P, D, nchunks, nslabbuf, nstages, units_of_cta, seed, async_commit=True, kwf=False):
     rng = random.Random(seed)
     nphases = 3 * nchunks
     resident = nslabbuf >= nphases
+    assert resident or not kwf, "the kw-fused variant needs resident slabs"
+    aphases = nchunks if kwf else nphases  # activation-stage phases: KWF loads one haloed box per (chunk, plane)
     full = [Bar(1) for _ in range(nstages)]
     empty = [Bar(1) for _ in range(nstages)]
     wfull = [Bar(1) for _ in range(max(nslabbuf, 1))]
@@ -48,7 +50,7 @@ def simulate(P, D, nchunks, nslabbuf, nstages, units_of_cta, seed, async_commit=
     def a_producer():
         stage, phase = 0, 0
         for (ui, d0) in units_of_cta:
-            for ph in range(nphases):
+            for ph in range(aphases):
                 for p in range(P + 2):
                     yield from wait(empty[stage], phase ^ 1)
                     assert stage_data[stage] is None, "activation stage overwritten while in use"
@@ -86,15 +88,22 @@ def simulate(P, D, nchunks, nslabbuf, nstages, units_of_cta, seed, async_commit=
         stage, phase, su, tcount = 0, 0, 0, 0
         for (ui, d0) in units_of_cta:
             bb, par = tcount & 1, (tcount >> 1) & 1
-            for ph in range(nphases):
-                if resident:
+            if kwf and tcount == 0:
+                for b in range(nphases):
+                    yield from wait(wfull[b], 0)
+            for ph in range(aphases):
+                if kwf:
+                    buf = None
+                    assert all(slab_data[ph * 3 + kw] == ph * 3 + kw for kw in range(3))
+                elif resident:
                     buf = ph
                     if tcount == 0:
                         yield from wait(wfull[buf], 0)
                 else:
                     buf = su % nslabbuf
                     yield from wait(wfull[buf], (su // nslabbuf) & 1)
-                assert slab_data[buf] == ph, f"slab {slab_data[buf]} != phase {ph}"
+                if not kwf:
+                    assert slab_data[buf] == ph, f"slab {slab_data[buf]} != phase {ph}"
                 for p in range(P + 2):
                     kd_lo, kd_hi = max(0, p - (P - 1)), min(2, p)
                     fresh = ph == 0 and p < P
@@ -109,15 +118,15 @@ def simulate(P, D, nchunks, nslabbuf, nstages, units_of_cta, seed, async_commit=
                         slot = bb * P + (p - kd)
                         assert acc[slot] is not None, "accumulating into a slot that was never started"
                         for kh in range(3):
-                            key = (ph, kd, kh)
-                            assert key not in acc[slot]
-                            acc[slot].add(key)
+                            for key in ([(ph * 3 + kw, kd, kh) for kw in range(3)] if kwf else [(ph, kd, kh)]):
+                                assert key not in acc[slot]
+                                acc[slot].add(key)
 
                     def free_stage(s=stage):
                         stage_data[s] = None
                         empty[s].arrive()
                     commit(free_stage)
-                    if ph == nphases - 1 and p >= 2:
+                    if ph == aphases - 1 and p >= 2:
                         commit(lambda s=bb * P + p - 2: tfull[s].arrive())
                     stage += 1
                     if stage == nstages:
@@ -177,6 +186,7 @@ def simulate(P, D, nchunks, nslabbuf, nstages, units_of_cta, seed, async_commit=
     (4, 2, 2, 4),    # 128->64
     (4, 1, 3, 2),    # minimum ring depth
     (8, 2, 2, 3),
+    (8, 2, 6, 4),    # 64->32 as two 32-channel chunks, resident
 ])
 def test_brick_protocol(P, nchunks, nslabbuf, nstages):
     D = 4 * P
@@ -186,3 +196,6 @@ def test_brick_protocol(P, nchunks, nslabbuf, nstages):
         simulate(P, D, nchunks, nslabbuf, nstages, units, seed)
     simulate(P, P, nchunks, nslabbuf, nstages, [(0, 0), (1, 0), (2, 0)], 99)  # single-brick volume: both edges at once
     simulate(P, D, nchunks, nslabbuf, nstages, [(0, P)], 5, async_commit=False)
+    if nslabbuf >= 3 * nchunks:  # resident slabs: the kernel runs the kw-fused variant
+        for seed in range(4):
+            simulate(P, D, nchunks, nslabbuf, nstages, [(i, (i % 4) * P) for i in range(5)], seed, kwf=True)
