@@ -23,44 +23,44 @@ struct MirrorSet {
 };
 
 // out[m][d][h][w][c] = vol[c][z0 + fz(d)][y0 + fy(h)][x0 + fx(w)], c < C; channels C..cpad-1 are zero.
+// grid (ceil(P1*P2 / 256), P0, mirrors): one thread per output voxel, 32-bit index math, 256-bit stores.
 __global__ void __launch_bounds__(kThreads) gather_patch_kernel(const float* __restrict__ vol, int C, int Z, int Y,
                                                                 int X, int z0, int y0, int x0, int P0, int P1, int P2,
                                                                 const MirrorSet ms, __nv_bfloat16* __restrict__ out,
                                                                 int cpad, int out_f16) {
-    const size_t pv = static_cast<size_t>(P0) * P1 * P2;
-    const size_t total = pv * ms.n;
+    const int hw = blockIdx.x * blockDim.x + threadIdx.x;
+    if (hw >= P1 * P2) return;
+    const int d = blockIdx.y, m = blockIdx.z;
+    const int h = hw / P2, w = hw - h * P2;
     const size_t plane = static_cast<size_t>(Z) * Y * X;
-    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const int m = static_cast<int>(i / pv);
-        size_t r = i - static_cast<size_t>(m) * pv;
-        const int w = static_cast<int>(r % P2);
-        r /= P2;
-        const int h = static_cast<int>(r % P1);
-        const int d = static_cast<int>(r / P1);
-        const int code = ms.code[m];
-        const int sx = x0 + ((code & 1) ? P2 - 1 - w : w);
-        const int sy = y0 + ((code & 2) ? P1 - 1 - h : h);
-        const int sz = z0 + ((code & 4) ? P0 - 1 - d : d);
-        const float* src = vol + (static_cast<size_t>(sz) * Y + sy) * X + sx;
-        __nv_bfloat16* dst = out + i * cpad;
-        // cpad is a multiple of 8: write 16-byte groups
-        for (int c0 = 0; c0 < cpad; c0 += 8) {
-            uint32_t pk[4];
+    const int code = ms.code[m];
+    const int sx = x0 + ((code & 1) ? P2 - 1 - w : w);
+    const int sy = y0 + ((code & 2) ? P1 - 1 - h : h);
+    const int sz = z0 + ((code & 4) ? P0 - 1 - d : d);
+    const float* src = vol + (static_cast<size_t>(sz) * Y + sy) * X + sx;
+    __nv_bfloat16* dst = out + ((static_cast<size_t>(m) * P0 + d) * P1 * P2 + hw) * cpad;
+    for (int c0 = 0; c0 < cpad; c0 += 16) {
+        uint32_t pk[8];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int ca = c0 + 2 * k, cb = ca + 1;
-                const float fa = ca < C ? __ldg(src + ca * plane) : 0.f;
-                const float fb = cb < C ? __ldg(src + cb * plane) : 0.f;
-                if (out_f16) {
-                    __half2 p = __floats2half2_rn(fa, fb);
-                    pk[k] = *reinterpret_cast<uint32_t*>(&p);
-                } else {
-                    __nv_bfloat162 p = __floats2bfloat162_rn(fa, fb);
-                    pk[k] = *reinterpret_cast<uint32_t*>(&p);
-                }
+        for (int k = 0; k < 8; ++k) {
+            const int ca = c0 + 2 * k, cb = ca + 1;
+            const float fa = ca < C ? __ldg(src + ca * plane) : 0.f;
+            const float fb = cb < C ? __ldg(src + cb * plane) : 0.f;
+            if (out_f16) {
+                __half2 p = __floats2half2_rn(fa, fb);
+                pk[k] = *reinterpret_cast<uint32_t*>(&p);
+            } else {
+                __nv_bfloat162 p = __floats2bfloat162_rn(fa, fb);
+                pk[k] = *reinterpret_cast<uint32_t*>(&p);
             }
+        }
+        if (c0 + 16 <= cpad && (reinterpret_cast<uintptr_t>(dst + c0) & 31) == 0) {
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(dst + c0), "r"(pk[0]), "r"(pk[1]),
+                         "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                         : "memory");
+        } else {
             *reinterpret_cast<uint4*>(dst + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            if (c0 + 8 < cpad) *reinterpret_cast<uint4*>(dst + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
     }
 }
@@ -166,89 +166,86 @@ struct HeadParams {
     float mirror_weight;  // 1 / num_results of the full TTA (the mirrors of a tile may be split over launches)
 };
 
+// grid (ceil(P1*P2 / 256), P0): one thread per tile voxel.  NCLS / CFEAT are compile-time bounds (the valid counts are
+// hp.ncls <= NCLS, hp.cfeat <= CFEAT, padded weights are zero), so the head weights become constant-bank operands of
+// fully unrolled FMAs.
+template <int NCLS, int CFEAT>
 __global__ void __launch_bounds__(kThreads) head_tta_accumulate_kernel(
     const __nv_bfloat16* __restrict__ feat, int ctot, int P0, int P1, int P2, const MirrorSet ms,
     const __grid_constant__ HeadParams hp, const int feat_f16, const float* __restrict__ gauss, float* __restrict__ acc, int Z, int Y, int X,
     int z0, int y0, int x0) {
-    const size_t pv = static_cast<size_t>(P0) * P1 * P2;
+    const int hw = blockIdx.x * blockDim.x + threadIdx.x;
+    if (hw >= P1 * P2) return;
+    const int d = blockIdx.y;
+    const int h = hw / P2, w = hw - h * P2;
     const size_t plane = static_cast<size_t>(Z) * Y * X;
-    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
     const float inv = hp.mirror_weight;
-    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < pv; i += stride) {
-        size_t r = i;
-        const int w = static_cast<int>(r % P2);
-        r /= P2;
-        const int h = static_cast<int>(r % P1);
-        const int d = static_cast<int>(r / P1);
-        float res[kMaxClasses];
+    float res[NCLS];
 #pragma unroll
-        for (int k = 0; k < kMaxClasses; ++k) res[k] = 0.f;
-        for (int m = 0; m < ms.n; ++m) {
-            const int code = ms.code[m];
-            // prediction m was computed on the flipped tile: its voxel for (d,h,w) sits at the flipped position
-            const int sw = (code & 1) ? P2 - 1 - w : w;
-            const int sh = (code & 2) ? P1 - 1 - h : h;
-            const int sd = (code & 4) ? P0 - 1 - d : d;
-            const size_t v = ((static_cast<size_t>(m) * P0 + sd) * P1 + sh) * P2 + sw;
-            const uint4* fp = reinterpret_cast<const uint4*>(feat + v * ctot);
-            float logit[kMaxClasses];
+    for (int k = 0; k < NCLS; ++k) res[k] = 0.f;
+#pragma unroll 2
+    for (int m = 0; m < ms.n; ++m) {
+        const int code = ms.code[m];
+        // prediction m was computed on the flipped tile: its voxel for (d,h,w) sits at the flipped position
+        const int sw = (code & 1) ? P2 - 1 - w : w;
+        const int sh = (code & 2) ? P1 - 1 - h : h;
+        const int sd = (code & 4) ? P0 - 1 - d : d;
+        const size_t v = ((static_cast<size_t>(m) * P0 + sd) * P1 + sh) * P2 + sw;
+        const uint4* fp = reinterpret_cast<const uint4*>(feat + v * ctot);
+        uint4 u[CFEAT / 8];
 #pragma unroll
-            for (int k = 0; k < kMaxClasses; ++k) logit[k] = hp.b[k];
-            for (int q = 0; q < hp.cfeat / 8; ++q) {
-                const uint4 u = __ldg(fp + q);
-                const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
-                float f[8];
+        for (int q = 0; q < CFEAT / 8; ++q) u[q] = (q * 8 < hp.cfeat) ? __ldg(fp + q) : make_uint4(0, 0, 0, 0);
+        float logit[NCLS];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (feat_f16) {
-                        const float2 h2 = __half22float2(*reinterpret_cast<const __half2*>(&ww[k]));
-                        f[2 * k] = h2.x;
-                        f[2 * k + 1] = h2.y;
-                    } else {
-                        const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&ww[k]);
-                        f[2 * k] = __bfloat162float(b2.x);
-                        f[2 * k + 1] = __bfloat162float(b2.y);
-                    }
-                }
+        for (int k = 0; k < NCLS; ++k) logit[k] = hp.b[k];
 #pragma unroll
-                for (int k = 0; k < kMaxClasses; ++k) {
-                    if (k < hp.ncls) {
+        for (int q = 0; q < CFEAT / 8; ++q) {
+            const uint32_t ww[4] = {u[q].x, u[q].y, u[q].z, u[q].w};
+            float f[8];
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) logit[k] = fmaf(hp.w[k][q * 8 + c], f[c], logit[k]);
-                    }
+            for (int k = 0; k < 4; ++k) {
+                if (feat_f16) {
+                    const float2 h2 = __half22float2(*reinterpret_cast<const __half2*>(&ww[k]));
+                    f[2 * k] = h2.x;
+                    f[2 * k + 1] = h2.y;
+                } else {
+                    const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&ww[k]);
+                    f[2 * k] = __bfloat162float(b2.x);
+                    f[2 * k + 1] = __bfloat162float(b2.y);
                 }
             }
-            if (hp.nonlin == 0) {
 #pragma unroll
-                for (int k = 0; k < kMaxClasses; ++k)
-                    if (k < hp.ncls) res[k] += inv * (1.0f / (1.0f + expf(-logit[k])));
-            } else if (hp.nonlin == 1) {
-                float mx = -INFINITY;
+            for (int k = 0; k < NCLS; ++k) {
 #pragma unroll
-                for (int k = 0; k < kMaxClasses; ++k)
-                    if (k < hp.ncls) mx = fmaxf(mx, logit[k]);
-                float e[kMaxClasses], sum = 0.f;
-#pragma unroll
-                for (int k = 0; k < kMaxClasses; ++k)
-                    if (k < hp.ncls) {
-                        e[k] = expf(logit[k] - mx);
-                        sum += e[k];
-                    }
-#pragma unroll
-                for (int k = 0; k < kMaxClasses; ++k)
-                    if (k < hp.ncls) res[k] += inv * (e[k] / sum);
-            } else {
-#pragma unroll
-                for (int k = 0; k < kMaxClasses; ++k)
-                    if (k < hp.ncls) res[k] += inv * logit[k];
+                for (int c = 0; c < 8; ++c) logit[k] = fmaf(hp.w[k][q * 8 + c], f[c], logit[k]);
             }
         }
-        const float g = gauss ? __ldg(gauss + i) : 1.0f;
-        float* ap = acc + (static_cast<size_t>(z0 + d) * Y + (y0 + h)) * X + (x0 + w);
+        if (hp.nonlin == 0) {
 #pragma unroll
-        for (int k = 0; k < kMaxClasses; ++k)
-            if (k < hp.ncls) ap[k * plane] += res[k] * g;
+            for (int k = 0; k < NCLS; ++k) res[k] += inv * (1.0f / (1.0f + expf(-logit[k])));
+        } else if (hp.nonlin == 1) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < NCLS; ++k)
+                if (k < hp.ncls) mx = fmaxf(mx, logit[k]);
+            float e[NCLS], sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < NCLS; ++k) {
+                e[k] = (k < hp.ncls) ? expf(logit[k] - mx) : 0.f;
+                sum += e[k];
+            }
+#pragma unroll
+            for (int k = 0; k < NCLS; ++k) res[k] += inv * (e[k] / sum);
+        } else {
+#pragma unroll
+            for (int k = 0; k < NCLS; ++k) res[k] += inv * logit[k];
+        }
     }
+    const float g = gauss ? __ldg(gauss + static_cast<size_t>(d) * P1 * P2 + hw) : 1.0f;
+    float* ap = acc + (static_cast<size_t>(z0 + d) * Y + (y0 + h)) * X + (x0 + w);
+#pragma unroll
+    for (int k = 0; k < NCLS; ++k)
+        if (k < hp.ncls) ap[k * plane] += res[k] * g;
 }
 
 // ---------------------------------------------------------------------------------------------- finalize
@@ -329,8 +326,8 @@ int bsg_gather_patch_tta(const float* vol, int C, int Z, int Y, int X, int z0, i
     MirrorSet ms;
     int rc = fill_mirrors(&ms, mirror_codes_host, nmirrors);
     if (rc != BSG_OK) return rc;
-    const size_t total = static_cast<size_t>(P0) * P1 * P2 * nmirrors;
-    gather_patch_kernel<<<grid_for(total, kThreads, 16), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+    dim3 grid(static_cast<unsigned>(ceil_div(P1 * P2, kThreads)), static_cast<unsigned>(P0), static_cast<unsigned>(nmirrors));
+    gather_patch_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         vol, C, Z, Y, X, z0, y0, x0, P0, P1, P2, ms, static_cast<__nv_bfloat16*>(out_bf16), cpad, out_f16);
     BSG_CUDA_OK(cudaGetLastError());
     return BSG_OK;
@@ -405,9 +402,21 @@ int bsg_head_tta_accumulate(const void* feat_bf16, int feat_f16, int cfeat, int 
         for (int c = 0; c < cfeat; ++c) hp.w[k][c] = head_w_host[k * cfeat + c];
         hp.b[k] = head_b_host ? head_b_host[k] : 0.f;
     }
-    const size_t pv = static_cast<size_t>(P0) * P1 * P2;
-    head_tta_accumulate_kernel<<<grid_for(pv, kThreads, 64), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(feat_bf16), ctot, P0, P1, P2, ms, hp, feat_f16, gauss, acc, Z, Y, X, z0, y0, x0);
+    dim3 grid(static_cast<unsigned>(ceil_div(P1 * P2, kThreads)), static_cast<unsigned>(P0));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const __nv_bfloat16* fp = static_cast<const __nv_bfloat16*>(feat_bf16);
+#define BSG_HEAD_LAUNCH(NC, CF)                                                                                     \
+    head_tta_accumulate_kernel<NC, CF><<<grid, kThreads, 0, st>>>(fp, ctot, P0, P1, P2, ms, hp, feat_f16, gauss, acc, Z, \
+                                                                  Y, X, z0, y0, x0)
+    if (ncls <= 4 && cfeat <= 32)
+        BSG_HEAD_LAUNCH(4, 32);
+    else if (ncls <= 4)
+        BSG_HEAD_LAUNCH(4, 64);
+    else if (cfeat <= 32)
+        BSG_HEAD_LAUNCH(8, 32);
+    else
+        BSG_HEAD_LAUNCH(8, 64);
+#undef BSG_HEAD_LAUNCH
     BSG_CUDA_OK(cudaGetLastError());
     return BSG_OK;
 }
