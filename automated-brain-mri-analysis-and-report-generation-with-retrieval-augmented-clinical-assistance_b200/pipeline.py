@@ -38,7 +38,7 @@ class BratsCasePipeline:
             self.predictors.append(sliding.SlidingWindowPredictor(engs, step_size, use_gaussian, codes,
                                                                   net._nonlin_name(), rank, world_size))
         self.device = self.predictors[0].device
-        self.conv_events = None  # optional: list collecting (start, end, flops) CUDA-event triples per engine run
+        self._post_stream = None
 
     def kernel_launches(self):
         return sum(p.kernel_launches for p in self.predictors)
@@ -55,9 +55,13 @@ class BratsCasePipeline:
             segs.append(seg)
         return segs
 
-    def run_case(self, volume, gt=None, voxel_dims=(1.0, 1.0, 1.0), features=True):
-        """volume: (C, Z, Y, X) float32, host (numpy / pinned tensor) or device.  Returns a dict with the ensemble
-        label volume in BraTS convention (device uint8) and the scalar results of the post-processing steps."""
+    # ------------------------------------------------------------------ two-phase API (cohort throughput)
+    # submit() enqueues the inference of a case and returns at once; finish() runs the post-processing on a second
+    # stream, whose host-side glue and small device->host reads then overlap the inference of the NEXT submitted case:
+    #     h = pipe.submit(case[0]); for i: nxt = pipe.submit(case[i+1]); out[i] = pipe.finish(h); h = nxt
+    def submit(self, volume, gt=None):
+        """volume: (C, Z, Y, X) float32, host (numpy / pinned tensor) or device; gt: optional label volume.  Enqueues
+        host->device copies, both models' sliding-window inference and the ensemble + remap; no host synchronisation."""
         if isinstance(volume, np.ndarray):
             volume = torch.from_numpy(volume)
         vol = volume.to(self.device, torch.float32, non_blocking=True).contiguous()
@@ -68,19 +72,44 @@ class BratsCasePipeline:
             brats = V.ensemble_round(segs[0], segs[1], post_lut=self.lut)  # ensemble + remap in one pass
         else:
             raise NotImplementedError("the reference ensembles exactly two models")
+        gt_dev = None
+        if gt is not None:
+            gt_dev = V.as_label_volume(gt)
+            if tuple(gt_dev.shape) != tuple(brats.shape):
+                gt_dev = gt  # let evaluate_arrays report the mismatch the way the reference does
+        done = torch.cuda.Event()
+        done.record()
+        return {"vol": vol, "segs": segs, "brats": brats, "gt": gt_dev, "done": done}
+
+    def finish(self, pending, voxel_dims=(1.0, 1.0, 1.0), features=True):
+        """Post-processing of a submitted case (Dice, components, morphology) on the pipeline's second stream."""
+        if self._post_stream is None:
+            self._post_stream = torch.cuda.Stream(self.device)
+        s = self._post_stream
+        s.wait_event(pending["done"])
+        brats, segs, gt = pending["brats"], pending["segs"], pending["gt"]
+        for t in [brats] + list(segs) + ([gt] if torch.is_tensor(gt) and gt.is_cuda else []):
+            t.record_stream(s)
         out = {"segmentation": brats, "model_segmentations": segs}
         self.extra_launches = 1
-        if gt is not None:
-            out["evaluation"] = EV.evaluate_arrays(brats, gt)
-            self.extra_launches += 1
-        if features:
-            lv = FU.LabelVolume(brats)
-            masks = FU.get_tumor_masks(lv)
-            out["components"] = S3.detect_connected_components(lv, voxel_dims)
-            out["enhancing"] = S3.analyze_enhancing_components(lv, voxel_dims)
-            out["shape"] = S4.calculate_shape_descriptors(lv, masks, voxel_dims)
-            out["necrosis"] = S4.analyze_necrosis_pattern(lv, masks, np.array(voxel_dims))
-            vv = float(np.prod(voxel_dims)) / 1000.0
-            out["volumes_cm3"] = {k: FU.calculate_volume(masks[k], vv) for k in ("ncr", "ed", "et", "tc", "wt")}
-            self.extra_launches += 2 * 8 + 2
+        with torch.cuda.stream(s):
+            if gt is not None:
+                out["evaluation"] = EV.evaluate_arrays(brats, gt)
+                self.extra_launches += 1
+            if features:
+                lv = FU.LabelVolume(brats)
+                masks = FU.get_tumor_masks(lv)
+                out["components"] = S3.detect_connected_components(lv, voxel_dims)
+                out["enhancing"] = S3.analyze_enhancing_components(lv, voxel_dims)
+                out["shape"] = S4.calculate_shape_descriptors(lv, masks, voxel_dims)
+                out["necrosis"] = S4.analyze_necrosis_pattern(lv, masks, np.array(voxel_dims))
+                vv = float(np.prod(voxel_dims)) / 1000.0
+                out["volumes_cm3"] = {k: FU.calculate_volume(masks[k], vv) for k in ("ncr", "ed", "et", "tc", "wt")}
+                self.extra_launches += 2 * 8 + 2
+            s.synchronize()
         return out
+
+    def run_case(self, volume, gt=None, voxel_dims=(1.0, 1.0, 1.0), features=True):
+        """One case start to finish: submit() + finish().  Returns a dict with the ensemble label volume in BraTS
+        convention (device uint8) and the scalar results of the post-processing steps."""
+        return self.finish(self.submit(volume, gt), voxel_dims, features)
