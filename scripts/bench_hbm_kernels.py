@@ -1,0 +1,112 @@
+"""Achieved HBM bandwidth of the memory-bound kernels at BASELINE sizes (CUDA events, best of 5, inputs > L2 or an L2
+flush between repetitions).  Algorithmic bytes are the minimum traffic stated in DESIGN.md.
+
+  python scripts/bench_hbm_kernels.py > gpurun_out/hbm_kernels.log
+"""
+import ctypes as C
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from brainseg_b200 import _lib as L
+from brainseg_b200 import convert_labels_to_brats as CL
+from brainseg_b200 import sliding
+from brainseg_b200 import voxelops as V
+from oracle import synthetic as SY
+
+dev = torch.device("cuda:0")
+lib = L.lib()
+PEAK = 6527.1
+if os.path.exists("MEASURED_PEAKS.json"):
+    PEAK = float(json.load(open("MEASURED_PEAKS.json")).get("hbm_gbs", PEAK))
+flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def timed(fn, reps=5):
+    fn()
+    best = 1e30
+    for _ in range(reps):
+        flush_buf.fill_(1)  # evict the 126 MB L2
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+
+
+def report(name, ms, nbytes):
+    gbs = nbytes / ms / 1e6
+    print(f"{name:44s} {ms:8.3f} ms  {nbytes / 1e6:9.1f} MB algorithmic  {gbs:7.0f} GB/s  {100 * gbs / PEAK:5.1f}% of measured {PEAK:.0f}",
+          flush=True)
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def main():
+    Vshape = (240, 240, 155)
+    nv = int(np.prod(Vshape))
+    pred, gt = SY.label_pair(0, Vshape)
+    a = torch.from_numpy(pred).to(dev)
+    b = torch.from_numpy(gt).to(dev)
+    report("label_lut_u8 (remap)", timed(lambda: V.label_lut(a, CL.LUT_BRATS2025)), 2 * nv)
+    report("label_pair_round_u8 (ensemble+remap)", timed(lambda: V.ensemble_round(a, b, post_lut=CL.LUT_BRATS2025)), 3 * nv)
+    buf = torch.empty(257, dtype=torch.int64, device=dev)
+    report("joint_hist_u8 (Dice bins)",
+           timed(lambda: L.check(lib.bsg_joint_hist_u8(ptr(a), ptr(b), nv, ptr(buf), C.c_void_p(buf.data_ptr() + 2048),
+                                                       L.stream_ptr()))), 2 * nv)
+    ws_bytes = lib.bsg_ccl26_workspace_bytes(*Vshape)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    labels = torch.empty(Vshape, dtype=torch.int32, device=dev)
+    ncomp = torch.zeros(1, dtype=torch.int32, device=dev)
+    st = torch.empty(4096 * 88, dtype=torch.uint8, device=dev)
+    report("ccl26_stats (6 kernels, blobby labels)",
+           timed(lambda: L.check(lib.bsg_ccl26_stats(ptr(a), *Vshape, V.MASK_GT0, ptr(labels), ptr(ncomp), ptr(st), 4096,
+                                                     ptr(ws), ws_bytes, L.stream_ptr()))), 5 * nv)
+    masks = (C.c_uint32 * 6)(*[V.bits_of(1), V.bits_of(2), V.bits_of(3), V.bits_of(1, 3), V.MASK_GT0, V.bits_of(3)])
+    out = torch.empty(6 * 120, dtype=torch.uint8, device=dev)
+    report("masked_moments (6 masks + surface)",
+           timed(lambda: L.check(lib.bsg_masked_moments(ptr(a), *Vshape, masks, 6, 0x10, ptr(out), L.stream_ptr()))), nv)
+
+    # sliding-window plumbing at the benchmark geometry
+    Z, Y, X = 155, 240, 240
+    vol = torch.randn(4, Z, Y, X, device=dev)
+    p = 128
+    pv = p ** 3
+    codes = (C.c_int * 8)(*range(8))
+    xin = torch.empty(8, p, p, p, 16, dtype=torch.bfloat16, device=dev)
+    report("gather_patch_tta (8 mirrors, 4->16 ch)",
+           timed(lambda: L.check(lib.bsg_gather_patch_tta(ptr(vol), 4, Z, Y, X, 27, 56, 56, p, p, p, codes, 8, ptr(xin), 16, 0,
+                                                          L.stream_ptr()))), 4 * pv * 4 + 8 * pv * 32)
+    feat = torch.randn(8, p, p, p, 32, device=dev).to(torch.bfloat16)
+    acc = torch.zeros(3, Z, Y, X, device=dev)
+    gauss = sliding.gaussian_importance_map((p, p, p), dev)
+    hw = (C.c_float * 96)(*np.random.default_rng(0).standard_normal(96).astype(np.float32))
+    report("head_tta_accumulate (8 mirrors, 32 ch, 3 cls)",
+           timed(lambda: L.check(lib.bsg_head_tta_accumulate(ptr(feat), 0, 32, 32, p, p, p, codes, 8, 0.125, hw, None, 3, 0,
+                                                             ptr(gauss), ptr(acc), Z, Y, X, 27, 56, 56, L.stream_ptr()))),
+           8 * pv * 64 + pv * (24 + 4))
+    wsum = torch.rand(Z, Y, X, device=dev) + 0.5
+    seg = torch.empty(Z, Y, X, dtype=torch.uint8, device=dev)
+    ptrs = (C.c_void_p * 1)(acc.data_ptr())
+    order = (C.c_int * 3)(1, 2, 3)
+    report("finalize (regions threshold, no probs)",
+           timed(lambda: L.check(lib.bsg_finalize(ptrs, 1, ptr(wsum), 3, Z * Y * X, 1, order, None, ptr(seg), L.stream_ptr()))),
+           Z * Y * X * 17)
+    x16 = torch.randn(4, p, p, p, 64, device=dev).to(torch.float16)
+    ss = torch.ones(4, 64, 2, device=dev)
+    report("norm_apply_lrelu (4 x 128^3 x 64 ch fp16)",
+           timed(lambda: L.check(lib.bsg_norm_apply_lrelu(ptr(x16), pv, 4, 64, 64, 0, ptr(ss), 0.01, 1, 1, L.stream_ptr()))),
+           2 * x16.numel() * 2)
+
+
+if __name__ == "__main__":
+    main()
