@@ -70,6 +70,11 @@ _EXTRA_SIGS = {
     "bsg_round_to_u8": [_vp, _i, _vp, _sz, _vp],
     "bsg_joint_hist_u8": [_vp, _vp, _sz, _vp, _vp, _vp],
     "bsg_ccl26_stats": [_vp, _i, _i, _i, _u32, _vp, _vp, _vp, _i, _vp, _sz, _vp],
+    "bsg_ccl_stats": [_vp, _i, _i, _i, _u32, _i, _vp, _vp, _vp, _i, _vp, _sz, _vp],
+    "bsg_nonzero_mask": [_vp, _i, _i, _i, _i, _vp, _vp],
+    "bsg_fill_holes_u8": [_vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp, _sz, _vp],
+    "bsg_masked_channel_stats": [_vp, _i, _sz, _vp, _vp, _vp],
+    "bsg_crop_normalize": [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "bsg_masked_moments": [_vp, _i, _i, _i, C.POINTER(_u32), _i, _u32, _vp, _vp],
     "bsg_gather_patch_tta": [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(_i), _i, _vp, _i, _i, _vp],
     "bsg_norm_finalize": [_vp, _i, _i, _i, _d, _f, _vp, _vp, _vp, _vp],

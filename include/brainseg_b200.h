@@ -131,6 +131,11 @@ typedef struct bsg_comp_stats {
  * count exceeds stats_cap only the first stats_cap components are recorded.  workspace: device scratch of at least
  * bsg_ccl26_workspace_bytes(). */
 size_t bsg_ccl26_workspace_bytes(int d0, int d1, int d2);
+/* Same with a choice of connectivity: 26 (above) or 6 (scipy.ndimage's default structure — the one binary_fill_holes
+ * uses in nnU-Net v1 create_nonzero_mask).  Label value 0 may be the foreground (maskbits bit 0). */
+int bsg_ccl_stats(const uint8_t* vol, int d0, int d1, int d2, uint32_t maskbits, int connectivity, int* labels,
+                  int* ncomp_dev, void* comp_stats, int stats_cap, void* workspace, size_t workspace_bytes,
+                  void* stream);
 int bsg_ccl26_stats(const uint8_t* vol, int d0, int d1, int d2, uint32_t maskbits, int* labels, int* ncomp_dev,
                     void* comp_stats, int stats_cap, void* workspace, size_t workspace_bytes, void* stream);
 
@@ -149,6 +154,26 @@ typedef struct bsg_mask_moments {
  * surface-voxel count with SciPy's border_value=0 semantics.  maskbits_host: nmask host words; out: device records. */
 int bsg_masked_moments(const uint8_t* vol, int d0, int d1, int d2, const uint32_t* maskbits_host, int nmask,
                        uint32_t want_surface, void* out_moments, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Preprocessing of one case — trainer.preprocess_patient (run_brats2021_inference_singlethread.py:89); UPSTREAM nnU-Net
+ * v1 crop_to_nonzero + GenericPreprocessor "nonCT" normalisation with use_mask_for_norm.
+ * vol: fp32 (C, Z, Y, X).
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* mask[z][y][x] = any modality != 0 (create_nonzero_mask before hole filling). */
+int bsg_nonzero_mask(const float* vol, int C, int Z, int Y, int X, uint8_t* mask, void* stream);
+/* scipy.ndimage.binary_fill_holes(mask) in place: background voxels whose 6-connected component does not reach a face
+ * of the volume become 1.  labels (int32, same shape), ncomp_dev (1 int), flags (>= n/2 + 2 bytes) and workspace
+ * (bsg_ccl26_workspace_bytes) are device scratch. */
+int bsg_fill_holes_u8(uint8_t* mask, int d0, int d1, int d2, int* labels, int* ncomp_dev, uint8_t* flags, size_t flags_cap,
+                      void* workspace, size_t workspace_bytes, void* stream);
+/* out[c] = (sum, sum of squares, count) in fp64 of vol[c][i] over mask[i] != 0 — data[c][mask].mean() / .std(). */
+int bsg_masked_channel_stats(const float* vol, int C, size_t n, const uint8_t* mask, double* out, void* stream);
+/* out[c] over the crop box (z0, y0, x0) + (cz, cy, cx): mask ? (v - mean_c) / (std_c + 1e-8) : 0 in float32 arithmetic
+ * (mean_std: device fp32 [C][2]); mask_out (may be NULL) receives the cropped mask. */
+int bsg_crop_normalize(const float* vol, int C, int Z, int Y, int X, const uint8_t* mask, int z0, int y0, int x0, int cz,
+                       int cy, int cx, const float* mean_std, float* out, uint8_t* mask_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Sliding-window plumbing of predict_3D (nnU-Net v1 _internal_predict_3D_3Dconv_tiled /
