@@ -148,3 +148,33 @@ def test_remap_luts_and_dice_formulas_on_host():
     assert CL.LUT_BRATS2025[5:].sum() == 0
     m = EV._metrics(np.float32(10), np.float32(2), np.float32(3), np.float32(100))
     assert m["dice"].dtype == np.float32 and m["dice"] == np.float32(20) / (np.float32(20) + np.float32(2) + np.float32(3) + 1e-8)
+
+
+def test_nifti_round_trip(tmp_path):
+    from brainseg_b200 import nifti_io as N
+
+    d = np.random.default_rng(0).standard_normal((5, 6, 7)).astype(np.float32)
+    like = N.new_header(d.shape, (1.0, 1.5, 2.0))
+    for ext in (".nii", ".nii.gz"):
+        p = str(tmp_path / ("a" + ext))
+        N.save(p, d, like)
+        im = N.load(p)
+        assert np.array_equal(im.data, d) and im.zooms == (1.0, 1.5, 2.0)
+        N.save(p, (d > 0).astype(np.uint8), im)  # label map written with the source image's geometry
+        im2 = N.load(p)
+        assert im2.data.dtype == np.uint8 and np.array_equal(im2.get_fdata(), (d > 0).astype(np.float64))
+    with pytest.raises(ValueError):
+        N.save(str(tmp_path / "b.nii"), np.zeros((2, 2, 2), np.uint8), like)  # geometry mismatch
+
+
+def test_network_config_is_inferred_from_the_checkpoint():
+    from brainseg_b200 import nnunet_compat as NC
+    from tests.helpers import build_dropin_unet
+
+    for kw, name in ((dict(variant="bn", base=32, num_pool=5), "nnUNetTrainerV2BraTSRegions_DA4_BN_BD"),
+                     (dict(variant="gn", base=32, num_pool=5, groups=8, encoder_scale=2, max_num_features=512),
+                      "nnUNetTrainerV2BraTSRegions_DA4_BN_BD_largeUnet_Groupnorm"),
+                     (dict(variant="in", base=16, num_pool=2), "")):
+        sd = build_dropin_unet(**kw).state_dict()
+        sd2 = NC.build_network(NC.infer_network_config(sd, name)).state_dict()
+        assert list(sd) == list(sd2) and all(sd[k].shape == sd2[k].shape for k in sd)
