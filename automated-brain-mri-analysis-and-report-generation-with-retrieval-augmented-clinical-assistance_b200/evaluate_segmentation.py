@@ -82,3 +82,82 @@ def evaluate_arrays(pred_data, gt_data):
     et = all_metrics.get(3)
     mean_dice = np.mean([wt["dice"], tc["dice"], et["dice"] if et is not None else 0])
     return {"labels": all_metrics, "wt": wt, "tc": tc, "et": et, "mean_dice": mean_dice}
+
+
+# ---------------------------------------------------------------------------------------------- file-level CLI
+LABEL_NAMES = {0: "Background", 1: "NCR (Necrotic Tumor Core)", 2: "ED (Peritumoral Edema)", 3: "ET (Enhancing Tumor)",
+               4: "ET (Enhancing Tumor - alternate)"}
+
+
+def evaluate_segmentation(pred_path, gt_path):
+    """Compare a predicted with a ground-truth NIfTI label file (reference evaluate_segmentation.py:52-178): same console
+    wording — run_full_pipeline.py:252-269 parses it — same return value (label -> metrics, None on shape mismatch)."""
+    from . import nifti_io
+
+    print("=" * 80)
+    print("SEGMENTATION EVALUATION")
+    print("=" * 80)
+    print(f"\nPredicted file: {pred_path}")
+    print(f"Ground truth file: {gt_path}")
+    print("\nLoading files...")
+    pred_data, gt_data = nifti_io.load(str(pred_path)).get_fdata(), nifti_io.load(str(gt_path)).get_fdata()
+    # nibabel reports (x, y, z); the arrays here are (z, y, x)
+    print(f"Prediction shape: {tuple(reversed(pred_data.shape))}")
+    print(f"Ground truth shape: {tuple(reversed(gt_data.shape))}")
+    res = evaluate_arrays(pred_data, gt_data)
+    if res is None:
+        return None
+    print(f"\nUnique labels in prediction: {np.unique(pred_data)}")
+    print(f"Unique labels in ground truth: {np.unique(gt_data)}")
+    print("\n" + "=" * 80 + "\nRESULTS BY CLASS\n" + "=" * 80)
+    all_metrics = {np.float64(k): v for k, v in res["labels"].items()}
+    for label, metrics in res["labels"].items():
+        label_name = LABEL_NAMES.get(label, f"Label {float(label)}")
+        print(f"\n{label_name} (Label {float(label)}):")
+        print(f"  Dice Score:      {metrics['dice']:.4f} ({metrics['dice'] * 100:.2f}%)")
+        print(f"  IoU (Jaccard):   {metrics['iou']:.4f} ({metrics['iou'] * 100:.2f}%)")
+        print(f"  Sensitivity:     {metrics['sensitivity']:.4f} ({metrics['sensitivity'] * 100:.2f}%)")
+        print(f"  Specificity:     {metrics['specificity']:.4f} ({metrics['specificity'] * 100:.2f}%)")
+        print(f"  True Positives:  {int(metrics['tp']):,}")
+        print(f"  False Positives: {int(metrics['fp']):,}")
+        print(f"  False Negatives: {int(metrics['fn']):,}")
+    print("\n" + "=" * 80 + "\nCOMPOUND METRICS (BraTS Standard)\n" + "=" * 80)
+    for title, m in (("Whole Tumor (WT) - Labels 1, 2, 3 combined:", res["wt"]),
+                     ("Tumor Core (TC) - Labels 1, 3 combined:", res["tc"]),
+                     ("Enhancing Tumor (ET) - Label 3 only:", res["et"])):
+        if m is None:
+            continue
+        print(f"\n{title}")
+        print(f"  Dice Score:      {m['dice']:.4f} ({m['dice'] * 100:.2f}%)")
+        print(f"  IoU:             {m['iou']:.4f} ({m['iou'] * 100:.2f}%)")
+        print(f"  Sensitivity:     {m['sensitivity']:.4f} ({m['sensitivity'] * 100:.2f}%)")
+    print("\n" + "=" * 80 + "\nOVERALL PERFORMANCE\n" + "=" * 80)
+    print(f"\nMean Dice Score (WT, TC, ET): {res['mean_dice']:.4f} ({res['mean_dice'] * 100:.2f}%)")
+    print("\n" + "=" * 80 + "\nINTERPRETATION\n" + "=" * 80)
+    print("\nDice Score Interpretation:\n  > 0.90: Excellent\n  0.80 - 0.90: Good\n  0.70 - 0.80: Moderate\n"
+          "  0.50 - 0.70: Fair\n  < 0.50: Poor")
+    print("\nNote: BraTS competition typically reports Dice scores for WT, TC, and ET.")
+    print("      State-of-the-art models achieve Dice scores of 0.85-0.92 for these regions.")
+    return all_metrics
+
+
+def main(argv=None):
+    import argparse
+    from pathlib import Path
+
+    parser = argparse.ArgumentParser(description="Evaluate brain tumor segmentation")
+    parser.add_argument("--pred", type=str, required=True, help="Path to predicted segmentation file (.nii.gz)")
+    parser.add_argument("--gt", type=str, required=True, help="Path to ground truth segmentation file (.nii.gz)")
+    args = parser.parse_args(argv)
+    pred_path, gt_path = Path(args.pred), Path(args.gt)
+    if not pred_path.exists():
+        print(f"Error: Predicted file not found: {pred_path}")
+        raise SystemExit(1)
+    if not gt_path.exists():
+        print(f"Error: Ground truth file not found: {gt_path}")
+        raise SystemExit(1)
+    evaluate_segmentation(pred_path, gt_path)
+
+
+if __name__ == "__main__":
+    main()
