@@ -255,6 +255,19 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
             return set_error(BSG_EINVAL, "cannot tile cout %d", d->cout);
         }
     }
+    if (d->kind != BSG_CONVT_K2S2) {
+        // small levels (<= 8^3 voxels per item): a handful of 128-voxel tiles cannot fill 148 SMs, and each CTA then walks
+        // the whole K = 27 * Cin loop at N = 256.  Narrower N tiles (>= 64 columns, still 67 % tensor-efficient) multiply
+        // the CTA count and divide every CTA's MMA time; the activation tile they re-read is tiny.
+        const long long mtiles = static_cast<long long>(a.tw) * a.th * a.td * a.tn;
+        const int sms = sm_count_cached();
+        while (mtiles * split < sms) {
+            int next = split + 1;
+            while (next <= a.cout_pad / 32 && (a.cout_pad % next != 0 || (a.cout_pad / next) % 32 != 0)) ++next;
+            if (next > a.cout_pad / 32 || a.cout_pad / next < 64 || mtiles * next > sms) break;  // stay within one wave
+            split = next;
+        }
+    }
     a.ntile = a.cout_pad / split;
     a.out_mul = (d->kind == BSG_CONVT_K2S2) ? 2 : 1;
     a.n_ntiles = split * (a.out_mul == 2 ? 8 : 1);

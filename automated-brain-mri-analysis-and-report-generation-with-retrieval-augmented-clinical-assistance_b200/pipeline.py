@@ -24,34 +24,43 @@ class BratsCasePipeline:
     def __init__(self, models, patch_size=(128, 128, 128), step_size=0.5, mirror_axes=(0, 1, 2), do_mirroring=True,
                  use_gaussian=True, regions_class_order=(1, 2, 3), label_format="brats2025", batch=8, rank=0,
                  world_size=1, reduce_fn=None, lanes=None):
-        """models: drop-in Generic_UNet instances (each may stand for one fold); `reduce_fn(acc)` sums an accumulator
-        over ranks when the (tile, mirror) work items of ONE case are sharded (latency mode)."""
-        self.models = list(models)
+        """models: one entry per ensemble member — a drop-in Generic_UNet, or a list of them = the folds of that model,
+        whose probabilities are averaged before the decision (np.mean over folds, reference :128);
+        `reduce_fn(acc)` sums an accumulator over ranks when the (tile, mirror) work items of ONE case are sharded
+        (latency mode)."""
+        self.models = [list(m) if isinstance(m, (list, tuple)) else [m] for m in models]
         self.patch = tuple(patch_size)
         self.regions = regions_class_order
         self.lut = CL.LUT_BRATS2025 if label_format == "brats2025" else CL.LUT_BRATS2021
         self.reduce_fn = reduce_fn
         codes = sliding.mirror_codes_for(mirror_axes, do_mirroring)
-        self.predictors = []
-        for net in self.models:
-            engs = net.engines_for(self.patch, batch, lanes)
-            self.predictors.append(sliding.SlidingWindowPredictor(engs, step_size, use_gaussian, codes,
-                                                                  net._nonlin_name(), rank, world_size))
+        self.fold_predictors = []  # [model][fold]
+        for folds in self.models:
+            row = []
+            for net in folds:
+                engs = net.engines_for(self.patch, batch, lanes)
+                row.append(sliding.SlidingWindowPredictor(engs, step_size, use_gaussian, codes, net._nonlin_name(), rank,
+                                                          world_size))
+            self.fold_predictors.append(row)
+        self.predictors = [row[0] for row in self.fold_predictors]  # first fold of every model (bench / diagnostics)
         self.device = self.predictors[0].device
         self._post_stream = None
 
     def kernel_launches(self):
-        return sum(p.kernel_launches for p in self.predictors)
+        return sum(p.kernel_launches for row in self.fold_predictors for p in row)
 
     def segment(self, vol):
         """vol: fp32 cuda tensor (C, Z, Y, X), extents >= patch.  Returns the per-model uint8 label volumes."""
         shape = tuple(vol.shape[1:])
         segs = []
-        for pred in self.predictors:
-            acc = pred.accumulate(vol)
-            if self.reduce_fn is not None:
-                acc = self.reduce_fn(acc)
-            seg, _ = pred.finalize([acc], shape, self.regions, want_probs=False)
+        for row in self.fold_predictors:
+            accs = []
+            for pred in row:
+                acc = pred.accumulate(vol)
+                if self.reduce_fn is not None:
+                    acc = self.reduce_fn(acc)
+                accs.append(acc)
+            seg, _ = row[0].finalize(accs, shape, self.regions, want_probs=False)  # mean over folds, then decide
             segs.append(seg)
         return segs
 

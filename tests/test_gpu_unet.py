@@ -126,3 +126,33 @@ def test_forward_full_patch_brats_architectures(variant):
     rms = (got - ref).pow(2).mean().sqrt().item()
     print(f"{variant}: logits rms err {rms:.4g} (scale {ref.abs().max().item():.3g}), sigmoid max err {perr:.4g}")
     assert perr < PROB_TOL
+
+
+def test_case_pipeline_folds_and_two_model_ensemble():
+    """BratsCasePipeline with two folds per model: device-side fold mean (bsg_finalize over K accumulators) + regions
+    decision + label-round ensemble + BraTS remap against the oracle chain (reference :128, :144-156, :305)."""
+    from brainseg_b200 import pipeline as PL
+    from oracle import postproc as OP
+
+    models = [[build_dropin_unet("bn", base=16, num_pool=2, seed=31), build_dropin_unet("bn", base=16, num_pool=2, seed=32)],
+              [build_dropin_unet("gn", base=16, num_pool=2, groups=4, seed=33),
+               build_dropin_unet("gn", base=16, num_pool=2, groups=4, seed=34)]]
+    vol = torch.randn(4, 40, 48, 36, generator=torch.Generator().manual_seed(9)).numpy()
+    patch = (32, 32, 32)
+    pipe = PL.BratsCasePipeline(models, patch, 0.5, (0, 1, 2), True, True, (1, 2, 3), "brats2025", batch=8)
+    out = pipe.run_case(vol, features=False)
+    segs_ref, decisive = [], np.ones(vol.shape[1:], dtype=bool)
+    for folds in models:
+        probs = [SW.predict_3d_tiled(oracle_fns(n)[0], torch.sigmoid, vol, 3, patch, True, (0, 1, 2), 0.5, True, (1, 2, 3))[1]
+                 for n in folds]
+        mean = np.mean(probs, axis=0)
+        seg = np.zeros(mean.shape[1:], dtype=np.uint8)
+        for i, c in enumerate((1, 2, 3)):
+            seg[mean[i] > 0.5] = c
+        segs_ref.append(seg)
+        decisive &= np.all(np.abs(mean - 0.5) > PROB_TOL, axis=0)
+    for got, ref in zip(out["model_segmentations"], segs_ref):
+        assert np.array_equal(got.cpu().numpy()[decisive], ref[decisive])
+    final_ref = OP.convert_labels_to_brats2025(OP.ensemble_labels_round(segs_ref[0], segs_ref[1]).astype(np.float64))
+    assert np.array_equal(out["segmentation"].cpu().numpy()[decisive], final_ref[decisive])
+    print(f"decisive voxels {decisive.mean() * 100:.1f}%")
