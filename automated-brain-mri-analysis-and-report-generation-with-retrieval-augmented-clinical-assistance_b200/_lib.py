@@ -80,7 +80,7 @@ _EXTRA_SIGS = {
     "bsg_norm_finalize": [_vp, _i, _i, _i, _d, _f, _vp, _vp, _vp, _vp],
     "bsg_norm_apply_lrelu": [_vp, _sz, _i, _i, _i, _i, _vp, _f, _i, _i, _vp],
     "bsg_head_tta_accumulate": [_vp, _i, _i, _i, _i, _i, _i, C.POINTER(_i), _i, _f, C.POINTER(_f), C.POINTER(_f), _i, _i,
-                                _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+                                _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _f, _vp],
     "bsg_finalize": [C.POINTER(_vp), _i, _vp, _i, _sz, _i, C.POINTER(_i), _vp, _vp, _vp],
 }
 

@@ -173,7 +173,7 @@ template <int NCLS, int CFEAT>
 __global__ void __launch_bounds__(kThreads) head_tta_accumulate_kernel(
     const __nv_bfloat16* __restrict__ feat, int ctot, int P0, int P1, int P2, const MirrorSet ms,
     const __grid_constant__ HeadParams hp, const int feat_f16, const float* __restrict__ gauss, float* __restrict__ acc, int Z, int Y, int X,
-    int z0, int y0, int x0) {
+    int z0, int y0, int x0, const float* __restrict__ norm_ss, const float norm_slope) {
     const int hw = blockIdx.x * blockDim.x + threadIdx.x;
     if (hw >= P1 * P2) return;
     const int d = blockIdx.y;
@@ -212,6 +212,18 @@ __global__ void __launch_bounds__(kThreads) head_tta_accumulate_kernel(
                     const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&ww[k]);
                     f[2 * k] = __bfloat162float(b2.x);
                     f[2 * k + 1] = __bfloat162float(b2.y);
+                }
+            }
+            if (norm_ss != nullptr) {
+                // deferred InstanceNorm / GroupNorm + LeakyReLU of the last conv block (the features are its raw
+                // output): y = lrelu(x * scale[m][c] + shift[m][c]) — saves the block's separate normalise pass
+                const float4* ss = reinterpret_cast<const float4*>(norm_ss + (static_cast<size_t>(m) * hp.cfeat + q * 8) * 2);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float4 t = (q * 8 < hp.cfeat) ? __ldg(ss + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float a = fmaf(f[2 * c], t.x, t.y), b = fmaf(f[2 * c + 1], t.z, t.w);
+                    f[2 * c] = a > 0.f ? a : a * norm_slope;
+                    f[2 * c + 1] = b > 0.f ? b : b * norm_slope;
                 }
             }
 #pragma unroll
@@ -380,7 +392,7 @@ int bsg_head_tta_accumulate(const void* feat_bf16, int feat_f16, int cfeat, int 
                             const int* mirror_codes_host, int nmirrors, float mirror_weight,
                             const float* head_w_host, const float* head_b_host, int ncls, int nonlin,
                             const float* gauss, float* acc, int Z, int Y, int X, int z0, int y0, int x0,
-                            void* stream) {
+                            const float* norm_scale_shift, float norm_slope, void* stream) {
     BSG_REQUIRE(feat_bf16 != nullptr && head_w_host != nullptr && acc != nullptr, "null argument");
     BSG_REQUIRE(cfeat % 8 == 0 && cfeat >= 8 && cfeat <= kMaxHeadCh, "head input channels %d (8..64, multiple of 8)",
                 cfeat);
@@ -407,7 +419,7 @@ int bsg_head_tta_accumulate(const void* feat_bf16, int feat_f16, int cfeat, int 
     const __nv_bfloat16* fp = static_cast<const __nv_bfloat16*>(feat_bf16);
 #define BSG_HEAD_LAUNCH(NC, CF)                                                                                     \
     head_tta_accumulate_kernel<NC, CF><<<grid, kThreads, 0, st>>>(fp, ctot, P0, P1, P2, ms, hp, feat_f16, gauss, acc, Z, \
-                                                                  Y, X, z0, y0, x0)
+                                                                  Y, X, z0, y0, x0, norm_scale_shift, norm_slope)
     if (ncls <= 4 && cfeat <= 32)
         BSG_HEAD_LAUNCH(4, 32);
     else if (ncls <= 4)

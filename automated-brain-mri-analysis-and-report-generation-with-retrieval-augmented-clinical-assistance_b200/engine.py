@@ -63,9 +63,11 @@ class UNetEngine:
         self.act_dtype = torch.float16 if self.f16 else torch.bfloat16
         self.steps = []       # callables, in launch order
         self.step_info = []   # per step: name, algorithmic flops, plan geometry (diagnostics / bench breakdown)
+        self.plans = []       # per step: the conv plan (bench.py times the dominant layer's launch alone)
         self.keep = []        # tensors the plans point at
         self.launches_per_forward = 0
         self.flops = 0.0
+        self.final_norm = None  # (scale_shift [batch][C][2], slope) when the last block's norm is left to the head
         self.sub_events = None  # scripts/diag_case.py: events recorded between a conv and its norm passes
         self.event_log = None  # bench.py: list collecting (start, end) CUDA events around each run()
         self._build()
@@ -76,7 +78,7 @@ class UNetEngine:
         self.keep.append(t)
         return t
 
-    def _add_block(self, blk, src, dst, spatial_in):
+    def _add_block(self, blk, src, dst, spatial_in, defer_apply=False):
         conv, norm = blk.conv, blk.instnorm
         stride = int(conv.stride[0])
         w = conv.weight.detach().to(self.device, torch.float32)
@@ -137,11 +139,14 @@ class UNetEngine:
                 ev.record()
                 self.sub_events.append(ev)
             L.check(lib.bsg_norm_finalize(_ptr(stats), self.batch, cout, groups, float(vox), eps, gp, bp2, _ptr(ss), sp))
-            L.check(lib.bsg_norm_apply_lrelu(_ptr(dst.buf), vox, self.batch, cout, dst.ctot, dst.coff, _ptr(ss), slope, 1,
-                                             self.f16, sp))
+            if not defer_apply:
+                L.check(lib.bsg_norm_apply_lrelu(_ptr(dst.buf), vox, self.batch, cout, dst.ctot, dst.coff, _ptr(ss), slope,
+                                                 1, self.f16, sp))
 
         self.steps.append(run)
-        self.launches_per_forward += 4
+        self.launches_per_forward += 3 if defer_apply else 4
+        if defer_apply:  # the consumer (head kernel / forward_logits) normalises on the fly
+            self.final_norm = (ss, slope)
 
     def _add_tu(self, tu, src, dst, spatial_in):
         w = tu.weight.detach().to(self.device, torch.float32)
@@ -159,6 +164,7 @@ class UNetEngine:
 
     def _note(self, name, plan):
         i = plan.info()
+        self.plans.append(plan)
         self.step_info.append({"name": name, "flops": i.flops,
                                "plan": f"box {i.bw}x{i.bh}x{i.bd}x{i.bn} ntile {i.ntile}x{i.n_ntiles} cc {i.cc} "
                                        f"stages {i.nstages} khs {i.khshift} grid {i.grid}"})
@@ -198,9 +204,12 @@ class UNetEngine:
             spatial = tuple(2 * s for s in spatial)
             cur = _Act(cat, 0, 2 * cskip)
             loc = net.conv_blocks_localization[u]
-            for blk in list(loc[0].blocks) + list(loc[1].blocks):
+            blks = list(loc[0].blocks) + list(loc[1].blocks)
+            for j, blk in enumerate(blks):
                 dst = _Act(self._alloc(spatial, blk.conv.out_channels), 0, blk.conv.out_channels)
-                self._add_block(blk, cur, dst, spatial)
+                # the very last block's norm + LeakyReLU is applied by its only consumer, the head
+                last = (u == num_pool - 1) and (j == len(blks) - 1) and blk.conv.out_channels <= 64
+                self._add_block(blk, cur, dst, spatial, defer_apply=last)
                 cur = dst
         self.features = cur
         head = net.seg_outputs[num_pool - 1]
@@ -235,6 +244,9 @@ class UNetEngine:
         self.x.buf[:n, ..., :self.in_channels] = x.to(self.device).permute(0, 2, 3, 4, 1).to(self.act_dtype)
         self.run()
         f = self.features.view()[:n].float()  # (n, d, h, w, c)
+        if self.final_norm is not None:
+            ss, slope = self.final_norm
+            f = torch.nn.functional.leaky_relu(f * ss[:n, :, 0].view(n, 1, 1, 1, -1) + ss[:n, :, 1].view(n, 1, 1, 1, -1), slope)
         logits = torch.einsum("ndhwc,kc->nkdhw", f, self.head_w.to(self.device))
         if self.head_b is not None:
             logits = logits + self.head_b.to(self.device).view(1, -1, 1, 1, 1)

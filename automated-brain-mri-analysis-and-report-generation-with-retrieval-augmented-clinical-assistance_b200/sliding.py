@@ -148,6 +148,15 @@ class SlidingWindowPredictor:
         cfeat = eng0.head_w.shape[1]
         gptr = _ptr(gauss) if gauss is not None else None
 
+        def nss(eng, first_item):  # deferred last-block norm of `eng`: scale/shift rows of the group's batch items
+            if eng.final_norm is None:
+                return None
+            ss = eng.final_norm[0]
+            return C.c_void_p(ss.data_ptr() + first_item * ss.shape[1] * 2 * 4)
+
+        def nslope(eng):
+            return float(eng.final_norm[1]) if eng.final_norm is not None else 0.0
+
         def groups_of(chunk):
             # consecutive items of the same tile: one gather / one head launch per group
             out, start = [], 0
@@ -192,7 +201,7 @@ class SlidingWindowPredictor:
                         fptr = feat.buf.data_ptr() + 2 * (a * pv * feat.ctot + feat.coff)
                         L.check(lib.bsg_head_tta_accumulate(C.c_void_p(fptr), eng.f16, cfeat, feat.ctot, p0, p1, p2, codes, b - a,
                                                             weight, hw, hb, eng.num_classes, self.nonlin, gptr,
-                                                            _ptr(acc), Z, Y, X, z, y, x, sp))
+                                                            _ptr(acc), Z, Y, X, z, y, x, nss(eng, a), nslope(eng), sp))
                     if multi:
                         head_done = torch.cuda.Event()
                         head_done.record(s)

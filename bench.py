@@ -342,6 +342,20 @@ def run_ours(args):
         b.record()
         torch.cuda.synchronize()
         conv_ms.append(a.elapsed_time(b))
+    # dominant launch: the conv layer with the most FLOPs (model 2's 128->64 @128^3 brick-kernel launch), timed alone
+    dom_eng = max((eng1, eng2), key=lambda e: max(i["flops"] for i in e.step_info))
+    dom_idx = max(range(len(dom_eng.step_info)), key=lambda i: dom_eng.step_info[i]["flops"])
+    dom_plan, dom_info = dom_eng.plans[dom_idx], dom_eng.step_info[dom_idx]
+    dom_plan.run()
+    torch.cuda.synchronize()
+    dom_reps = 6
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(dom_reps):
+        dom_plan.run()
+    b.record()
+    torch.cuda.synchronize()
+    dom_ms = a.elapsed_time(b) / dom_reps
     clocks = sampler.stop() if sampler is not None else None
 
     times = torch.tensor([t_res, t_e2e], dtype=torch.float64, device=dev)
@@ -352,23 +366,27 @@ def run_ours(args):
 
     if rank == 0:
         peaks = load_peaks()
-        # dominant kernel: conv_tc_kernel.  Model 1 (BatchNorm folded) runs nothing else inside engine.run().
-        flops1 = eng1.flops  # algorithmic 2*MAC of one engine.run() (a lane's batch of tile-mirrors)
-        launches1 = eng1.launches_per_forward
-        avg_launch_s = conv_ms[0] / 1e3 / (conv_runs * launches1)
-        achieved = (flops1 / launches1) / avg_launch_s / 1e12 if avg_launch_s > 0 else 0.0
-        conv2_tflops = eng2.flops * conv_runs / (conv_ms[1] / 1e3) / 1e12 if conv_ms[1] > 0 else 0.0
+        # forward aggregates (all conv launches of each model) and the dominant launch
+        fwd_tflops = [e.flops * conv_runs / (ms / 1e3) / 1e12 for e, ms in zip((eng1, eng2), conv_ms)]
         fwd_per_case = N_TILES * N_MIRRORS
         conv_alone_s = sum(ms / 1e3 / conv_runs / e.batch for ms, e in zip(conv_ms, (eng1, eng2))) * fwd_per_case
-        roofline = {"bound": "tensor", "kernel": "conv_brick_kernel / conv_tc_kernel (tcgen05 implicit-GEMM conv3d), "
-                                                 "all conv launches of model 1's forward",
+        achieved = dom_info["flops"] / (dom_ms / 1e3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+        if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from one ncu --set full capture
+            with open(tpath) as f:
+                traffic = json.load(f)
+        roofline = {"bound": "tensor",
+                    "kernel": f"conv_brick_kernel (tcgen05 implicit-GEMM conv3d): {dom_info['name']}, "
+                              f"{dom_eng.batch} tile-mirrors per launch ({dom_info['plan']})",
                     "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                    "frac": achieved / peaks["tflops"], "traffic": None, "peak_source": peaks["source"],
-                    "flops_per_launch": flops1 / launches1, "avg_launch_ms": avg_launch_s * 1e3,
-                    "launches_timed": conv_runs * launches1, "batch_per_launch": eng1.batch,
-                    "timed": "dedicated single-stream pass after the timed steps (the steps overlap two stream lanes)",
-                    "share_of_step": conv_alone_s / (t_res / args.steps),
-                    "model2_conv_stack_tflops_incl_norm_passes": conv2_tflops}
+                    "frac": achieved / peaks["tflops"], "traffic": traffic, "peak_source": peaks["source"],
+                    "flops_per_launch": dom_info["flops"], "avg_launch_ms": dom_ms, "launches_timed": dom_reps,
+                    "share_of_forward": dom_ms / (conv_ms[1 if dom_eng is eng2 else 0] / conv_runs),
+                    "timed": "dedicated single-stream pass after the timed steps (the steps overlap two stream lanes), "
+                             "CUDA events on the launching stream, same buffers",
+                    "model1_forward_tflops": fwd_tflops[0], "model2_forward_tflops_incl_norm_passes": fwd_tflops[1],
+                    "conv_share_of_step": conv_alone_s / (t_res / args.steps)}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             c = cpu_reference_sample(args.model2, include_post=True)

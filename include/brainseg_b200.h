@@ -205,12 +205,15 @@ int bsg_norm_apply_lrelu(void* x, size_t voxels_per_item, int N, int C, int ctot
  * result += mirror_weight * pred (mirror_weight = 1/num_results of the whole TTA), result *= gaussian,
  * aggregated_results[:, tile] += result.
  * feat: bf16 (fp16 when feat_f16 = 1) (nmirrors, P0, P1, P2, ctot) with the cfeat head inputs in channels [0,cfeat) (cfeat % 8 == 0, <= 64);
- * acc: fp32 [ncls][Z][Y][X]; gauss: fp32 [P0][P1][P2] or NULL. */
+ * acc: fp32 [ncls][Z][Y][X]; gauss: fp32 [P0][P1][P2] or NULL.
+ * norm_scale_shift (device fp32 [nmirrors][cfeat][2], or NULL): when given, `feat` holds the RAW output of the last conv
+ * block and the head applies its deferred norm + LeakyReLU(norm_slope) on the fly (generic_UNet.py:72 of that block),
+ * saving the block's separate bsg_norm_apply_lrelu pass. */
 int bsg_head_tta_accumulate(const void* feat16, int feat_f16, int cfeat, int ctot, int P0, int P1, int P2,
                             const int* mirror_codes_host, int nmirrors, float mirror_weight,
                             const float* head_w_host, const float* head_b_host, int ncls, int nonlin,
                             const float* gauss, float* acc, int Z, int Y, int X, int z0, int y0, int x0,
-                            void* stream);
+                            const float* norm_scale_shift, float norm_slope, void* stream);
 
 /* class_probabilities = aggregated_results / aggregated_nb_of_predictions; mean over K accumulators (np.mean over
  * folds, run_brats2021_inference_singlethread.py:128); decision: mode 0 argmax(0) (main_files/run_inference.py:150),

@@ -92,7 +92,7 @@ def main():
     hw = (C.c_float * 96)(*np.random.default_rng(0).standard_normal(96).astype(np.float32))
     report("head_tta_accumulate (8 mirrors, 32 ch, 3 cls)",
            timed(lambda: L.check(lib.bsg_head_tta_accumulate(ptr(feat), 0, 32, 32, p, p, p, codes, 8, 0.125, hw, None, 3, 0,
-                                                             ptr(gauss), ptr(acc), Z, Y, X, 27, 56, 56, L.stream_ptr()))),
+                                                             ptr(gauss), ptr(acc), Z, Y, X, 27, 56, 56, None, 0.0, L.stream_ptr()))),
            8 * pv * 64 + pv * (24 + 4))
     wsum = torch.rand(Z, Y, X, device=dev) + 0.5
     seg = torch.empty(Z, Y, X, dtype=torch.uint8, device=dev)

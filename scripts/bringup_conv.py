@@ -158,6 +158,7 @@ CASES = [
     ("perfh_64_32_128_f16_stats", dict(kind=0, N=2, D=128, H=128, W=128, cin=64, cout=32, time_it=True, stats=True, f16=True)),
     ("perfh_256_256_32_f16", dict(kind=0, N=8, D=32, H=32, W=32, cin=256, cout=256, act=1, time_it=True, f16=True)),
     ("perfh_256_256_32_bf16", dict(kind=0, N=8, D=32, H=32, W=32, cin=256, cout=256, act=1, time_it=True)),
+    ("perfd_128_64_128_b8_f16_stats", dict(kind=0, N=8, D=128, H=128, W=128, cin=128, cout=64, time_it=True, stats=True, f16=True)),
     ("perft_32_32_128", dict(kind=0, N=2, D=128, H=128, W=128, cin=32, cout=32, act=1, time_it=True, algo=0)),
     ("perft_64_64_128", dict(kind=0, N=2, D=128, H=128, W=128, cin=64, cout=64, act=1, time_it=True, algo=0)),
     ("perft_128_64_128", dict(kind=0, N=1, D=128, H=128, W=128, cin=128, cout=64, act=1, time_it=True, algo=0)),
