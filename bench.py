@@ -371,16 +371,19 @@ def run_ours(args):
         fwd_per_case = N_TILES * N_MIRRORS
         conv_alone_s = sum(ms / 1e3 / conv_runs / e.batch for ms, e in zip(conv_ms, (eng1, eng2))) * fwd_per_case
         achieved = dom_info["flops"] / (dom_ms / 1e3) / 1e12
-        traffic = None
+        traffic, traffic_note = None, None
         tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
         if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from one ncu --set full capture
             with open(tpath) as f:
-                traffic = json.load(f)
+                t = json.load(f)
+            traffic = t["bytes_per_launch"]
+            traffic_note = f"{t['source']}; algorithmic bytes {t['algorithmic_bytes']}"
         roofline = {"bound": "tensor",
                     "kernel": f"conv_brick_kernel (tcgen05 implicit-GEMM conv3d): {dom_info['name']}, "
                               f"{dom_eng.batch} tile-mirrors per launch ({dom_info['plan']})",
                     "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                    "frac": achieved / peaks["tflops"], "traffic": traffic, "peak_source": peaks["source"],
+                    "frac": achieved / peaks["tflops"], "traffic": traffic, "traffic_source": traffic_note,
+                    "peak_source": peaks["source"],
                     "flops_per_launch": dom_info["flops"], "avg_launch_ms": dom_ms, "launches_timed": dom_reps,
                     "share_of_forward": dom_ms / (conv_ms[1 if dom_eng is eng2 else 0] / conv_runs),
                     "timed": "dedicated single-stream pass after the timed steps (the steps overlap two stream lanes), "
