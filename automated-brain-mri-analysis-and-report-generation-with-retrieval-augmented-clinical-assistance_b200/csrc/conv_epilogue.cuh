@@ -113,13 +113,19 @@ __device__ __forceinline__ void epilogue_32cols(const uint32_t (&v)[32], const E
     }
     if (!valid) return;
     if (co + 32 <= e.cout) {
+        // one uniform branch around the whole block: a per-element `out_f16 ? half : bf16` is if-converted into BOTH
+        // F2FP conversions plus a select, and the conversion pipe is what bounds the store-heavy epilogues (ncu on the
+        // transposed conv: 82 % busy)
         uint32_t pk[16];
+        if (e.out_f16) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            if (e.out_f16) {
+            for (int i = 0; i < 16; ++i) {
                 __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
                 pk[i] = *reinterpret_cast<uint32_t*>(&h);
-            } else {
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
                 __nv_bfloat162 b = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
                 pk[i] = *reinterpret_cast<uint32_t*>(&b);
             }

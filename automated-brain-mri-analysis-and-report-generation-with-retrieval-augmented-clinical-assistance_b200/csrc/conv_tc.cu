@@ -249,6 +249,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + acc * static_cast<uint32_t>(a.ntile) + (static_cast<uint32_t>(q * 32) << 16);
+            int par = 0, cpar = 0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int cb = j * 32;
@@ -259,9 +260,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 int co = q0 + cb;
                 if (a.out_mul == 2) {
                     // transposed conv: GEMM columns enumerate (parity (pd, ph, pw), channel); an N tile may span
-                    // several parities, so the output voxel is re-derived per 32-column chunk
-                    const int par = co / a.cout_pad;
-                    co -= par * a.cout_pad;
+                    // several parities, so the output voxel is re-derived per 32-column chunk (no division: the
+                    // parity / channel pair of the tile's first column is advanced chunk by chunk)
+                    if (j == 0) {
+                        par = q0 / a.cout_pad;
+                        cpar = q0 - par * a.cout_pad;
+                    } else if ((cpar += 32) >= a.cout_pad) {
+                        cpar = 0;
+                        ++par;
+                    }
+                    co = cpar;
                     orow = obase + static_cast<long long>(2 * d + ((par >> 2) & 1)) * a.os_d +
                            static_cast<long long>(2 * h + ((par >> 1) & 1)) * a.os_h +
                            static_cast<long long>(2 * w + (par & 1)) * a.os_w;

@@ -159,6 +159,9 @@ CASES = [
     ("perfh_256_256_32_f16", dict(kind=0, N=8, D=32, H=32, W=32, cin=256, cout=256, act=1, time_it=True, f16=True)),
     ("perfh_256_256_32_bf16", dict(kind=0, N=8, D=32, H=32, W=32, cin=256, cout=256, act=1, time_it=True)),
     ("perfd_128_64_128_b8_f16_stats", dict(kind=0, N=8, D=128, H=128, W=128, cin=128, cout=64, time_it=True, stats=True, f16=True)),
+    ("perfT_64_64_64_b8", dict(kind=1, N=8, D=64, H=64, W=64, cin=64, cout=64, out_extra=64, time_it=True, f16=True)),
+    ("perfT_64_32_64_b8", dict(kind=1, N=8, D=64, H=64, W=64, cin=64, cout=32, out_extra=32, time_it=True)),
+    ("perfs2_32_64_128_b8", dict(kind=0, N=8, D=128, H=128, W=128, cin=32, cout=64, stride=2, act=1, time_it=True)),
     ("perft_32_32_128", dict(kind=0, N=2, D=128, H=128, W=128, cin=32, cout=32, act=1, time_it=True, algo=0)),
     ("perft_64_64_128", dict(kind=0, N=2, D=128, H=128, W=128, cin=64, cout=64, act=1, time_it=True, algo=0)),
     ("perft_128_64_128", dict(kind=0, N=1, D=128, H=128, W=128, cin=128, cout=64, act=1, time_it=True, algo=0)),
