@@ -2,7 +2,9 @@
 // (reference: model_architecture/generic_UNet.py:56,69 Conv3d k3; :285-288 stride-2 conv pooling; :363-364
 // ConvTranspose3d k2 s2).  Persistent, warp-specialised:
 //   warps 0..3  epilogue       (tcgen05.ld -> bias / LeakyReLU / norm statistics -> 16-bit channels-last stores;
-//                               TMEM lane quadrant = warp id)
+//   warps 6..9                  TMEM lane quadrant = warp id % 4; the two warps of a quadrant take alternate 32-column
+//                               chunks of the N tile — the wide-N, short-K launches (transposed convs, the <= 8^3 levels)
+//                               are bound by the epilogue's convert + store rate, not by the MMAs)
 //   warp 4      TMA producer   (activation halo boxes + weight slabs -> swizzled smem ring)
 //   warp 5      MMA issuer     (one elected lane, tcgen05.mma kind::f16, fp32 accumulators in TMEM, 2 buffers); the
 //                               highest warp id of its scheduler partition, which the warp arbiter favours over the
@@ -16,7 +18,7 @@ namespace bsg {
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;  // warps 0-3 + 6-9 epilogue, 4 producer, 5 MMA issuer
 constexpr int kMaxStages = 12;
 
 struct TileCoord {
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+            mbar_init(&tempty_bar[i], 8);  // one arrive per epilogue warp
         }
         fence_barrier_init();
     }
@@ -201,6 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     } else {
         // =========================================================== epilogue (4 warps, one TMEM lane quadrant each)
         const int q = warp & 3;
+        const int half = warp >= 6 ? 1 : 0;  // which of the quadrant's two epilogue warps: odd / even chunks
         const int row = q * 32 + lane;
         int r = row;
         const int iw = r % a.bw;
@@ -254,6 +257,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             for (int j = 0; j < 8; ++j) {
                 const int cb = j * 32;
                 if (cb >= a.ntile) break;
+                if (a.out_mul == 2) {  // advance the (parity, channel) cursor for every chunk, also the skipped ones
+                    if (j == 0) {
+                        par = q0 / a.cout_pad;
+                        cpar = q0 - par * a.cout_pad;
+                    } else if ((cpar += 32) >= a.cout_pad) {
+                        cpar = 0;
+                        ++par;
+                    }
+                }
+                if ((j & 1) != half) continue;
                 uint32_t v[32];
                 tmem_ld_32x32(t_addr + cb, v);
                 tmem_ld_wait();
@@ -262,13 +275,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     // transposed conv: GEMM columns enumerate (parity (pd, ph, pw), channel); an N tile may span
                     // several parities, so the output voxel is re-derived per 32-column chunk (no division: the
                     // parity / channel pair of the tile's first column is advanced chunk by chunk)
-                    if (j == 0) {
-                        par = q0 / a.cout_pad;
-                        cpar = q0 - par * a.cout_pad;
-                    } else if ((cpar += 32) >= a.cout_pad) {
-                        cpar = 0;
-                        ++par;
-                    }
                     co = cpar;
                     orow = obase + static_cast<long long>(2 * d + ((par >> 2) & 1)) * a.os_d +
                            static_cast<long long>(2 * h + ((par >> 1) & 1)) * a.os_h +
