@@ -220,7 +220,11 @@ def run_reference(args):
 
 
 def workload_config(args):
-    return {"workload": "configs[1]: one synthetic BraTS case 4x155x240x240 (C,z,y,x), patch 128^3, step 0.5, "
+    sweep = ""
+    if PATCH != (128, 128, 128) or VOL_SHAPE != (4, 155, 240, 240) or args.step_size != 0.5:
+        sweep = (f"configs[4] sweep point: volume {'x'.join(map(str, VOL_SHAPE))}, patch {PATCH[0]}^3, step {args.step_size}, "
+                 f"{N_TILES} tiles; otherwise as ")
+    return {"workload": sweep + "configs[1]: one synthetic BraTS case 4x155x240x240 (C,z,y,x), patch 128^3, step 0.5, "
                         "Gaussian weighting, 8-way mirror TTA, 2-model ensemble (model 1: Generic_UNet BN 31.2 M; "
                         f"model 2: GroupNorm {'large 87.4 M (encoder_scale 2, max 512)' if args.model2 == 'large' else 'standard 31.2 M'}), "
                         "one fold per model, regions threshold, label-round ensemble, BraTS-2025 remap, Dice vs "
@@ -259,7 +263,7 @@ def run_ours(args):
         def reduce_fn(acc):
             dist.all_reduce(acc)
             return acc
-    pipe = PL.BratsCasePipeline([m1, m2], PATCH, 0.5, (0, 1, 2), True, True, (1, 2, 3), "brats2025", batch=args.batch,
+    pipe = PL.BratsCasePipeline([m1, m2], PATCH, args.step_size, (0, 1, 2), True, True, (1, 2, 3), "brats2025", batch=args.batch,
                                 rank=rank if args.mode == "latency" else 0,
                                 world_size=world if args.mode == "latency" else 1, reduce_fn=reduce_fn)
     eng1, eng2 = pipe.predictors[0].engine, pipe.predictors[1].engine
@@ -270,7 +274,7 @@ def run_ours(args):
     # synthetic inputs: pinned host volume (seeded per rank) + synthetic ground truth labels
     seed = 0 if args.mode == "latency" else rank
     host_vol = torch.from_numpy(SY.case_volume(seed, VOL_SHAPE)).pin_memory()
-    gt_host = torch.from_numpy(np.ascontiguousarray(SY.label_volume(seed, (155, 240, 240)))).pin_memory()
+    gt_host = torch.from_numpy(np.ascontiguousarray(SY.label_volume(seed, VOL_SHAPE[1:]))).pin_memory()
     dev_vol = host_vol.to(dev)
     dev_gt = gt_host.to(dev)
 
@@ -425,7 +429,20 @@ def main():
     ap.add_argument("--model2", default="large", choices=["large", "standard"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=16, help="(tile, mirror) forwards in flight per model (2 stream lanes)")
+    ap.add_argument("--patch", type=int, default=128, help="cubic patch size (configs[4] sweep: 128 / 160)")
+    ap.add_argument("--step-size", type=float, default=0.5, help="sliding-window step (configs[4] sweep: 0.5 / 0.25)")
+    ap.add_argument("--volume", type=int, nargs=3, default=None, metavar=("Z", "Y", "X"),
+                    help="volume extents (default 155 240 240; configs[4]: 256 256 256)")
     args = ap.parse_args()
+    global PATCH, VOL_SHAPE, N_TILES
+    if args.patch != 128 or args.volume is not None or args.step_size != 0.5:  # configs[4]: patch / overlap sweep
+        from brainseg_b200 import sliding
+        PATCH = (args.patch,) * 3
+        if args.volume is not None:
+            VOL_SHAPE = (4,) + tuple(args.volume)
+        padded = [max(v, p) for v, p in zip(VOL_SHAPE[1:], PATCH)]
+        steps = sliding.compute_steps_for_sliding_window(PATCH, padded, args.step_size)
+        N_TILES = len(steps[0]) * len(steps[1]) * len(steps[2])
     if args.impl == "reference":
         run_reference(args)
     else:

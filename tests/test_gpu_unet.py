@@ -156,3 +156,12 @@ def test_case_pipeline_folds_and_two_model_ensemble():
     final_ref = OP.convert_labels_to_brats2025(OP.ensemble_labels_round(segs_ref[0], segs_ref[1]).astype(np.float64))
     assert np.array_equal(out["segmentation"].cpu().numpy()[decisive], final_ref[decisive])
     print(f"decisive voxels {decisive.mean() * 100:.1f}%")
+
+
+@pytest.mark.parametrize("patch,step,shape", [((160, 160, 160), 0.5, (4, 168, 176, 160)), ((128, 128, 128), 0.25, (4, 130, 140, 128))])
+def test_predict_3d_sweep_geometries(patch, step, shape):
+    """BASELINE configs[4]: the patch-size / overlap sweep geometries (160^3 patches: odd 5^3 bottleneck level, levels
+    that are not multiples of the tile boxes; step 0.25: denser tile grid) on a small net against the oracle."""
+    net = build_dropin_unet("in", base=16, num_pool=5, seed=17)
+    vol = torch.randn(*shape, generator=torch.Generator().manual_seed(6)).numpy()
+    _check_predict(net, vol, patch, (0, 1, 2), False, step, (1, 2, 3), torch.sigmoid)
