@@ -37,38 +37,38 @@ def convert_labels_to_brats2021(seg):
 
 
 # ---------------------------------------------------------------------------------------------- file-level CLI
+# per output format: (converter, labels expected in the output, value the enhancing tumour maps to)
+_FORMATS = {"brats2025": (convert_labels_to_brats2025, (0, 1, 2, 3), 3),
+            "brats2021": (convert_labels_to_brats2021, (0, 1, 2, 4), 4)}
+
+
 def convert_file(input_path, output_path, format="brats2025"):
-    """Convert a single NIfTI file (reference convert_labels_to_brats.py:58-108, same console wording)."""
+    """Remap one NIfTI label file (reference convert_labels_to_brats.py:58-108).  The console text is the reference's,
+    line for line (tests/golden/cli_convert_*.txt)."""
     from . import nifti_io
 
-    print(f"\n{'=' * 70}")
-    print(f"Converting: {input_path}")
-    print(f"Format: {format.upper()}")
-    print(f"{'=' * 70}")
-    img = nifti_io.load(str(input_path))
-    data = img.get_fdata()
-    unique_before = np.unique(data)
-    print(f"\nLabels before conversion: {unique_before}")
-    if format == "brats2025":
-        data_converted, expected_labels, et_label = convert_labels_to_brats2025(data), {0, 1, 2, 3}, 3
-    else:
-        data_converted, expected_labels, et_label = convert_labels_to_brats2021(data), {0, 1, 2, 4}, 4
-    unique_after = np.unique(data_converted)
-    print(f"Labels after conversion:  {unique_after}")
-    print(f"\nLabel mapping applied ({format.upper()}):")
-    if 1 in unique_before:
-        print("  1 (ED) -> 2 (ED)")
-    if 2 in unique_before:
-        print("  2 (NCR) -> 1 (NCR)")
-    if 3 in unique_before:
-        print(f"  3 (ET) -> {et_label} (ET)  [CRITICAL CONVERSION]")
-    nifti_io.save(str(output_path), data_converted, img)
+    convert, expected, et_label = _FORMATS[format if format in _FORMATS else "brats2021"]
+    tag, rule = format.upper(), "=" * 70
+    print(f"\n{rule}\nConverting: {input_path}\nFormat: {tag}\n{rule}")
+    source = nifti_io.load(str(input_path))
+    before = source.get_fdata()
+    seen = np.unique(before)
+    print(f"\nLabels before conversion: {seen}")
+    after = convert(before)
+    produced = np.unique(after)
+    print(f"Labels after conversion:  {produced}")
+    print(f"\nLabel mapping applied ({tag}):")
+    for old, text in ((1, "  1 (ED) -> 2 (ED)"), (2, "  2 (NCR) -> 1 (NCR)"),
+                      (3, f"  3 (ET) -> {et_label} (ET)  [CRITICAL CONVERSION]")):
+        if old in seen:
+            print(text)
+    nifti_io.save(str(output_path), after, source)
     print(f"\n[OK] Saved converted segmentation to: {output_path}")
-    print(f"\nExpected {format.upper()} labels: {sorted(expected_labels)}")
-    print(f"Actual labels in output: {unique_after}")
-    if set(unique_after) == expected_labels:
-        print(f"[OK] SUCCESS: All {format.upper()} labels present!")
-    elif et_label not in unique_after:
+    print(f"\nExpected {tag} labels: {sorted(expected)}")
+    print(f"Actual labels in output: {produced}")
+    if set(produced) == set(expected):
+        print(f"[OK] SUCCESS: All {tag} labels present!")
+    elif et_label not in produced:
         print(f"[WARNING] Label {et_label} missing - check if input had label 3")
 
 
@@ -77,19 +77,18 @@ def main(argv=None):
     import sys
     from pathlib import Path
 
-    parser = argparse.ArgumentParser(description="Convert nnU-Net labels to BraTS format")
-    parser.add_argument("input", help="Input NIfTI file with nnU-Net labels [0,1,2,3]")
-    parser.add_argument("output", nargs="?", help="Output NIfTI file (optional, defaults to input_brats.nii.gz)")
-    parser.add_argument("--format", choices=["brats2025", "brats2021"], default="brats2025",
-                        help="Output format: brats2025 (default, ET=3) or brats2021 (legacy, ET=4)")
-    args = parser.parse_args(argv)
-    input_file = Path(args.input)
-    output_file = Path(args.output) if args.output else input_file.parent / (
-        input_file.stem.replace(".nii", "_brats.nii") + ".gz")
-    if not input_file.exists():
-        print(f"[ERROR] Input file not found: {input_file}")
+    cli = argparse.ArgumentParser(description="Convert nnU-Net labels to BraTS format")
+    cli.add_argument("input", help="Input NIfTI file with nnU-Net labels [0,1,2,3]")
+    cli.add_argument("output", nargs="?", help="Output NIfTI file (optional, defaults to input_brats.nii.gz)")
+    cli.add_argument("--format", choices=sorted(_FORMATS, reverse=True), default="brats2025",
+                     help="Output format: brats2025 (default, ET=3) or brats2021 (legacy, ET=4)")
+    args = cli.parse_args(argv)
+    src = Path(args.input)
+    if not src.exists():
+        print(f"[ERROR] Input file not found: {src}")
         sys.exit(1)
-    convert_file(input_file, output_file, args.format)
+    dst = Path(args.output) if args.output else src.with_name(src.name.replace(".nii", "_brats.nii", 1))
+    convert_file(src, dst, args.format)
 
 
 if __name__ == "__main__":
