@@ -24,7 +24,7 @@ class ConvDesc(C.Structure):
         ("cout", C.c_int), ("out_ptr", C.c_void_p), ("out_ctot", C.c_int), ("out_coff", C.c_int),
         ("weights", C.c_void_p), ("bias", C.c_void_p),
         ("act", C.c_int), ("slope", C.c_float), ("stats", C.c_void_p), ("out_f16", C.c_int),
-        ("use_khshift", C.c_int), ("max_ctas", C.c_int), ("in_f16", C.c_int), ("algo", C.c_int),
+        ("use_khshift", C.c_int), ("max_ctas", C.c_int), ("in_f16", C.c_int), ("algo", C.c_int), ("pair", C.c_int),
     ]
 
 
@@ -123,6 +123,7 @@ class ConvPlan:
         d = ConvDesc()
         d.use_khshift = -1
         d.algo = -1
+        d.pair = -1
         for k, v in kw.items():
             setattr(d, k, v)
         self._h = C.c_void_p()

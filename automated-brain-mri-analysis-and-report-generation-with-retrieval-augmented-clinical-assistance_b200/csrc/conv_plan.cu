@@ -342,6 +342,25 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
         uint32_t box[3] = {static_cast<uint32_t>(a.cc), static_cast<uint32_t>(a.ntile), khs ? 3u : 1u};
         rc = encode_map(&a.mapW, d->weights, 3, dims, str, box, a.cc);
     }
+    // pair mode: 2-CTA clusters share every weight stage (each CTA fetches half of the N rows and multicasts them), which
+    // halves the L2 -> SM weight traffic of the layers that re-read their weights once per 128-voxel tile
+    a.pair = 0;
+    {
+        const long long mtiles = static_cast<long long>(a.tw) * a.th * a.td * a.tn;
+        // measured (gpurun_out/bringup16.log): +3 % on the stride-1 layers with N >= 128, nothing on the stride-2 layers
+        // (they are bound by the per-stage issue overhead of their 1-tap stages, not by weight traffic)
+        const bool wanted = d->pair == 1 || (d->pair != 0 && a.ntile >= 128 && stride == 1);
+        if (wanted && d->kind != BSG_CONVT_K2S2 && a.ntile % 16 == 0 && mtiles % 2 == 0 &&
+            (d->pair == 1 || mtiles * a.n_ntiles >= 2ll * sm_count_cached()))
+            a.pair = 1;
+    }
+    if (rc == BSG_OK && a.pair) {
+        const uint64_t rows = static_cast<uint64_t>(a.cout_pad);
+        uint64_t dims[3] = {static_cast<uint64_t>(d->cin), rows, static_cast<uint64_t>(a.ntaps)};
+        uint64_t str[2] = {static_cast<uint64_t>(d->cin) * 2, static_cast<uint64_t>(d->cin) * 2 * rows};
+        uint32_t box[3] = {static_cast<uint32_t>(a.cc), static_cast<uint32_t>(a.ntile / 2), 1u};
+        rc = encode_map(&a.mapWh, d->weights, 3, dims, str, box, a.cc);
+    }
     if (rc != BSG_OK) {
         delete p;
         return rc;
@@ -365,6 +384,10 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
     const int total_tiles = a.tn * a.td * a.th * a.tw * a.n_ntiles;
     int max_ctas = d->max_ctas > 0 ? d->max_ctas : sm_count_cached();
     p->grid = total_tiles < max_ctas ? total_tiles : max_ctas;
+    if (a.pair) {
+        const int clusters = (total_tiles / 2) < (max_ctas / 2) ? (total_tiles / 2) : (max_ctas / 2);
+        p->grid = 2 * (clusters > 0 ? clusters : 1);
+    }
     p->smem_bytes = conv_tc_smem_bytes(a);
     p->flops = 2.0 * a.ntaps * (a.out_mul == 2 ? 8 : 1) * static_cast<double>(d->cin) * d->cout *
                (static_cast<double>(a.Wo) * a.Ho * a.Do * a.No);
@@ -411,7 +434,7 @@ int bsg_conv_plan_info(const bsg_conv_plan* plan, bsg_conv_info* info) {
     info->n_ntiles = a.n_ntiles;
     info->cc = a.cc;
     info->nstages = a.nstages;
-    info->khshift = a.khshift;
+    info->khshift = a.khshift + (a.pair ? 100 : 0);  /* +100: 2-CTA pair mode (multicast weight stages) */
     info->grid = plan->grid;
     info->smem_bytes = plan->smem_bytes;
     info->flops = plan->flops;

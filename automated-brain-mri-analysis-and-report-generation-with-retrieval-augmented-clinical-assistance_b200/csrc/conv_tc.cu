@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         tma_prefetch_desc(&a.mapA[0]);
         for (int s = 0; s < a.nstages; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], a.pair ? 2 : 1);  // pair mode: both CTAs' MMAs must have drained the stage
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
@@ -85,8 +85,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t crank = a.pair ? cluster_ctarank() : 0u;
+    if (a.pair) cluster_sync_all();  // the peer's barriers are initialised before any multicast / remote arrive
 
     const int total_tiles = a.tn * a.td * a.th * a.tw * a.n_ntiles;
+    // work items: plain mode = tiles, dealt round-robin to the CTAs; pair mode = (pair of neighbouring M tiles, N tile),
+    // dealt to the clusters — both CTAs of a cluster walk the same item sequence, hence the same K-step sequence
+    const int item0 = a.pair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int item_step = a.pair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    const int nitems = a.pair ? total_tiles / 2 : total_tiles;
+    auto tile_of = [&](int item) {
+        return a.pair ? (2 * (item / a.n_ntiles) + static_cast<int>(crank)) * a.n_ntiles + item % a.n_ntiles : item;
+    };
     const int ntg = KHS ? 9 : a.ntaps;  // pipeline steps per chunk: (kd,kw) pairs or single taps
     const int ksteps = ntg * a.nchunks;
     constexpr int NKH = KHS ? 3 : 1;
@@ -99,8 +109,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const TileCoord t = decode_tile(a, tile);
+            for (int item = item0; item < nitems; item += item_step) {
+                const TileCoord t = decode_tile(a, tile_of(item));
                 const int nrow0 = t.nt * a.ntile;
                 int kd = 0, kw = 0, kh = 0;  // tap order (kd, kw, kh): kh fastest, absent when KHS
                 for (int tg = 0; tg < ntg; ++tg) {
@@ -131,7 +141,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                         uint8_t* sb = sa + a.a_stage_bytes;
                         mbar_expect_tx(&full_bar[stage], a.stage_tx_bytes);
                         tma_load_5d(sa, mapA, &full_bar[stage], c * CC, cw, ch, cd, t.n0);
-                        tma_load_3d(sb, &a.mapW, &full_bar[stage], c * CC, nrow0, tap);
+                        if (a.pair) {
+                            // my half of the N rows of every tap of the stage, to both CTAs (same smem offset)
+                            const int half = a.ntile >> 1;
+                            for (int j = 0; j < NKH; ++j)
+                                tma_load_3d_mc(sb + (j * a.ntile + static_cast<int>(crank) * half) * kRowBytes, &a.mapWh,
+                                               &full_bar[stage], c * CC, nrow0 + static_cast<int>(crank) * half, tap + j,
+                                               static_cast<uint16_t>(3));
+                        } else {
+                            tma_load_3d(sb, &a.mapW, &full_bar[stage], c * CC, nrow0, tap);
+                        }
                         if (++stage == nstages) {
                             stage = 0;
                             phase ^= 1u;
@@ -168,7 +187,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             uint32_t phase = 0;
             uint32_t tcount = 0;
             bool ready = false;  // next stage's full barrier already seen complete (probed early, see below)
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+            for (int item = item0; item < nitems; item += item_step, ++tcount) {
                 const uint32_t acc = tcount & 1u;
                 const uint32_t acc_phase = (tcount >> 1) & 1u;
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
@@ -192,7 +211,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                             if (kh == 0 && k == 0) ready = mbar_try_wait(&full_bar[nstage], nphase);
                         }
                     }
-                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+                    // frees the smem slot once these MMAs have read it (pair mode: in both CTAs — either producer
+                    // writes weight rows into both)
+                    if (a.pair)
+                        umma_commit_mc(&empty_bar[stage], static_cast<uint16_t>(3));
+                    else
+                        umma_commit(&empty_bar[stage]);
                     if (ks == ksteps - 1) umma_commit(&tfull_bar[acc]);
                     stage = nstage;
                     phase = nphase;
@@ -229,8 +253,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         int stat_n = -1, stat_nt = 0;
         float unused1[32], unused2[32];  // per-thread statistic sums: brick kernel only
         uint32_t tcount = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-            const TileCoord t = decode_tile(a, tile);
+        for (int item = item0; item < nitems; item += item_step, ++tcount) {
+            const TileCoord t = decode_tile(a, tile_of(item));
             const uint32_t acc = tcount & 1u;
             const uint32_t acc_phase = (tcount >> 1) & 1u;
             const int w = t.w0 + iw, h = t.h0 + ih, d = t.d0 + id, n = t.n0 + in;
@@ -294,6 +318,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
     tc_fence_before();
     __syncthreads();
+    if (a.pair) cluster_sync_all();  // no CTA leaves while its peer can still multicast into it / arrive on its barriers
     if (warp == 5) {
         tc_fence_after();
         tmem_dealloc(tmem_base, a.tmem_cols);
@@ -315,6 +340,21 @@ static cudaError_t launch_variant(const ConvArgs& a, int grid, size_t smem_bytes
                                              232448);
         if (e != cudaSuccess) return e;
         attr_set = true;
+    }
+    if (a.pair) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(static_cast<unsigned>(grid));
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = smem_bytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, conv_tc_kernel<CC, KHS>, a);
     }
     conv_tc_kernel<CC, KHS><<<grid, kThreads, smem_bytes, stream>>>(a);
     return cudaGetLastError();

@@ -12,6 +12,9 @@ namespace bsg {
 struct ConvArgs {
     CUtensorMap mapA[8];  // stride 1: [0] only.  stride 2: one half-resolution view per input parity (pd,ph,pw).
     CUtensorMap mapW;     // packed weights, dims (Cin_pad, Nrows, ntaps), tap order (kd, kw, kh)
+    CUtensorMap mapWh;    // pair mode: box (cc, ntile / 2, 1) of the same tensor
+    int pair;             // 1: launched as 2-CTA clusters; the two CTAs work on neighbouring M tiles of the same N tile
+                          //    in lock-step, each fetches half of every weight stage and multicasts it to both
     int bw, bh, bd, bn;   // output tile box, bw*bh*bd*bn == 128
     int tw, th, td, tn;   // tile counts per dimension
     int n_ntiles, ntile;  // N tiling (ntile % 32 == 0, ntile <= 256)
@@ -39,7 +42,7 @@ struct ConvArgs {
     int in_f16;    // 1: activations and weights are IEEE fp16 instead of bf16
 };
 
-cudaError_t launch_conv_tc(const ConvArgs& a, int grid, size_t smem_bytes, cudaStream_t stream);
+cudaError_t launch_conv_tc(const ConvArgs& a, int grid, size_t smem_bytes, cudaStream_t stream);  // pair: grid even
 size_t conv_tc_smem_bytes(const ConvArgs& a);
 
 }  // namespace bsg

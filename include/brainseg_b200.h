@@ -75,6 +75,8 @@ typedef struct bsg_conv_desc {
                             InstanceNorm / GroupNorm stacks, whose activations are bounded by construction) */
     int algo;            /* -1 auto, 0 tile kernel (one 128-voxel tile per accumulator), 1 brick kernel when the layer
                             suits it (stride-1 k3, Cout <= 64, W % 8 == 0, H % 16 == 0, D % (256/Cout_pad) == 0) */
+    int pair;            /* tile kernel only: -1 auto, 0 off, 1 on when possible — launch as 2-CTA clusters whose CTAs work
+                            on neighbouring tiles in lock-step and share every weight stage through TMA multicast */
 } bsg_conv_desc;
 
 typedef struct bsg_conv_plan bsg_conv_plan;

@@ -19,7 +19,7 @@ dev = torch.device("cuda:0")
 
 
 def run_case(name, kind, N, D, H, W, cin, cout, stride=1, khshift=-1, act=0, stats=False, in_extra=0, out_extra=0,
-             out_coff=0, seed=0, bias=True, time_it=False, algo=-1, f16=False):
+             out_coff=0, seed=0, bias=True, time_it=False, algo=-1, f16=False, pair=-1):
     g = torch.Generator(device="cpu").manual_seed(seed)
     dt = torch.float16 if f16 else torch.bfloat16
     cin_pad = P.round_up(cin, 16)
@@ -54,7 +54,7 @@ def run_case(name, kind, N, D, H, W, cin, cout, stride=1, khshift=-1, act=0, sta
     plan = L.ConvPlan(kind=kind, stride=stride, N=N, D=D, H=H, W=W, cin=cin_pad, in_ptr=xb.data_ptr(),
                       in_ctot=in_ctot, cout=cout, out_ptr=out.data_ptr(), out_ctot=out_ctot, out_coff=out_coff,
                       weights=wp.data_ptr(), bias=bp.data_ptr() if bp is not None else None, act=act, slope=0.01,
-                      stats=st.data_ptr() if st is not None else None, use_khshift=khshift, max_ctas=0, algo=algo,
+                      stats=st.data_ptr() if st is not None else None, use_khshift=khshift, max_ctas=0, algo=algo, pair=pair,
                       in_f16=1 if f16 else 0, out_f16=1 if f16 else 0)
     inf = plan.info()
     plan.run()
@@ -162,6 +162,20 @@ CASES = [
     ("perfT_64_64_64_b8", dict(kind=1, N=8, D=64, H=64, W=64, cin=64, cout=64, out_extra=64, time_it=True, f16=True)),
     ("perfT_64_32_64_b8", dict(kind=1, N=8, D=64, H=64, W=64, cin=64, cout=32, out_extra=32, time_it=True)),
     ("perfs2_32_64_128_b8", dict(kind=0, N=8, D=128, H=128, W=128, cin=32, cout=64, stride=2, act=1, time_it=True)),
+    ("pair_c128_128", dict(kind=0, N=2, D=8, H=32, W=16, cin=128, cout=128, act=1, pair=1)),
+    ("pair_c64_256_stats", dict(kind=0, N=2, D=8, H=16, W=16, cin=64, cout=256, stats=True, pair=1, f16=True)),
+    ("pair_s2", dict(kind=0, N=2, D=16, H=32, W=16, cin=32, cout=64, stride=2, pair=1)),
+    ("pair_c320", dict(kind=0, N=4, D=8, H=8, W=8, cin=64, cout=320, act=1, pair=1)),
+    ("pair_many", dict(kind=0, N=6, D=16, H=32, W=24, cin=128, cout=128, act=1, pair=1)),
+    ("perfp_128_128_64_pair", dict(kind=0, N=8, D=64, H=64, W=64, cin=128, cout=128, act=1, time_it=True, pair=1)),
+    ("perfp_128_128_64_solo", dict(kind=0, N=8, D=64, H=64, W=64, cin=128, cout=128, act=1, time_it=True, pair=0)),
+    ("perfp_256_128_64_pair", dict(kind=0, N=8, D=64, H=64, W=64, cin=256, cout=128, act=1, time_it=True, pair=1)),
+    ("perfp_256_128_64_solo", dict(kind=0, N=8, D=64, H=64, W=64, cin=256, cout=128, act=1, time_it=True, pair=0)),
+    ("perfp_s2_64_128_128_pair", dict(kind=0, N=8, D=128, H=128, W=128, cin=64, cout=128, stride=2, act=1, time_it=True, pair=1)),
+    ("perfp_s2_64_128_128_solo", dict(kind=0, N=8, D=128, H=128, W=128, cin=64, cout=128, stride=2, act=1, time_it=True, pair=0)),
+    ("perfp_s2_32_64_128_pair", dict(kind=0, N=8, D=128, H=128, W=128, cin=32, cout=64, stride=2, act=1, time_it=True, pair=1)),
+    ("perfp_512_256_32_pair", dict(kind=0, N=8, D=32, H=32, W=32, cin=512, cout=256, act=1, time_it=True, pair=1)),
+    ("perfp_512_256_32_solo", dict(kind=0, N=8, D=32, H=32, W=32, cin=512, cout=256, act=1, time_it=True, pair=0)),
     ("perft_32_32_128", dict(kind=0, N=2, D=128, H=128, W=128, cin=32, cout=32, act=1, time_it=True, algo=0)),
     ("perft_64_64_128", dict(kind=0, N=2, D=128, H=128, W=128, cin=64, cout=64, act=1, time_it=True, algo=0)),
     ("perft_128_64_128", dict(kind=0, N=1, D=128, H=128, W=128, cin=128, cout=64, act=1, time_it=True, algo=0)),
