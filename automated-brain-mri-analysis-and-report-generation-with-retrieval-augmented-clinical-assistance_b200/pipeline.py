@@ -23,11 +23,19 @@ from .feature_extraction import utils as FU
 class BratsCasePipeline:
     def __init__(self, models, patch_size=(128, 128, 128), step_size=0.5, mirror_axes=(0, 1, 2), do_mirroring=True,
                  use_gaussian=True, regions_class_order=(1, 2, 3), label_format="brats2025", batch=8, rank=0,
-                 world_size=1, reduce_fn=None, lanes=None):
+                 world_size=1, reduce_fn=None, lanes=None, ensemble="label_round", small_et_threshold=None,
+                 small_et_replace=2):
         """models: one entry per ensemble member — a drop-in Generic_UNet, or a list of them = the folds of that model,
         whose probabilities are averaged before the decision (np.mean over folds, reference :128);
         `reduce_fn(acc)` sums an accumulator over ranks when the (tile, mirror) work items of ONE case are sharded
         (latency mode)."""
+        if ensemble not in ("label_round", "prob_mean"):
+            raise ValueError("ensemble must be 'label_round' (run_brats2021_inference_singlethread.py:305) or 'prob_mean' "
+                             "(archived/kaist_original_inference.py:29-33)")
+        # 'prob_mean' = the original KAIST pipeline: nnUNet_ensemble (mean of the members' probabilities, then the regions
+        # decision) + apply_threshold_to_folder(..., small_et_threshold=200, small_et_replace=2): an enhancing-tumour label
+        # (3, nnU-Net convention) with fewer voxels than the threshold is relabelled
+        self.ensemble, self.small_et_threshold, self.small_et_replace = ensemble, small_et_threshold, small_et_replace
         self.models = [list(m) if isinstance(m, (list, tuple)) else [m] for m in models]
         self.patch = tuple(patch_size)
         self.regions = regions_class_order
@@ -53,6 +61,15 @@ class BratsCasePipeline:
         """vol: fp32 cuda tensor (C, Z, Y, X), extents >= patch.  Returns the per-model uint8 label volumes."""
         shape = tuple(vol.shape[1:])
         segs = []
+        if self.ensemble == "prob_mean":
+            # every member (model x fold) weighs the same, as np.mean over the folds' means does for equal fold counts
+            accs = []
+            for row in self.fold_predictors:
+                for pred in row:
+                    acc = pred.accumulate(vol)
+                    accs.append(self.reduce_fn(acc) if self.reduce_fn is not None else acc)
+            seg, _ = self.fold_predictors[0][0].finalize(accs, shape, self.regions, want_probs=False)
+            return [seg]
         for row in self.fold_predictors:
             accs = []
             for pred in row:
@@ -76,7 +93,19 @@ class BratsCasePipeline:
         vol = volume.to(self.device, torch.float32, non_blocking=True).contiguous()
         segs = self.segment(vol)
         if len(segs) == 1:
-            brats = V.label_lut(segs[0], self.lut)
+            seg = segs[0]
+            if self.small_et_threshold is not None:
+                # apply_brats_threshold: `if np.sum(seg == 3) < threshold: seg[seg == 3] = replace_with`; the count is
+                # needed on the host to pick the LUT (one 120-byte read)
+                n_et = int(V.masked_moments(seg, [V.bits_of(3)])[0]["count"])
+                if n_et < self.small_et_threshold:
+                    lut = np.array(self.lut, dtype=np.uint8).copy()
+                    lut[3] = self.lut[self.small_et_replace]
+                    brats = V.label_lut(seg, lut)
+                else:
+                    brats = V.label_lut(seg, self.lut)
+            else:
+                brats = V.label_lut(seg, self.lut)
         elif len(segs) == 2:
             brats = V.ensemble_round(segs[0], segs[1], post_lut=self.lut)  # ensemble + remap in one pass
         else:

@@ -165,3 +165,33 @@ def test_predict_3d_sweep_geometries(patch, step, shape):
     net = build_dropin_unet("in", base=16, num_pool=5, seed=17)
     vol = torch.randn(*shape, generator=torch.Generator().manual_seed(6)).numpy()
     _check_predict(net, vol, patch, (0, 1, 2), False, step, (1, 2, 3), torch.sigmoid)
+
+
+def test_case_pipeline_kaist_probability_ensemble():
+    """The original KAIST post-processing (archived/kaist_original_inference.py:29-33): mean of the two models'
+    probabilities, regions decision, enhancing-tumour suppression below 200 voxels, BraTS-2021 label convention."""
+    from brainseg_b200 import pipeline as PL
+    from oracle import postproc as OP
+
+    models = [build_dropin_unet("bn", base=16, num_pool=2, seed=41), build_dropin_unet("gn", base=16, num_pool=2, groups=4, seed=42)]
+    vol = torch.randn(4, 36, 40, 44, generator=torch.Generator().manual_seed(10)).numpy()
+    patch = (32, 32, 32)
+    probs = [SW.predict_3d_tiled(oracle_fns(n)[0], torch.sigmoid, vol, 3, patch, True, (0, 1, 2), 0.5, True, (1, 2, 3))[1]
+             for n in models]
+    mean = np.mean(probs, axis=0)
+    seg = np.zeros(mean.shape[1:], dtype=np.uint8)
+    for i, c in enumerate((1, 2, 3)):
+        seg[mean[i] > 0.5] = c
+    decisive = np.all(np.abs(mean - 0.5) > PROB_TOL, axis=0)
+    n_et = int((seg == 3).sum())
+    for thr in (n_et // 2, 4 * n_et + 200):  # below / above the measured enhancing-tumour count
+        pipe = PL.BratsCasePipeline(models, patch, 0.5, (0, 1, 2), True, True, (1, 2, 3), "brats2021", batch=8,
+                                    ensemble="prob_mean", small_et_threshold=thr, small_et_replace=2)
+        out = pipe.run_case(vol, features=False)
+        ref = seg.copy()
+        if n_et < thr:
+            ref[ref == 3] = 2
+        ref = OP.convert_labels_to_brats2021(ref.astype(np.float64))
+        got = out["segmentation"].cpu().numpy()
+        assert np.array_equal(got[decisive], ref[decisive])
+        assert (4 in np.unique(got)) == (n_et >= thr) or abs(n_et - thr) < (~decisive).sum()
