@@ -19,7 +19,8 @@
 // address bits (profiles/r01_probe_umma_shift.log).  One TMA box then feeds 27 taps instead of 9, which matters
 // because the box fill and the MMA operand reads share the same 128 B/clk shared-memory port.
 // Roles: warps 0..3 epilogue (TMEM lane quadrant = warp id), warp 4 activation TMA producer, warp 5 weight-slab TMA
-// producer, warp 6 MMA issuer (one thread).  The issuer is the highest warp id of its scheduler partition: the
+// producer, warp 6 MMA issuer (one thread); CC = 16 instantiations add a second epilogue group on warps 7..10 (the
+// groups take alternate planes).  With one group the issuer is the highest warp id of its scheduler partition: the
 // warp arbiter favours the highest id, so the latency-critical tcgen05.mma stream is never queued behind the
 // instruction-heavy epilogue warp it shares the partition with.
 #include "bsg_ptx.cuh"
@@ -54,9 +55,16 @@ __device__ __forceinline__ Unit decode_unit(const BrickArgs& a, int u, int P) {
 
 // STATS: the epilogue also accumulates the norm statistics (a.stats != null) — a separate instantiation because the
 // per-thread sums cost 2 * NT registers.
+//
+// CC == 16 (the 4-channel network input, one K chunk): a plane takes only 9 MMAs, so one epilogue warp group
+// (TMEM -> bias/stats/activation -> global) is the bottleneck; those instantiations run a second group on warps
+// 7..10 and the groups take alternate planes.  With 352 threads the per-thread register budget is 186, so the
+// NT = 64 statistics there are reduced per tile (shuffles) instead of kept as 128 per-thread sums.
 template <int CC, int NT, bool STATS, bool KWF>
-__global__ void __launch_bounds__(kBrickThreads, 1) conv_brick_kernel(const __grid_constant__ BrickArgs a) {
+__global__ void __launch_bounds__(brick_threads(CC), 1) conv_brick_kernel(const __grid_constant__ BrickArgs a) {
     constexpr int P = 256 / NT;
+    constexpr int kEpiGroups = (CC == 16) ? 2 : 1;
+    constexpr bool kThreadAcc = !(kEpiGroups == 2 && NT == 64);
     constexpr uint32_t kRowBytes = CC * 2u;
     constexpr uint32_t kAtom = 8u * kRowBytes;              // 8 rows: one swizzle atom, one h step of the 8-wide box
     constexpr uint32_t kTapBytes = NT * kRowBytes;          // one tap of a weight slab
@@ -288,8 +296,10 @@ __global__ void __launch_bounds__(kBrickThreads, 1) conv_brick_kernel(const __gr
         }
         __syncwarp();
     } else {
-        // =========================================================== epilogue (4 warps, one TMEM lane quadrant each)
+        // =========================================================== epilogue (4 warps per group, one TMEM lane
+        // quadrant each: a warp may only touch lanes 32 * (warp % 4) ..)
         const int q4 = warp & 3;
+        const int group = (warp >= 7) ? 1 : 0;
         const int row = q4 * 32 + lane;
         const int iw = row & 7, ih = row >> 3;
         EpiParams epi;
@@ -321,7 +331,7 @@ __global__ void __launch_bounds__(kBrickThreads, 1) conv_brick_kernel(const __gr
             }
             __nv_bfloat16* obase = a.out + t.n * a.os_n + static_cast<long long>(t.h0 + ih) * a.os_h +
                                    static_cast<long long>(t.w0 + iw) * a.os_w + a.out_c_off;
-            for (int q = 0; q < P; ++q) {
+            for (int q = group; q < P; q += kEpiGroups) {
                 const uint32_t slot = bb * P + static_cast<uint32_t>(q);
                 mbar_wait(&tfull_bar[slot], par);
                 tc_fence_after();
@@ -332,13 +342,13 @@ __global__ void __launch_bounds__(kBrickThreads, 1) conv_brick_kernel(const __gr
                     uint32_t v[32];
                     tmem_ld_32x32(t_addr + cb, v);
                     tmem_ld_wait();
-                    epilogue_32cols<true>(v, epi, cb, true, lane, sacc[cb / 32], orow, t1[cb / 32], t2[cb / 32]);
+                    epilogue_32cols<kThreadAcc>(v, epi, cb, true, lane, sacc[cb / 32], orow, t1[cb / 32], t2[cb / 32]);
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[slot]);
             }
-            if (STATS) {  // one warp reduction per brick instead of one per plane
+            if (STATS && kThreadAcc) {  // one warp reduction per brick instead of one per plane
 #pragma unroll
                 for (int j = 0; j < NT / 32; ++j) {
                     stats_transpose_reduce(t1[j], t2[j], lane, sacc[j]);
@@ -370,7 +380,7 @@ cudaError_t launch_variant(const BrickArgs& a, int grid, size_t smem_bytes, cuda
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    conv_brick_kernel<CC, NT, STATS, KWF><<<grid, kBrickThreads, smem_bytes, stream>>>(a);
+    conv_brick_kernel<CC, NT, STATS, KWF><<<grid, brick_threads(CC), smem_bytes, stream>>>(a);
     return cudaGetLastError();
 }
 

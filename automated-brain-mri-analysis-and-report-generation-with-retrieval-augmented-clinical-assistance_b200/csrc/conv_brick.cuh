@@ -40,7 +40,9 @@ struct BrickArgs {
     int in_f16;  // 1: activations and weights are IEEE fp16 instead of bf16
 };
 
-constexpr int kBrickThreads = 224;
+constexpr int kBrickThreads = 224;  // 4 epilogue warps + activation producer + weight producer + MMA issuer
+// CC == 16 instantiations run a second epilogue warp group (see conv_brick.cu)
+constexpr int brick_threads(int cc) { return cc == 16 ? kBrickThreads + 128 : kBrickThreads; }
 cudaError_t launch_conv_brick(const BrickArgs& a, int cc, int nt, int grid, size_t smem_bytes, cudaStream_t stream);
 size_t conv_brick_smem_bytes(const BrickArgs& a);
 

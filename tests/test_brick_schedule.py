@@ -25,7 +25,7 @@ class Bar:
         return self.phase != parity
 
 
-def simulate(P, D, nchunks, nslabbuf, nstages, units_of_cta, seed, async_commit=True, kwf=False):
+def simulate(P, D, nchunks, nslabbuf, nstages, units_of_cta, seed, async_commit=True, kwf=False, epi_groups=1):
     rng = random.Random(seed)
     nphases = 3 * nchunks
     resident = nslabbuf >= nphases
@@ -140,11 +140,11 @@ def simulate(P, D, nchunks, nslabbuf, nstages, units_of_cta, seed, async_commit=
                 su += 1
             tcount += 1
 
-    def epilogue(widx):
+    def epilogue(widx, group):
         tcount = 0
         for (ui, d0) in units_of_cta:
             bb, par = tcount & 1, (tcount >> 1) & 1
-            for q in range(P):
+            for q in range(group, P, epi_groups):  # CC = 16 kernels: two warp groups take alternate planes
                 slot = bb * P + q
                 yield from wait(tfull[slot], par)
                 want = {(ph, kd, kh) for ph in range(nphases) for kd in range(3) for kh in range(3)}
@@ -157,7 +157,7 @@ def simulate(P, D, nchunks, nslabbuf, nstages, units_of_cta, seed, async_commit=
                     acc[slot] = None
             tcount += 1
 
-    roles = [a_producer(), w_producer(), mma()] + [epilogue(i) for i in range(4)]
+    roles = [a_producer(), w_producer(), mma()] + [epilogue(i, g) for g in range(epi_groups) for i in range(4)]
     alive = list(range(len(roles)))
     idle_rounds = 0
     while alive:
@@ -199,3 +199,5 @@ def test_brick_protocol(P, nchunks, nslabbuf, nstages):
     if nslabbuf >= 3 * nchunks:  # resident slabs: the kernel runs the kw-fused variant
         for seed in range(4):
             simulate(P, D, nchunks, nslabbuf, nstages, [(i, (i % 4) * P) for i in range(5)], seed, kwf=True)
+            simulate(P, D, nchunks, nslabbuf, nstages, [(i, (i % 4) * P) for i in range(5)], seed, kwf=True,
+                     epi_groups=2)
