@@ -43,9 +43,16 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvArgs& a, int tile) {
     return t;
 }
 
-// CC: channels per K chunk (16/32/64 <-> swizzle 32/64/128 B); KHS: kh halo reuse (3 kh taps per stage).
-template <int CC, bool KHS>
+// CC: channels per K chunk (16/32/64 <-> swizzle 32/64/128 B).
+// MODE: kModeGeneric (one tap per stage, everything decided at run time), kModeKhs (kh halo reuse: 3 kh taps per
+// stage), kModeS1 / kModeS2 (27 taps at stride 1 / 2, one tap per stage, no pair mode: the producer's tap loop is
+// unrolled so that the parity view and the coordinate offsets of every tap are compile-time constants — ncu showed the
+// generic producer thread spending ~105 dependent instructions = ~470 cycles per one-tap stage, 2..4x the stage's
+// MMA time).
+constexpr int kModeGeneric = 0, kModeKhs = 1, kModeS2 = 2, kModeS1 = 3;
+template <int CC, int MODE>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvArgs a) {
+    constexpr bool KHS = MODE == kModeKhs;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-B aligned carve-up (swizzle-128B atoms need it)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -109,6 +116,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
+            if constexpr (MODE == kModeS2 || MODE == kModeS1) {
+                const uint32_t a_bytes = a.a_stage_bytes, tx_bytes = a.stage_tx_bytes;
+                const int nchunks = a.nchunks;
+                for (int item = item0; item < nitems; item += item_step) {
+                    const TileCoord t = decode_tile(a, tile_of(item));
+                    const int nrow0 = t.nt * a.ntile;
+#pragma unroll
+                    for (int tap = 0; tap < 27; ++tap) {  // tap order (kd, kw, kh), kh fastest
+                        const int kd = tap / 9, kw = (tap / 3) % 3, kh = tap % 3;
+                        // stride 2: input index 2*o + k - 1: k=0 -> odd parity view, o-1; k=1 -> even, o; k=2 -> odd, o
+                        constexpr bool S2 = MODE == kModeS2;
+                        const int mi = S2 ? ((kw + 1) & 1) | (((kh + 1) & 1) << 1) | (((kd + 1) & 1) << 2) : 0;
+                        const int cw = S2 ? t.w0 - (kw == 0) : t.w0 + kw - 1;
+                        const int ch = S2 ? t.h0 - (kh == 0) : t.h0 + kh - 1;
+                        const int cd = S2 ? t.d0 - (kd == 0) : t.d0 + kd - 1;
+                        for (int c = 0; c < nchunks; ++c) {
+                            mbar_wait(&empty_bar[stage], phase ^ 1u);
+                            uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+                            mbar_expect_tx(&full_bar[stage], tx_bytes);
+                            tma_load_5d(sa, &a.mapA[mi], &full_bar[stage], c * CC, cw, ch, cd, t.n0);
+                            tma_load_3d(sa + a_bytes, &a.mapW, &full_bar[stage], c * CC, nrow0, tap);
+                            if (++stage == nstages) {
+                                stage = 0;
+                                phase ^= 1u;
+                            }
+                        }
+                    }
+                }
+            } else
             for (int item = item0; item < nitems; item += item_step) {
                 const TileCoord t = decode_tile(a, tile_of(item));
                 const int nrow0 = t.nt * a.ntile;
@@ -332,11 +368,11 @@ size_t conv_tc_smem_bytes(const ConvArgs& a) {
            1024 /*align*/;
 }
 
-template <int CC, bool KHS>
+template <int CC, int MODE>
 static cudaError_t launch_variant(const ConvArgs& a, int grid, size_t smem_bytes, cudaStream_t stream) {
     static bool attr_set = false;  // one process drives one device
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<CC, KHS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<CC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              232448);
         if (e != cudaSuccess) return e;
         attr_set = true;
@@ -354,21 +390,31 @@ static cudaError_t launch_variant(const ConvArgs& a, int grid, size_t smem_bytes
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, conv_tc_kernel<CC, KHS>, a);
+        return cudaLaunchKernelEx(&cfg, conv_tc_kernel<CC, MODE>, a);
     }
-    conv_tc_kernel<CC, KHS><<<grid, kThreads, smem_bytes, stream>>>(a);
+    conv_tc_kernel<CC, MODE><<<grid, kThreads, smem_bytes, stream>>>(a);
     return cudaGetLastError();
 }
 
 cudaError_t launch_conv_tc(const ConvArgs& a, int grid, size_t smem_bytes, cudaStream_t stream) {
     if (a.khshift) {
-        if (a.cc == 64) return launch_variant<64, true>(a, grid, smem_bytes, stream);
-        if (a.cc == 32) return launch_variant<32, true>(a, grid, smem_bytes, stream);
-        return launch_variant<16, true>(a, grid, smem_bytes, stream);
+        if (a.cc == 64) return launch_variant<64, kModeKhs>(a, grid, smem_bytes, stream);
+        if (a.cc == 32) return launch_variant<32, kModeKhs>(a, grid, smem_bytes, stream);
+        return launch_variant<16, kModeKhs>(a, grid, smem_bytes, stream);
     }
-    if (a.cc == 64) return launch_variant<64, false>(a, grid, smem_bytes, stream);
-    if (a.cc == 32) return launch_variant<32, false>(a, grid, smem_bytes, stream);
-    return launch_variant<16, false>(a, grid, smem_bytes, stream);
+    if (a.stride == 2 && a.ntaps == 27 && !a.pair) {
+        if (a.cc == 64) return launch_variant<64, kModeS2>(a, grid, smem_bytes, stream);
+        if (a.cc == 32) return launch_variant<32, kModeS2>(a, grid, smem_bytes, stream);
+        return launch_variant<16, kModeS2>(a, grid, smem_bytes, stream);
+    }
+    if (a.stride == 1 && a.ntaps == 27 && !a.pair) {
+        if (a.cc == 64) return launch_variant<64, kModeS1>(a, grid, smem_bytes, stream);
+        if (a.cc == 32) return launch_variant<32, kModeS1>(a, grid, smem_bytes, stream);
+        return launch_variant<16, kModeS1>(a, grid, smem_bytes, stream);
+    }
+    if (a.cc == 64) return launch_variant<64, kModeGeneric>(a, grid, smem_bytes, stream);
+    if (a.cc == 32) return launch_variant<32, kModeGeneric>(a, grid, smem_bytes, stream);
+    return launch_variant<16, kModeGeneric>(a, grid, smem_bytes, stream);
 }
 
 }  // namespace bsg
