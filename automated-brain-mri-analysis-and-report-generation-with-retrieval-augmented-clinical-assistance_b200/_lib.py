@@ -60,6 +60,8 @@ def _declare(lib):
         fn.argtypes = sig
     lib.bsg_ccl26_workspace_bytes.restype = C.c_size_t
     lib.bsg_ccl26_workspace_bytes.argtypes = [i, i, i]
+    lib.bsg_select_workspace_bytes.restype = C.c_size_t
+    lib.bsg_select_workspace_bytes.argtypes = []
 
 
 _vp, _i, _sz, _u32, _f, _d = C.c_void_p, C.c_int, C.c_size_t, C.c_uint32, C.c_float, C.c_double
@@ -76,6 +78,14 @@ _EXTRA_SIGS = {
     "bsg_masked_channel_stats": [_vp, _i, _sz, _vp, _vp, _vp],
     "bsg_crop_normalize": [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "bsg_masked_moments": [_vp, _i, _i, _i, C.POINTER(_u32), _i, _u32, _vp, _vp],
+    "bsg_binary_morph6": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "bsg_mask_andnot": [_vp, _vp, _sz, _vp, _vp],
+    "bsg_edt": [_vp, _i, _i, _i, C.POINTER(_d), _vp, _vp, _vp],
+    "bsg_surface_gradient_sums": [_vp, _vp, _vp, _i, _i, _i, _d, _vp, _vp],
+    "bsg_intensity_moments": [_vp, _vp, _sz, _d, _vp, _vp, _vp],
+    "bsg_masked_compact_keys": [_vp, _vp, _sz, _vp, _vp, _vp],
+    "bsg_select_ranks": [_vp, _sz, C.POINTER(C.c_ulonglong), _i, _vp, _vp, _sz, _vp],
+    "bsg_masked_threshold_count": [_vp, _vp, _vp, _vp, _sz, _d, _d, _d, _vp, _vp],
     "bsg_gather_patch_tta": [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(_i), _i, _vp, _i, _i, _vp],
     "bsg_norm_finalize": [_vp, _i, _i, _i, _d, _f, _vp, _vp, _vp, _vp],
     "bsg_norm_apply_lrelu": [_vp, _sz, _i, _i, _i, _i, _vp, _f, _i, _i, _vp],

@@ -197,9 +197,10 @@ constexpr int kT0 = 4, kT1 = 8, kT2 = 64, kTileVox = kT0 * kT1 * kT2;
 
 // Pass 1: union-find inside each tile, entirely in shared memory; writes L[i] = global index of the local root
 // (or -1 for background).
-// conn6 != 0: face neighbours only (scipy.ndimage default structure, used by binary_fill_holes); else 26-connected.
+// maxd: largest |o0|+|o1|+|o2| of a neighbour offset — 1: 6-connected (scipy.ndimage default structure, used by
+// binary_fill_holes), 2: 18-connected, 3: 26-connected.
 __global__ void __launch_bounds__(kThreads) ccl_local_kernel(const uint8_t* __restrict__ vol, uint32_t maskbits, int d0,
-                                                             int d1, int d2, int* __restrict__ L, int conn6) {
+                                                             int d1, int d2, int* __restrict__ L, int maxd) {
     __shared__ int sl[kTileVox];
     __shared__ uint8_t sf[kTileVox];
     const int t2n = (d2 + kT2 - 1) / kT2, t1n = (d1 + kT1 - 1) / kT1, t0n = (d0 + kT0 - 1) / kT0;
@@ -222,10 +223,10 @@ __global__ void __launch_bounds__(kThreads) ccl_local_kernel(const uint8_t* __re
             // 13 backward neighbours (smaller raster index)
 #pragma unroll
             for (int k = 0; k < 13; ++k) {
-                if (conn6 && k != 4 && k != 10 && k != 12) continue;  // (-1,0,0), (0,-1,0), (0,0,-1)
                 const int o0 = k < 9 ? -1 : 0;
                 const int o1 = k < 9 ? (k / 3 - 1) : (k < 12 ? -1 : 0);
                 const int o2 = k < 9 ? (k % 3 - 1) : (k < 12 ? (k - 9 - 1) : -1);
+                if ((o0 != 0) + (o1 != 0) + (o2 != 0) > maxd) continue;
                 const int j0 = i0 + o0, j1 = i1 + o1, j2 = i2 + o2;
                 if (j0 < 0 || j1 < 0 || j1 >= kT1 || j2 < 0 || j2 >= kT2) continue;
                 const int m = (j0 * kT1 + j1) * kT2 + j2;
@@ -251,7 +252,7 @@ __global__ void __launch_bounds__(kThreads) ccl_local_kernel(const uint8_t* __re
 }
 
 // Pass 2: merge across tile faces with global atomics (only voxels on a low face of their tile do any work).
-__global__ void __launch_bounds__(kThreads) ccl_border_kernel(int d0, int d1, int d2, int* __restrict__ L, int conn6) {
+__global__ void __launch_bounds__(kThreads) ccl_border_kernel(int d0, int d1, int d2, int* __restrict__ L, int maxd) {
     const size_t n = static_cast<size_t>(d0) * d1 * d2;
     const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -263,10 +264,10 @@ __global__ void __launch_bounds__(kThreads) ccl_border_kernel(int d0, int d1, in
         if (!(f0 || f1lo || f1hi || f2lo || f2hi)) continue;
 #pragma unroll
         for (int k = 0; k < 13; ++k) {
-            if (conn6 && k != 4 && k != 10 && k != 12) continue;
             const int o0 = k < 9 ? -1 : 0;
             const int o1 = k < 9 ? (k / 3 - 1) : (k < 12 ? -1 : 0);
             const int o2 = k < 9 ? (k % 3 - 1) : (k < 12 ? (k - 9 - 1) : -1);
+            if ((o0 != 0) + (o1 != 0) + (o2 != 0) > maxd) continue;
             const int j0 = i0 + o0, j1 = i1 + o1, j2 = i2 + o2;
             if (j0 < 0 || j1 < 0 || j1 >= d1 || j2 < 0 || j2 >= d2) continue;
             // same tile => already merged by the local pass
@@ -651,8 +652,9 @@ int bsg_ccl26_stats(const uint8_t* vol, int d0, int d1, int d2, uint32_t maskbit
 int bsg_ccl_stats(const uint8_t* vol, int d0, int d1, int d2, uint32_t maskbits, int connectivity, int* labels,
                   int* ncomp_dev, void* comp_stats, int stats_cap, void* workspace, size_t workspace_bytes,
                   void* stream) {
-    BSG_REQUIRE(connectivity == 6 || connectivity == 26, "connectivity %d (6 or 26)", connectivity);
-    const int conn6 = connectivity == 6;
+    BSG_REQUIRE(connectivity == 6 || connectivity == 18 || connectivity == 26, "connectivity %d (6, 18 or 26)",
+                connectivity);
+    const int maxd = connectivity == 6 ? 1 : (connectivity == 18 ? 2 : 3);
     BSG_REQUIRE(vol != nullptr && labels != nullptr && ncomp_dev != nullptr && workspace != nullptr, "null argument");
     BSG_REQUIRE(d0 > 0 && d1 > 0 && d2 > 0, "empty volume");
     const size_t n = static_cast<size_t>(d0) * d1 * d2;
@@ -665,8 +667,8 @@ int bsg_ccl_stats(const uint8_t* vol, int d0, int d1, int d2, uint32_t maskbits,
     const int nchunks = static_cast<int>((n + kChunk - 1) / kChunk);
     const int ntiles = ceil_div(d0, kT0) * ceil_div(d1, kT1) * ceil_div(d2, kT2);
     const int sms = sm_count_cached();
-    ccl_local_kernel<<<ntiles < sms * 8 ? ntiles : sms * 8, kThreads, 0, s>>>(vol, maskbits, d0, d1, d2, L, conn6);
-    ccl_border_kernel<<<grid_for(n, kThreads), kThreads, 0, s>>>(d0, d1, d2, L, conn6);
+    ccl_local_kernel<<<ntiles < sms * 8 ? ntiles : sms * 8, kThreads, 0, s>>>(vol, maskbits, d0, d1, d2, L, maxd);
+    ccl_border_kernel<<<grid_for(n, kThreads), kThreads, 0, s>>>(d0, d1, d2, L, maxd);
     ccl_flatten_count_kernel<<<nchunks < sms * 8 ? nchunks : sms * 8, kThreads, 0, s>>>(n, L, chunk);
     ccl_scan_kernel<<<1, 1024, 0, s>>>(nchunks, chunk, ncomp_dev);
     BSG_CUDA_OK(cudaMemsetAsync(labels, 0, n * sizeof(int), s));

@@ -121,3 +121,126 @@ def analyze_necrosis_pattern(seg_data, tumor_masks, voxel_dims):
     return {"necrosis_present": True, "necrosis_volume_cm3": float(ncr_volume),
             "necrosis_percentage": float(necrosis_pct), "pattern": pattern, "location": location,
             "location_description": where, "description": description}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Border regularity, margin definition, cystic / solid (reference :133-397) — device morphology, exact EDT, fp64
+# reductions and exact percentiles (csrc/morph.cu); the scalar scoring stays on the host.
+# ------------------------------------------------------------------------------------------------------------------
+
+def _grade(score, table, default):
+    """first (threshold, classification, description) whose threshold the score exceeds"""
+    for thr, name, text in table:
+        if score > thr:
+            return name, text
+    return default
+
+
+_CONTOUR_GRADES = (
+    (0.7, "Smooth contour", "Smooth, regular outer contour (note: does not indicate margin sharpness)"),
+    (0.5, "Mildly lobulated", "Some contour irregularity with mild lobulation"),
+    (0.3, "Lobulated", "Lobulated/irregular outer contour"),
+)
+_CONTOUR_WORST = ("Highly irregular", "Highly irregular/spiculated outer contour")
+
+_MARGIN_GRADES = (
+    (0.6, "Sharp transition", "Abrupt tumor-brain intensity transition, well-demarcated margin"),
+    (0.4, "Moderate transition", "Moderately distinct margin with some gradual transition zones"),
+    (0.2, "Gradual transition", "Indistinct margin with gradual intensity blending into brain"),
+)
+_MARGIN_WORST = ("Infiltrative transition", "No clear intensity demarcation, tumor infiltrates surrounding parenchyma")
+
+
+def analyze_border_regularity(mask, voxel_dims):
+    """Contour smoothness from the variation of |grad(signed distance)| over the surface voxels (reference :133-205)."""
+    from .. import voxelops as V
+    from .utils import mask_u8
+
+    m = mask_u8(mask)
+    if int(m.count_nonzero()) == 0:
+        return {"regularity_score": 0, "classification": "No tumor", "description": "No tumor detected"}
+    inside = V.distance_transform_edt(m)
+    outside = V.distance_transform_edt((m == 0).to(m.dtype))
+    count, mean, std = V.surface_gradient_stats(m, inside, outside)
+    if count < 10:
+        return {"regularity_score": 1.0, "classification": "Too small to assess",
+                "description": "Tumor too small for border analysis"}
+    regularity = 1.0 / (1.0 + std / mean) if std > 0 else 1.0
+    name, text = _grade(regularity, _CONTOUR_GRADES, _CONTOUR_WORST)
+    return {"regularity_score": float(regularity), "classification": name, "description": text,
+            "surface_voxel_count": int(count), "concept": "contour_smoothness"}
+
+
+def analyze_margin_definition(t1ce_data, seg_data, tumor_masks, voxel_dims):
+    """Sharpness of the tumour-brain intensity transition on T1ce (reference :208-290)."""
+    from .. import voxelops as V
+    from .utils import mask_u8
+
+    wt = mask_u8(tumor_masks["wt"])
+    if int(wt.count_nonzero()) == 0:
+        return {"margin_sharpness": 0, "classification": "No tumor", "description": "No tumor detected"}
+    t1ce = V.as_intensity(t1ce_data)
+    peritumoral = V.mask_andnot(V.binary_dilation(wt, iterations=5), wt)
+    _, tumor_mean, _, _, _ = V.intensity_moments(t1ce, wt)
+    n_peri, peri_mean, _, _, _ = V.intensity_moments(t1ce, peritumoral)
+    if n_peri == 0:
+        return {"margin_sharpness": 0.5, "classification": "Could not assess",
+                "description": "Insufficient peritumoral tissue for analysis"}
+    contrast = abs(tumor_mean - peri_mean) / peri_mean if peri_mean > 0 else 0
+    n_in, in_mean, in_std, _, _ = V.intensity_moments(t1ce, V.mask_andnot(wt, V.binary_erosion(wt)))
+    n_out, out_mean, out_std, _, _ = V.intensity_moments(t1ce, V.mask_andnot(V.binary_dilation(wt), wt))
+    step = abs(in_mean - out_mean) / (in_std + out_std + 1e-6) if n_in > 0 and n_out > 0 else 0
+    sharpness = min(1.0, (contrast + step) / 2)
+    name, text = _grade(sharpness, _MARGIN_GRADES, _MARGIN_WORST)
+    return {"margin_sharpness": float(sharpness), "contrast_ratio": float(contrast), "border_gradient": float(step),
+            "classification": name, "description": text, "concept": "intensity_transition"}
+
+
+def analyze_cystic_vs_solid(t1_data, t2_data, flair_data, seg_data, tumor_masks, voxel_dims):
+    """Cystic / solid / mixed classification from CSF-like signal inside the necrotic core (reference :293-397)."""
+    from .. import voxelops as V
+    from .utils import mask_u8
+
+    ncr_count, wt_count = tumor_masks["ncr"].sum(), tumor_masks["wt"].sum()
+    if wt_count == 0:
+        return {"classification": "No tumor", "cystic_percentage": 0, "solid_percentage": 0,
+                "description": "No tumor detected"}
+    voxel_vol = np.prod(voxel_dims) / 1000
+    t1, t2, flair = V.as_intensity(t1_data), V.as_intensity(t2_data), V.as_intensity(flair_data)
+    # CSF reference levels: bottom 10 % of T1, top 15 % of T2, bottom 20 % of FLAIR (over the non-zero voxels)
+    t1_upper = V.MaskedValues(t1).percentiles([10])[0]
+    t2_lower = V.MaskedValues(t2).percentiles([85])[0]
+    flair_upper = V.MaskedValues(flair).percentiles([20])[0]
+    cystic_fraction, t2_cv, flair_t2_ratio = 0, 0, 1
+    if ncr_count > 0:
+        ncr = mask_u8(tumor_masks["ncr"])
+        csf_like = V.masked_threshold_count(ncr, t1, t1_upper * 1.5, t2, t2_lower * 0.8, flair, flair_upper * 2)
+        cystic_fraction = csf_like / ncr_count
+        _, t2_mean, t2_std, _, _ = V.intensity_moments(t2, ncr)
+        _, flair_mean, _, _, _ = V.intensity_moments(flair, ncr)
+        if t2_mean > 0:
+            t2_cv, flair_t2_ratio = t2_std / t2_mean, flair_mean / t2_mean
+    wt_volume = wt_count * voxel_vol
+    cystic_volume = ncr_count * voxel_vol * cystic_fraction
+    cystic_pct = (cystic_volume / wt_volume * 100) if wt_volume > 0 else 0
+    if cystic_pct > 70:
+        name, text = "Predominantly cystic", "Large cystic component with thin wall/rim"
+    elif cystic_pct > 40:
+        name, text = "Cystic with solid component", "Mixed cystic and solid tumor with significant cystic component"
+    elif cystic_pct > 15:
+        name, text = "Solid with cystic component", "Predominantly solid tumor with cystic/necrotic areas"
+    elif ncr_count > 0 and t2_cv > 0.3:
+        name, text = "Solid with necrosis", "Solid tumor with central necrotic (non-cystic) component"
+    elif ncr_count > 0:
+        name, text = "Solid with possible cyst", "Solid tumor with possible small cystic component"
+    else:
+        name, text = "Solid", "Homogeneous solid tumor without significant cystic component"
+    signal = {
+        "t2_homogeneity": "Homogeneous" if t2_cv < 0.2 else ("Mildly heterogeneous" if t2_cv < 0.4 else "Heterogeneous"),
+        "flair_suppression": "Present (suggests true cyst)" if flair_t2_ratio < 0.7
+        else "Absent (suggests necrosis/protein)",
+        "csf_like_signal_fraction": float(cystic_fraction),
+    }
+    return {"classification": name, "cystic_volume_cm3": float(cystic_volume), "cystic_percentage": float(cystic_pct),
+            "solid_volume_cm3": float(wt_volume - cystic_volume), "solid_percentage": float(100 - cystic_pct),
+            "signal_characteristics": signal, "description": text}

@@ -113,3 +113,57 @@ def get_bounding_box(mask):
     mx = [int(s["mx0"]), int(s["mx1"]), int(s["mx2"])]
     return {"min_x": mn[0], "max_x": mx[0], "min_y": mn[1], "max_y": mx[1], "min_z": mn[2], "max_z": mx[2],
             "size_x": mx[0] - mn[0] + 1, "size_y": mx[1] - mn[1] + 1, "size_z": mx[2] - mn[2] + 1}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Intensity statistics (reference utils.py:27-68)
+# ------------------------------------------------------------------------------------------------------------------
+
+def mask_u8(mask):
+    """LabelMask / bool array / tensor -> cuda uint8 volume (non-zero = set)."""
+    if isinstance(mask, LabelMask):
+        return mask.tensor().to(torch.uint8)
+    return V.as_mask(mask)
+
+
+_EMPTY_STATS = ("mean", "std", "min", "max", "median", "q25", "q75")
+
+
+def get_intensity_stats(data, mask):
+    """mean / std / min / max / median / quartiles of data[mask > 0] (reference utils.py:27-51).  Moments are fp64
+    device sums; the order statistics are exact (radix select) and interpolated the way np.percentile does."""
+    d, m = V.as_intensity(data), mask_u8(mask)
+    cnt, mean, std, lo, hi = V.intensity_moments(d, m)
+    if cnt == 0:
+        out = {k: None for k in _EMPTY_STATS}
+        out["voxel_count"] = 0
+        return out
+    sel = V.MaskedValues(d, m)
+    q25, q75 = sel.percentiles([25, 75])
+    return {"mean": float(mean), "std": float(std), "min": float(lo), "max": float(hi), "median": float(sel.median()),
+            "q25": q25, "q75": q75, "voxel_count": int(cnt)}
+
+
+def _gt_threshold(data, thr):
+    """data > thr for float32 data and a float64 threshold, decided as numpy decides it for float64 data."""
+    t32 = np.float32(thr)
+    if np.float64(t32) > thr:  # rounding went up: x > thr  <=>  x >= t32
+        return data >= float(t32)
+    return data > float(t32)
+
+
+def get_brain_mask(data, threshold_percentile=5):
+    """data > percentile(data[data > 0], p) (reference utils.py:62-67); cuda bool tensor."""
+    d = V.as_intensity(data)
+    sel = V.MaskedValues(d, None)
+    if sel.count == 0:  # data.max() <= 0 (the reference tests == 0): nothing is brain
+        return d > 0
+    return _gt_threshold(d, sel.percentiles([threshold_percentile])[0])
+
+
+def get_normal_brain_stats(data, seg_mask):
+    """Intensity statistics of non-tumour brain tissue (reference utils.py:54-60)."""
+    d = V.as_intensity(data)
+    seg = seg_mask.vol if isinstance(seg_mask, LabelVolume) else V.as_label_volume(seg_mask)
+    normal = get_brain_mask(d, 5) & (seg == 0)
+    return get_intensity_stats(d, normal)

@@ -133,8 +133,9 @@ typedef struct bsg_comp_stats {
  * count exceeds stats_cap only the first stats_cap components are recorded.  workspace: device scratch of at least
  * bsg_ccl26_workspace_bytes(). */
 size_t bsg_ccl26_workspace_bytes(int d0, int d1, int d2);
-/* Same with a choice of connectivity: 26 (above) or 6 (scipy.ndimage's default structure — the one binary_fill_holes
- * uses in nnU-Net v1 create_nonzero_mask).  Label value 0 may be the foreground (maskbits bit 0). */
+/* Same with a choice of connectivity: 26 (above), 18 (generate_binary_structure(3, 2), step6_normal_structures.py:66-67)
+ * or 6 (scipy.ndimage's default structure — the one binary_fill_holes uses in nnU-Net v1 create_nonzero_mask,
+ * SURVEY App. A.8).  Label value 0 may be the foreground (maskbits bit 0). */
 int bsg_ccl_stats(const uint8_t* vol, int d0, int d1, int d2, uint32_t maskbits, int connectivity, int* labels,
                   int* ncomp_dev, void* comp_stats, int stats_cap, void* workspace, size_t workspace_bytes,
                   void* stream);
@@ -176,6 +177,45 @@ int bsg_masked_channel_stats(const float* vol, int C, size_t n, const uint8_t* m
  * (mean_std: device fp32 [C][2]); mask_out (may be NULL) receives the cropped mask. */
 int bsg_crop_normalize(const float* vol, int C, int Z, int Y, int X, const uint8_t* mask, int z0, int y0, int x0, int cz,
                        int cy, int cx, const float* mean_std, float* out, uint8_t* mask_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Voxel operations of the remaining feature-extraction steps.  Masks are uint8 volumes
+ * (non-zero = set; outputs are 0 / 1), intensities fp32 volumes, all C-order (d0, d1, d2), device memory.
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* scipy.ndimage.binary_erosion / binary_dilation with the default 6-connected structure, border_value = 0 and
+ * `iterations` >= 1 repetitions (feature_extraction/step4_morphology.py:146,227,252-254; step1:225; step2:373).
+ * in / out / tmp are distinct buffers; tmp (same size) is only touched when iterations > 1. */
+int bsg_binary_morph6(const uint8_t* in, uint8_t* out, uint8_t* tmp, int d0, int d1, int d2, int dilate, int iterations,
+                      void* stream);
+/* out = a & ~b (`dilated & ~wt_mask`, step4:228); b may be NULL (out = a != 0). */
+int bsg_mask_andnot(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out, void* stream);
+/* scipy.ndimage.distance_transform_edt(mask, sampling) (step4:160-161, step6:206): out (fp64) = exact Euclidean
+ * distance of every non-zero voxel to the nearest zero voxel, 0 on zero voxels; sampling: 3 host doubles or NULL (1,1,1).
+ * Bit-exact with SciPy for isotropic sampling; +inf everywhere if the mask has no zero voxel (SciPy's result is
+ * unspecified there).  tmp: fp64 scratch of the same size. */
+int bsg_edt(const uint8_t* mask, int d0, int d1, int d2, const double* sampling, double* out, double* tmp, void* stream);
+/* Border-regularity reduction (analyze_border_regularity, step4:146-176): over the surface voxels mask & ~erode6(mask),
+ * g = |np.gradient(dist_in - dist_out)|; out3 (device fp64) = {count, sum(g - center), sum((g - center)^2)}. */
+int bsg_surface_gradient_sums(const uint8_t* mask, const double* dist_in, const double* dist_out, int d0, int d1, int d2,
+                              double center, double* out3, void* stream);
+/* Intensity statistics of data[mask > 0] (get_intensity_stats, feature_extraction/utils.py:27-51) or, with mask NULL,
+ * of data[data > 0] (utils.py:57,66; step4:318-320): out3 (device fp64) = {count, sum(x - center), sum((x - center)^2)},
+ * minmax (device, 2 floats) = {min, max} (undefined when count == 0). */
+int bsg_intensity_moments(const float* data, const uint8_t* mask, size_t n, double center, double* out3, float* minmax,
+                          void* stream);
+/* The selected values as order-preserving uint32 keys, unordered, into keys_out (capacity >= n); *count_dev = how many. */
+int bsg_masked_compact_keys(const float* data, const uint8_t* mask, size_t n, uint32_t* keys_out,
+                            unsigned long long* count_dev, void* stream);
+/* Exact order statistics by 4-pass radix select: out_dev[r] (device floats) = the value of 0-based rank ranks_host[r]
+ * (1 <= nranks <= 8) among the `count` keys — the two neighbours np.percentile / np.median interpolate between. */
+size_t bsg_select_workspace_bytes(void);
+int bsg_select_ranks(const uint32_t* keys, size_t count, const unsigned long long* ranks_host, int nranks,
+                     float* out_dev, void* workspace, size_t workspace_bytes, void* stream);
+/* *out_dev = number of voxels with mask != 0 and x1 < t1 and x2 > t2 and x3 < t3 (fp64 comparisons; a NULL x_k skips
+ * its test) — the CSF-like signal count of analyze_cystic_vs_solid (step4:331-337). */
+int bsg_masked_threshold_count(const float* x1, const float* x2, const float* x3, const uint8_t* mask, size_t n, double t1,
+                               double t2, double t3, unsigned long long* out_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Sliding-window plumbing of predict_3D (nnU-Net v1 _internal_predict_3D_3Dconv_tiled /

@@ -6,6 +6,9 @@ Fixtures (all small, committed):
   unet_keys.json          state_dict key list / shapes, parameter count and forward GFLOPs of the two BraTS shapes
   postproc.npz/.json      label volumes and the reference functions' outputs on them (remap, Dice, step3, step4)
   sliding_window.json     known-answer facts for the restated nnU-Net v1 tiler
+  voxelops.npz/.json      MRI-like volumes + the reference's intensity statistics / border / margin / cystic results
+                          and SciPy's morphology, EDT and 6/18/26-connected labellings on them (python -m
+                          oracle.make_golden voxelops regenerates only these)
 """
 import json
 import os
@@ -118,6 +121,54 @@ def postproc_fixtures():
         json.dump(results, f, indent=1)
 
 
+def voxelops_fixtures():
+    """feature_extraction/utils.py:27-68 and step4_morphology.py:133-397 run on seeded synthetic cases, plus the SciPy
+    primitives underneath them (the kernels in csrc/morph.cu are checked against both)."""
+    from scipy import ndimage as ndi
+    ns = R.load_reference()
+    shape = (48, 40, 36)
+    vols, results = {}, {}
+    for seed in (0, 1):
+        pred, _ = SY.label_pair(seed, shape)
+        mri = SY.mri_volumes(seed, pred)
+        vols[f"seg{seed}"] = pred
+        for k, v in mri.items():
+            assert np.array_equal(v, v.astype(np.int16).astype(np.float32))
+            vols[f"{k}{seed}"] = v.astype(np.int16)  # integer-valued, like int16 NIfTI data
+        d = {k: v.astype(np.float64) for k, v in mri.items()}  # what nibabel's get_fdata() hands the reference
+        segf = pred.astype(np.float64)
+        masks = ns.utils.get_tumor_masks(segf)
+        r = {}
+        for tag, vd in (("iso", (1.0, 1.0, 1.0)), ("aniso", (0.9, 1.1, 1.25))):
+            r[f"border_{tag}"] = ns.step4.analyze_border_regularity(masks["wt"], vd)
+            r[f"margin_{tag}"] = ns.step4.analyze_margin_definition(d["t1ce"], segf, masks, vd)
+            r[f"cystic_{tag}"] = ns.step4.analyze_cystic_vs_solid(d["t1"], d["t2"], d["flair"], segf, masks, vd)
+        r["stats"] = {f"{mod}_{reg}": ns.utils.get_intensity_stats(d[mod], masks[reg])
+                      for mod in ("t1", "t1ce", "t2", "flair") for reg in ("wt", "ncr", "et")}
+        r["stats_empty"] = ns.utils.get_intensity_stats(d["t1"], np.zeros(shape, bool))
+        r["normal_brain"] = {mod: ns.utils.get_normal_brain_stats(d[mod], segf) for mod in ("t1", "flair")}
+        r["brain_mask_count"] = {str(p): int(ns.utils.get_brain_mask(d["t2"], p).sum()) for p in (5, 37.5)}
+        wt = np.asarray(masks["wt"])
+        r["erode"] = {str(k): int(ndi.binary_erosion(wt, iterations=k).sum()) for k in (1, 2, 3)}
+        r["dilate"] = {str(k): int(ndi.binary_dilation(wt, iterations=k).sum()) for k in (1, 2, 5)}
+        vols[f"dilate5_{seed}"] = ndi.binary_dilation(wt, iterations=5)
+        vols[f"erode2_{seed}"] = ndi.binary_erosion(wt, iterations=2)
+        edt = ndi.distance_transform_edt(wt)
+        sq = np.rint(edt ** 2).astype(np.int32)  # isotropic: SciPy's value is sqrt(exact integer) — store the integer
+        assert np.array_equal(np.sqrt(sq.astype(np.float64)), edt)
+        vols[f"edt_in_sq_{seed}"] = sq
+        if seed == 0:
+            vols["edt_out_aniso_0"] = ndi.distance_transform_edt(~wt, sampling=(0.9, 1.1, 1.25))
+        for conn, rank in ((6, 1), (18, 2), (26, 3)):
+            lab, n = ndi.label(pred == 3, structure=ndi.generate_binary_structure(3, rank))
+            vols[f"label{conn}_{seed}"] = lab.astype(np.int32)
+            r[f"label{conn}_count"] = int(n)
+        results[str(seed)] = jsonable(r)
+    np.savez_compressed(os.path.join(OUT, "voxelops.npz"), **vols)
+    with open(os.path.join(OUT, "voxelops.json"), "w") as f:
+        json.dump(results, f, indent=1)
+
+
 def sliding_window_facts():
     g = SW.get_gaussian((128, 128, 128), 1.0 / 8)
     facts = {
@@ -150,8 +201,12 @@ def sliding_window_facts():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    unet_fixtures()
-    postproc_fixtures()
-    sliding_window_facts()
+    if sys.argv[1:] == ["voxelops"]:
+        voxelops_fixtures()
+    else:
+        unet_fixtures()
+        postproc_fixtures()
+        sliding_window_facts()
+        voxelops_fixtures()
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))
