@@ -28,11 +28,14 @@ inline int grid_for(size_t work, int per_block, int waves = 16) {
 // (scipy border_value=0), so an erosion always peels the volume faces.
 __global__ void __launch_bounds__(kThreads) morph6_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
                                                           int d0, int d1, int d2, int dilate) {
-    const size_t n = static_cast<size_t>(d0) * d1 * d2;
-    const size_t s1 = static_cast<size_t>(d2), s0 = static_cast<size_t>(d1) * d2;
-    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const int i2 = static_cast<int>(i % d2), i1 = static_cast<int>((i / d2) % d1), i0 = static_cast<int>(i / s0);
+    // 32-bit index arithmetic (the host checks n < 2^31): 64-bit div / mod per voxel cost more than the 7 byte loads
+    const unsigned n = static_cast<unsigned>(d0) * d1 * d2;
+    const unsigned s1 = static_cast<unsigned>(d2), s0 = static_cast<unsigned>(d1) * d2;
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned row = i / s1;
+        const int i2 = static_cast<int>(i - row * s1), i0 = static_cast<int>(row / d1),
+                  i1 = static_cast<int>(row - static_cast<unsigned>(i0) * d1);
         const bool c = in[i] != 0;
         const bool a0 = i0 > 0 && in[i - s0] != 0, b0 = i0 + 1 < d0 && in[i + s0] != 0;
         const bool a1 = i1 > 0 && in[i - s1] != 0, b1 = i1 + 1 < d1 && in[i + s1] != 0;
@@ -350,6 +353,7 @@ int bsg_binary_morph6(const uint8_t* in, uint8_t* out, uint8_t* tmp, int d0, int
                       void* stream) {
     BSG_REQUIRE(in != nullptr && out != nullptr && d0 > 0 && d1 > 0 && d2 > 0, "bad argument");
     BSG_REQUIRE(iterations >= 1, "iterations %d (repeat-until-stable is not supported)", iterations);
+    BSG_REQUIRE(static_cast<size_t>(d0) * d1 * d2 < (1ull << 31), "volume too large (>= 2^31 voxels)");
     BSG_REQUIRE(in != out && (iterations == 1 || (tmp != nullptr && tmp != in && tmp != out)),
                 "in / out / tmp must be distinct buffers (tmp is needed for iterations > 1)");
     cudaStream_t s = static_cast<cudaStream_t>(stream);

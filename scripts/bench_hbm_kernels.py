@@ -107,6 +107,48 @@ def main():
            timed(lambda: L.check(lib.bsg_norm_apply_lrelu(ptr(x16), pv, 4, 64, 64, 0, ptr(ss), 0.01, 1, 1, L.stream_ptr()))),
            2 * x16.numel() * 2)
 
+    # feature-extraction voxel ops (csrc/morph.cu) at the BraTS volume size; CPU times of the SciPy / NumPy calls they
+    # replace beside them
+    import time
+    from scipy import ndimage as ndi
+    wt_np = pred > 0
+    wt = V.as_mask(wt_np)
+    mri = torch.from_numpy(SY.mri_volumes(0, pred)["t1ce"]).to(dev)
+
+    def cpu_ms(fn):
+        t = time.perf_counter()
+        fn()
+        return (time.perf_counter() - t) * 1e3
+
+    report("binary_dilation x5 (6-conn)", timed(lambda: V.binary_dilation(wt, 5)), 5 * 2 * nv)
+    print(f"    scipy.ndimage.binary_dilation(iterations=5): {cpu_ms(lambda: ndi.binary_dilation(wt_np, iterations=5)):.1f} ms")
+    report("binary_erosion x1", timed(lambda: V.binary_erosion(wt, 1)), 2 * nv)
+    report("distance_transform_edt (3 fp64 passes)", timed(lambda: V.distance_transform_edt(wt)), nv * (1 + 8 + 16 + 16))
+    print(f"    scipy.ndimage.distance_transform_edt: {cpu_ms(lambda: ndi.distance_transform_edt(wt_np)):.1f} ms")
+    report("intensity_moments (2 passes, masked)", timed(lambda: V.intensity_moments(mri, wt)), 2 * nv * 5)
+    report("compact + radix select (data > 0, 2 ranks)", timed(lambda: V.MaskedValues(mri).percentiles([5])),
+           nv * 4 + int((mri > 0).sum()) * 4 * 5)
+    mri_np = mri.cpu().numpy().astype(np.float64)
+    print(f"    np.percentile(data[data > 0], 5): {cpu_ms(lambda: np.percentile(mri_np[mri_np > 0], 5)):.1f} ms")
+    report("ccl 18-conn (labels only)", timed(lambda: V.ccl(a, V.MASK_GT0, 18)), 5 * nv)
+    from brainseg_b200.feature_extraction import step4_morphology as S4
+    from brainseg_b200.feature_extraction import utils as U
+    from oracle import intensity as OI
+    from oracle import postproc as OP
+    lv = U.LabelVolume(pred)
+    gm = U.get_tumor_masks(lv)
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    S4.analyze_border_regularity(gm["wt"], (1.0, 1.0, 1.0))
+    S4.analyze_margin_definition(mri, lv, gm, (1.0, 1.0, 1.0))
+    torch.cuda.synchronize()
+    gpu_ms = (time.perf_counter() - t) * 1e3
+    om = OP.get_tumor_masks(pred.astype(np.float64))
+    c = cpu_ms(lambda: (OI.analyze_border_regularity(om["wt"], (1.0, 1.0, 1.0)),
+                        OI.analyze_margin_definition(mri_np, pred, om, (1.0, 1.0, 1.0))))
+    print(f"analyze_border_regularity + analyze_margin_definition: {gpu_ms:.1f} ms through the drop-in functions (host wall "
+          f"clock, incl. syncs) vs {c:.0f} ms for the NumPy / SciPy restatement on this host")
+
 
 if __name__ == "__main__":
     main()
