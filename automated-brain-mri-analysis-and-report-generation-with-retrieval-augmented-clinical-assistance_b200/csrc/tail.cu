@@ -23,22 +23,20 @@ struct MirrorSet {
 };
 
 // out[m][d][h][w][c] = vol[c][z0 + fz(d)][y0 + fy(h)][x0 + fx(w)], c < C; channels C..cpad-1 are zero.
-// grid (ceil(P1*P2 / 256), P0, mirrors): one thread per output voxel, 32-bit index math, 256-bit stores.
+// grid (ceil(P1*P2 / 256), P0): one thread per SOURCE voxel of the tile — it is read and converted once and stored to
+// its position in each of the (up to 8) mirrored copies; a warp's 32 consecutive w land on 32 consecutive (or
+// reversed) voxels of every copy, so each store instruction still covers one contiguous 1 KB run.  32-bit index
+// math, 256-bit stores.
 __global__ void __launch_bounds__(kThreads) gather_patch_kernel(const float* __restrict__ vol, int C, int Z, int Y,
                                                                 int X, int z0, int y0, int x0, int P0, int P1, int P2,
                                                                 const MirrorSet ms, __nv_bfloat16* __restrict__ out,
                                                                 int cpad, int out_f16) {
     const int hw = blockIdx.x * blockDim.x + threadIdx.x;
     if (hw >= P1 * P2) return;
-    const int d = blockIdx.y, m = blockIdx.z;
+    const int d = blockIdx.y;
     const int h = hw / P2, w = hw - h * P2;
     const size_t plane = static_cast<size_t>(Z) * Y * X;
-    const int code = ms.code[m];
-    const int sx = x0 + ((code & 1) ? P2 - 1 - w : w);
-    const int sy = y0 + ((code & 2) ? P1 - 1 - h : h);
-    const int sz = z0 + ((code & 4) ? P0 - 1 - d : d);
-    const float* src = vol + (static_cast<size_t>(sz) * Y + sy) * X + sx;
-    __nv_bfloat16* dst = out + ((static_cast<size_t>(m) * P0 + d) * P1 * P2 + hw) * cpad;
+    const float* src = vol + (static_cast<size_t>(z0 + d) * Y + (y0 + h)) * X + (x0 + w);
     for (int c0 = 0; c0 < cpad; c0 += 16) {
         uint32_t pk[8];
 #pragma unroll
@@ -54,13 +52,21 @@ __global__ void __launch_bounds__(kThreads) gather_patch_kernel(const float* __r
                 pk[k] = *reinterpret_cast<uint32_t*>(&p);
             }
         }
-        if (c0 + 16 <= cpad && (reinterpret_cast<uintptr_t>(dst + c0) & 31) == 0) {
-            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(dst + c0), "r"(pk[0]), "r"(pk[1]),
-                         "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
-                         : "memory");
-        } else {
-            *reinterpret_cast<uint4*>(dst + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            if (c0 + 8 < cpad) *reinterpret_cast<uint4*>(dst + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        for (int m = 0; m < ms.n; ++m) {
+            // the source voxel (d, h, w) is element (fz(d), fy(h), fx(w)) of the copy flipped by code m
+            const int code = ms.code[m];
+            const int ow = (code & 1) ? P2 - 1 - w : w;
+            const int oh = (code & 2) ? P1 - 1 - h : h;
+            const int od = (code & 4) ? P0 - 1 - d : d;
+            __nv_bfloat16* dst = out + (((static_cast<size_t>(m) * P0 + od) * P1 + oh) * P2 + ow) * cpad + c0;
+            if (c0 + 16 <= cpad && (reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(dst), "r"(pk[0]), "r"(pk[1]),
+                             "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                             : "memory");
+            } else {
+                *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                if (c0 + 8 < cpad) *reinterpret_cast<uint4*>(dst + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
         }
     }
 }
@@ -269,40 +275,80 @@ struct FinalizeParams {
     int order[kMaxClasses];  // regions_class_order
 };
 
+// One voxel's decision from its class probabilities (argmax, or the ordered > 0.5 assignment of the region trainers).
+__device__ __forceinline__ int decide_label(const FinalizeParams& fp, const float (&p)[kMaxClasses]) {
+    int lab = 0;
+    if (fp.mode == 0) {
+        float best = p[0];
+#pragma unroll
+        for (int k = 1; k < kMaxClasses; ++k)
+            if (k < fp.ncls && p[k] > best) {
+                best = p[k];
+                lab = k;
+            }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kMaxClasses; ++k)
+            if (k < fp.ncls && p[k] > 0.5f) lab = fp.order[k];
+    }
+    return lab;
+}
+
+// VEC voxels per thread and step (VEC = 4: 128-bit loads of the accumulators / weight sums, 32-bit label stores; the
+// host picks it when nvox and every pointer allow).  class_probabilities = aggregated_results /
+// aggregated_nb_of_predictions (IEEE division, as numpy), then np.mean over the folds.
+template <int VEC>
 __global__ void __launch_bounds__(kThreads) finalize_kernel(const FinalizeParams fp, const float* __restrict__ wsum,
                                                             size_t nvox, float* __restrict__ probs,
                                                             uint8_t* __restrict__ seg) {
     const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvox; i += stride) {
-        const float wv = __ldg(wsum + i);
-        float p[kMaxClasses];
+    const size_t ngroups = nvox / VEC;
+    for (size_t g = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
+        const size_t i = g * VEC;
+        float wv[VEC], p[VEC][kMaxClasses];
+        if constexpr (VEC == 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(wsum + i));
+            wv[0] = t.x, wv[1] = t.y, wv[2] = t.z, wv[3] = t.w;
+        } else {
+            wv[0] = __ldg(wsum + i);
+        }
 #pragma unroll
         for (int k = 0; k < kMaxClasses; ++k) {
             if (k < fp.ncls) {
-                // class_probabilities = aggregated_results / aggregated_nb_of_predictions, then np.mean over folds
-                float s = __ldg(fp.acc[0] + k * nvox + i) / wv;
-                for (int j = 1; j < fp.K; ++j) s += __ldg(fp.acc[j] + k * nvox + i) / wv;
-                if (fp.K > 1) s = s / static_cast<float>(fp.K);
-                p[k] = s;
-                if (probs) probs[k * nvox + i] = s;
+                float s[VEC];
+                for (int j = 0; j < fp.K; ++j) {
+                    float a[VEC];
+                    if constexpr (VEC == 4) {
+                        const float4 t = __ldg(reinterpret_cast<const float4*>(fp.acc[j] + k * nvox + i));
+                        a[0] = t.x, a[1] = t.y, a[2] = t.z, a[3] = t.w;
+                    } else {
+                        a[0] = __ldg(fp.acc[j] + k * nvox + i);
+                    }
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) s[v] = j == 0 ? __fdiv_rn(a[v], wv[v]) : s[v] + __fdiv_rn(a[v], wv[v]);
+                }
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    if (fp.K > 1) s[v] = __fdiv_rn(s[v], static_cast<float>(fp.K));
+                    p[v][k] = s[v];
+                }
+                if (probs) {
+                    if constexpr (VEC == 4)
+                        *reinterpret_cast<float4*>(probs + k * nvox + i) = make_float4(s[0], s[1], s[2], s[3]);
+                    else
+                        probs[k * nvox + i] = s[0];
+                }
             }
         }
         if (seg) {
-            int lab = 0;
-            if (fp.mode == 0) {
-                float best = p[0];
+            if constexpr (VEC == 4) {
+                uint32_t packed = 0;
 #pragma unroll
-                for (int k = 1; k < kMaxClasses; ++k)
-                    if (k < fp.ncls && p[k] > best) {
-                        best = p[k];
-                        lab = k;
-                    }
+                for (int v = 0; v < VEC; ++v) packed |= static_cast<uint32_t>(decide_label(fp, p[v]) & 255) << (8 * v);
+                *reinterpret_cast<uint32_t*>(seg + i) = packed;
             } else {
-#pragma unroll
-                for (int k = 0; k < kMaxClasses; ++k)
-                    if (k < fp.ncls && p[k] > 0.5f) lab = fp.order[k];
+                seg[i] = static_cast<uint8_t>(decide_label(fp, p[0]));
             }
-            seg[i] = static_cast<uint8_t>(lab);
         }
     }
 }
@@ -338,7 +384,7 @@ int bsg_gather_patch_tta(const float* vol, int C, int Z, int Y, int X, int z0, i
     MirrorSet ms;
     int rc = fill_mirrors(&ms, mirror_codes_host, nmirrors);
     if (rc != BSG_OK) return rc;
-    dim3 grid(static_cast<unsigned>(ceil_div(P1 * P2, kThreads)), static_cast<unsigned>(P0), static_cast<unsigned>(nmirrors));
+    dim3 grid(static_cast<unsigned>(ceil_div(P1 * P2, kThreads)), static_cast<unsigned>(P0));
     gather_patch_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         vol, C, Z, Y, X, z0, y0, x0, P0, P1, P2, ms, static_cast<__nv_bfloat16*>(out_bf16), cpad, out_f16);
     BSG_CUDA_OK(cudaGetLastError());
@@ -447,8 +493,14 @@ int bsg_finalize(const float* const* acc_list_host, int K, const float* wsum, in
     fp.mode = mode;
     for (int k = 0; k < ncls; ++k) fp.order[k] = order_host ? order_host[k] : k;
     if (nvox == 0) return BSG_OK;
-    finalize_kernel<<<grid_for(nvox, kThreads, 16), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(fp, wsum, nvox,
-                                                                                                     probs, seg);
+    auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    bool vec = nvox % 4 == 0 && aligned16(wsum) && aligned16(probs) && (reinterpret_cast<uintptr_t>(seg) & 3) == 0;
+    for (int j = 0; j < K; ++j) vec = vec && aligned16(acc_list_host[j]);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (vec)
+        finalize_kernel<4><<<grid_for(nvox / 4, kThreads, 16), kThreads, 0, s>>>(fp, wsum, nvox, probs, seg);
+    else
+        finalize_kernel<1><<<grid_for(nvox, kThreads, 16), kThreads, 0, s>>>(fp, wsum, nvox, probs, seg);
     BSG_CUDA_OK(cudaGetLastError());
     return BSG_OK;
 }
