@@ -34,4 +34,14 @@ inline int sm_count_cached() {
     return n;
 }
 
+// Blocks for a grid-stride kernel: enough to cover `work` items at `per_block` each, capped at `waves` resident
+// blocks per SM (a multiple of the SM count, so the last wave is full).
+inline int grid_for(size_t work, int per_block, int waves = 8) {
+    size_t blocks = (work + per_block - 1) / per_block;
+    const size_t cap = static_cast<size_t>(sm_count_cached()) * waves;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return static_cast<int>(blocks);
+}
+
 }  // namespace bsg

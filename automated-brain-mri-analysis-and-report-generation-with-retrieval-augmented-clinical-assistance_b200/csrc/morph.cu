@@ -15,14 +15,6 @@ namespace {
 
 constexpr int kThreads = 256;
 
-inline int grid_for(size_t work, int per_block, int waves = 16) {
-    size_t blocks = (work + per_block - 1) / per_block;
-    const size_t cap = static_cast<size_t>(sm_count_cached()) * waves;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    return static_cast<int>(blocks);
-}
-
 // ------------------------------------------------------------------------------------------ 6-connected morphology
 // out = AND (erosion) / OR (dilation) of the voxel and its six face neighbours; outside the volume counts as 0
 // (scipy border_value=0), so an erosion always peels the volume faces.
@@ -358,7 +350,7 @@ int bsg_binary_morph6(const uint8_t* in, uint8_t* out, uint8_t* tmp, int d0, int
                 "in / out / tmp must be distinct buffers (tmp is needed for iterations > 1)");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t n = static_cast<size_t>(d0) * d1 * d2;
-    const int grid = grid_for(n, kThreads);
+    const int grid = grid_for(n, kThreads, 16);
     // ping-pong so that the last iteration lands in `out`
     const uint8_t* src = in;
     for (int it = 0; it < iterations; ++it) {
@@ -372,7 +364,7 @@ int bsg_binary_morph6(const uint8_t* in, uint8_t* out, uint8_t* tmp, int d0, int
 
 int bsg_mask_andnot(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out, void* stream) {
     BSG_REQUIRE(a != nullptr && out != nullptr, "null argument");
-    mask_andnot_kernel<<<grid_for(n, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a, b, n, out);
+    mask_andnot_kernel<<<grid_for(n, kThreads, 16), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a, b, n, out);
     BSG_CUDA_OK(cudaGetLastError());
     return BSG_OK;
 }

@@ -17,14 +17,6 @@ __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
     return r;
 }
 
-inline int grid_for(size_t work_items, int per_block, int waves = 8) {
-    size_t blocks = (work_items + per_block - 1) / per_block;
-    size_t cap = static_cast<size_t>(sm_count_cached()) * waves;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    return static_cast<int>(blocks);
-}
-
 // ---------------------------------------------------------------------------------------------- LUT kernels
 struct Lut256 {
     uint8_t v[256];

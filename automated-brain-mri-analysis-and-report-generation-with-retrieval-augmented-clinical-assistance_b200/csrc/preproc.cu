@@ -9,14 +9,6 @@ namespace {
 
 constexpr int kThreads = 256;
 
-inline int grid_for(size_t work, int per_block, int waves = 8) {
-    size_t blocks = (work + per_block - 1) / per_block;
-    const size_t cap = static_cast<size_t>(sm_count_cached()) * waves;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    return static_cast<int>(blocks);
-}
-
 // mask[i] = any_c(vol[c][i] != 0)      (create_nonzero_mask: `nonzero_mask = nonzero_mask | (data[c] != 0)`)
 __global__ void __launch_bounds__(kThreads) nonzero_mask_kernel(const float* __restrict__ vol, int C, size_t n,
                                                                 uint8_t* __restrict__ mask) {

@@ -353,14 +353,6 @@ __global__ void __launch_bounds__(kThreads) finalize_kernel(const FinalizeParams
     }
 }
 
-inline int grid_for(size_t work, int per_block, int waves = 8) {
-    size_t blocks = (work + per_block - 1) / per_block;
-    const size_t cap = static_cast<size_t>(sm_count_cached()) * waves;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    return static_cast<int>(blocks);
-}
-
 int fill_mirrors(MirrorSet* ms, const int* codes, int n) {
     BSG_REQUIRE(n >= 1 && n <= kMaxMirrors && codes != nullptr, "mirror count %d (1..8)", n);
     ms->n = n;
