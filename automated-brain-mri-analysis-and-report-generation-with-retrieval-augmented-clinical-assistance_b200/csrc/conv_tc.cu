@@ -6,9 +6,7 @@
 //                               chunks of the N tile — the wide-N, short-K launches (transposed convs, the <= 8^3 levels)
 //                               are bound by the epilogue's convert + store rate, not by the MMAs)
 //   warp 4      TMA producer   (activation halo boxes + weight slabs -> swizzled smem ring)
-//   warp 5      MMA issuer     (one elected lane, tcgen05.mma kind::f16, fp32 accumulators in TMEM, 2 buffers); the
-//                               highest warp id of its scheduler partition, which the warp arbiter favours over the
-//                               instruction-heavy epilogue warp sharing it
+//   warp 5      MMA issuer     (one elected lane, tcgen05.mma kind::f16, fp32 accumulators in TMEM, 2 buffers)
 #include <cuda_fp16.h>
 #include "bsg_ptx.cuh"
 #include "conv_epilogue.cuh"
