@@ -110,3 +110,126 @@ def label_components(seg_data, maskbits=V.MASK_GT0):
     lv = _volume(seg_data)
     labels, n, _ = V.ccl26(lv.vol, maskbits, stats_cap=0)
     return labels, n
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Lesion-level bookkeeping on the component list (reference :155-205, :266-375) and the file-level driver (:445-546).
+# Host arithmetic over a handful of centroids; kept so that `analyze_multiplicity` returns the reference's sections.
+# ------------------------------------------------------------------------------------------------------------------
+SATELLITE_DISTANCE_MM = 20  # step3_multiplicity.py:34
+SEPARATE_DISTANCE_MM = 40   # step3_multiplicity.py:35
+
+
+def _centroid_distance(a, b):
+    return np.sqrt((a["x"] - b["x"]) ** 2 + (a["y"] - b["y"]) ** 2 + (a["z"] - b["z"]) ** 2)
+
+
+def classify_distance_relationship(distance_mm):
+    if distance_mm < SATELLITE_DISTANCE_MM:
+        return "Satellite/adjacent"
+    return "Regional spread" if distance_mm < SEPARATE_DISTANCE_MM else "Distant/separate"
+
+
+def calculate_inter_lesion_distances(components, voxel_dims):
+    """Pairwise centroid distances (mm) between the significant lesions."""
+    pairs = []
+    for i, first in enumerate(components):
+        for second in components[i + 1:]:
+            d = _centroid_distance(first["centroid_mm"], second["centroid_mm"])
+            pairs.append({"component_1": first["id"], "component_2": second["id"], "distance_mm": float(d),
+                          "relationship": classify_distance_relationship(d)})
+    values = [p["distance_mm"] for p in pairs]
+    if not values:
+        return {"distances": [], "min_distance_mm": None, "max_distance_mm": None, "mean_distance_mm": None}
+    return {"distances": pairs, "min_distance_mm": float(min(values)), "max_distance_mm": float(max(values)),
+            "mean_distance_mm": float(np.mean(values))}
+
+
+def detect_satellite_lesions(components, primary_component, voxel_dims):
+    """Secondary lesions whose centroid lies within SATELLITE_DISTANCE_MM of the primary's."""
+    if len(components) < 2:
+        return {"satellite_count": 0, "satellites": [], "has_satellites": False,
+                "description": "Single lesion, no satellites"}
+    found = []
+    for comp in components[1:]:
+        d = _centroid_distance(primary_component["centroid_mm"], comp["centroid_mm"])
+        if d < SATELLITE_DISTANCE_MM:
+            found.append({"component_id": comp["id"], "volume_cm3": comp["volume_cm3"],
+                          "distance_from_primary_mm": float(d), "has_enhancement": comp["has_enhancement"]})
+    text = (f"{len(found)} satellite lesion(s) within {SATELLITE_DISTANCE_MM}mm of primary tumor" if found
+            else "No satellite lesions detected")
+    return {"satellite_count": len(found), "satellites": found, "has_satellites": bool(found),
+            "satellite_threshold_mm": SATELLITE_DISTANCE_MM, "description": text}
+
+
+_PATTERNS = {  # pattern -> (classification, clinical implication, differential considerations)
+    "Solitary": ("Single contiguous lesion", "Unifocal disease, typical for primary brain tumor",
+                 ["Primary glioma", "Solitary metastasis", "Lymphoma", "Abscess"]),
+    "Primary with satellites": ("Main lesion with satellite nodules",
+                                "Suggests local tumor spread or infiltrative growth pattern",
+                                ["High-grade glioma with infiltration", "Multicentric glioma", "Inflammatory process"]),
+    "Regional multifocal": ("Few lesions in regional distribution",
+                            "Regional disease, may be contiguous or multicentric",
+                            ["Multicentric glioma", "Regional metastases", "Demyelinating disease"]),
+    "Distant multifocal": ("Separate lesions in different brain regions",
+                           "Multifocal disease, consider metastatic process",
+                           ["Metastatic disease", "Multicentric glioma", "CNS lymphoma", "Multifocal infection"]),
+    "Diffuse/scattered": ("Multiple lesions throughout brain",
+                          "Diffuse disease pattern, high probability of metastatic or systemic process",
+                          ["Metastatic carcinoma", "CNS lymphoma", "Miliary tuberculosis", "Septic emboli"]),
+}
+
+
+def classify_distribution_pattern(component_analysis, distance_analysis, satellite_analysis, enhancing_analysis):
+    n = component_analysis["num_components"]
+    if n == 0:
+        return {"pattern": "No tumor", "classification": "No lesion detected", "clinical_implication": "N/A",
+                "differential_considerations": []}
+    if n == 1:
+        pattern = "Solitary"
+    elif satellite_analysis["has_satellites"]:
+        pattern = "Primary with satellites"
+    elif n <= 3:
+        far = distance_analysis["max_distance_mm"]
+        pattern = "Regional multifocal" if far and far < SEPARATE_DISTANCE_MM else "Distant multifocal"
+    else:
+        pattern = "Diffuse/scattered"
+    foci = enhancing_analysis["num_enhancing_foci"]
+    if foci == 0:
+        note = "Non-enhancing pattern may suggest low-grade pathology"
+    elif foci > n:
+        note = "Multiple enhancing foci within lesions suggest heterogeneous enhancement"
+    else:
+        note = "Enhancement pattern consistent with lesion count"
+    classification, implication, differentials = _PATTERNS[pattern]
+    return {"pattern": pattern, "classification": classification, "clinical_implication": implication,
+            "differential_considerations": list(differentials), "enhancement_note": note, "lesion_count": n,
+            "enhancing_foci_count": foci}
+
+
+def analyze_multiplicity(input_folder, segmentation_path, output_path=None):
+    """File-level driver (reference :445-546): NIfTI in, the step-3 result dictionary (and JSON file) out.  The
+    narrative `text_summary` of the reference is report generation and is not produced."""
+    from . import utils as U
+
+    case_id = U.get_case_id(input_folder)
+    _, _, t1_header = U.load_nifti(U.get_mri_paths(input_folder, case_id)["t1"])
+    seg, _, _ = U.load_nifti(segmentation_path)
+    voxel_info = U.get_voxel_dimensions(t1_header)
+    dims = [float(v) for v in voxel_info["dimensions_mm"]]  # float64 from here on (see utils.NiftiHeaderView)
+    lv = LabelVolume(seg)  # np.round(seg).astype(int) on the device
+    components = detect_connected_components(lv, dims)
+    lesions = components["components"]
+    distances = calculate_inter_lesion_distances(lesions, dims)
+    if lesions:
+        satellites = detect_satellite_lesions(lesions, lesions[0], dims)
+    else:
+        satellites = {"satellite_count": 0, "satellites": [], "has_satellites": False, "description": "No tumor detected"}
+    enhancing = analyze_enhancing_components(lv, dims)
+    results = {"case_id": case_id, "step": "Step 3 - Lesion multiplicity and distribution", "voxel_info": voxel_info,
+               "component_analysis": components, "distance_analysis": distances, "satellite_analysis": satellites,
+               "enhancing_analysis": enhancing,
+               "distribution_pattern": classify_distribution_pattern(components, distances, satellites, enhancing)}
+    if output_path:
+        U.save_results(results, output_path)
+    return results

@@ -244,3 +244,35 @@ def analyze_cystic_vs_solid(t1_data, t2_data, flair_data, seg_data, tumor_masks,
     return {"classification": name, "cystic_volume_cm3": float(cystic_volume), "cystic_percentage": float(cystic_pct),
             "solid_volume_cm3": float(wt_volume - cystic_volume), "solid_percentage": float(100 - cystic_pct),
             "signal_characteristics": signal, "description": text}
+
+
+def analyze_morphology(input_folder, segmentation_path, output_path=None):
+    """File-level driver (reference :602-687): the four modalities and the label file in, the step-4 result dictionary
+    (and JSON file) out.  The narrative `text_summary` of the reference is report generation and is not produced."""
+    from . import utils as U
+
+    case_id = U.get_case_id(input_folder)
+    paths = U.get_mri_paths(input_folder, case_id)
+    t1, _, t1_header = U.load_nifti(paths["t1"])
+    volumes = {"t1": t1}
+    for mod in ("t1ce", "t2", "flair"):
+        volumes[mod] = U.load_nifti(paths[mod])[0]
+    seg, _, _ = U.load_nifti(segmentation_path)
+    voxel_info = U.get_voxel_dimensions(t1_header)
+    dims = [float(v) for v in voxel_info["dimensions_mm"]]
+    lv = U.LabelVolume(seg)
+    masks = U.get_tumor_masks(lv)
+    results = {
+        "case_id": case_id,
+        "step": "Step 4 - Tumor morphology and margins",
+        "voxel_info": voxel_info,
+        "shape_descriptors": calculate_shape_descriptors(lv, masks, dims),
+        "border_regularity": analyze_border_regularity(masks["wt"], dims),
+        "margin_definition": analyze_margin_definition(volumes["t1ce"], lv, masks, dims),
+        "necrosis_pattern": analyze_necrosis_pattern(lv, masks, np.array(dims)),
+        "cystic_solid_classification": analyze_cystic_vs_solid(volumes["t1"], volumes["t2"], volumes["flair"], lv, masks,
+                                                               dims),
+    }
+    if output_path:
+        U.save_results(results, output_path)
+    return results

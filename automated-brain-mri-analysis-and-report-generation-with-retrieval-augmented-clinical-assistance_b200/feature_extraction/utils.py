@@ -167,3 +167,95 @@ def get_normal_brain_stats(data, seg_mask):
     seg = seg_mask.vol if isinstance(seg_mask, LabelVolume) else V.as_label_volume(seg_mask)
     normal = get_brain_mask(d, 5) & (seg == 0)
     return get_intensity_stats(d, normal)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# File-level helpers of the step drivers (reference utils.py:15-24, 71-125, 218-247) on brainseg_b200.nifti_io
+# ------------------------------------------------------------------------------------------------------------------
+
+class NiftiHeaderView:
+    """The two header queries the reference makes on a nibabel header."""
+
+    def __init__(self, image):
+        self._image = image
+
+    def get_zooms(self):
+        return tuple(np.float32(v) for v in self._image.zooms)  # (x, y, z) mm, float32 scalars as nibabel returns them
+
+    def get_data_shape(self):
+        return tuple(reversed(self._image.data.shape))
+
+
+def load_nifti(filepath):
+    """(data, affine, header) like the reference's nibabel loader: data is float64 in nibabel's (x, y, z) axis order;
+    affine is None (nothing on this path reads it)."""
+    from .. import nifti_io
+
+    image = nifti_io.load(str(filepath))
+    return np.ascontiguousarray(image.get_fdata().transpose(2, 1, 0)), None, NiftiHeaderView(image)
+
+
+def get_case_id(input_folder):
+    """Case id from the T1 file name (BraTS-2021 `<id>_t1.nii.gz`, else BraTS-2025 `<id>-t1n.nii.gz`), else the
+    folder name."""
+    from pathlib import Path
+
+    folder = Path(input_folder)
+    for pattern, cut in (("*_t1.nii.gz", "_t1"), ("*-t1n.nii.gz", "-t1")):
+        hits = list(folder.glob(pattern))
+        if hits:
+            return hits[0].name.split(cut)[0]
+    return folder.name
+
+
+_MODALITY_SUFFIXES = (  # (probe, {modality: suffix})
+    ("_t1.nii.gz", {"t1": "_t1", "t1ce": "_t1ce", "t2": "_t2", "flair": "_flair"}),
+    ("-t1n.nii.gz", {"t1": "-t1n", "t1ce": "-t1c", "t2": "-t2w", "flair": "-t2f"}),
+)
+
+
+def get_mri_paths(input_folder, case_id=None):
+    from pathlib import Path
+
+    folder = Path(input_folder)
+    case_id = get_case_id(folder) if case_id is None else case_id
+    for probe, names in _MODALITY_SUFFIXES:
+        if (folder / f"{case_id}{probe}").exists():
+            return {mod: folder / f"{case_id}{suffix}.nii.gz" for mod, suffix in names.items()}
+    raise ValueError(f"Could not find MRI files in {folder}")
+
+
+def get_voxel_dimensions(header):
+    dims = header.get_zooms()[:3]
+    return {"dimensions_mm": list(dims), "volume_mm3": float(np.prod(dims)), "volume_cm3": float(np.prod(dims) / 1000)}
+
+
+class NumpyEncoder(__import__("json").JSONEncoder):
+    def default(self, obj):
+        if isinstance(obj, np.floating):
+            return float(obj)
+        if isinstance(obj, np.integer):
+            return int(obj)
+        if isinstance(obj, np.ndarray):
+            return obj.tolist()
+        if isinstance(obj, np.bool_):
+            return bool(obj)
+        return super().default(obj)
+
+
+def save_results(results, output_path):
+    import json
+    from pathlib import Path
+
+    target = Path(output_path)
+    target.parent.mkdir(parents=True, exist_ok=True)
+    with open(target, "w") as f:
+        json.dump(results, f, indent=2, cls=NumpyEncoder)
+    print(f"Results saved to: {target}")
+
+
+def load_results(json_path):
+    import json
+
+    with open(json_path) as f:
+        return json.load(f)

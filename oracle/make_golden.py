@@ -169,6 +169,55 @@ def voxelops_fixtures():
         json.dump(results, f, indent=1)
 
 
+def write_case_folder(folder, case_id, seg_xyz, mri_xyz, zooms=(0.9, 1.1, 1.25)):
+    """A BraTS-2021 style case folder from (x, y, z) arrays (nibabel's axis order), written with the package's own
+    NIfTI writer; returns the label file's path.  Shared with tests/test_gpu_drivers.py."""
+    from brainseg_b200 import nifti_io
+
+    os.makedirs(folder, exist_ok=True)
+    like = nifti_io.new_header(seg_xyz.shape[::-1], zooms)
+    for mod, vol in mri_xyz.items():
+        nifti_io.save(os.path.join(folder, f"{case_id}_{mod}.nii.gz"), np.ascontiguousarray(vol.transpose(2, 1, 0)), like)
+    seg_path = os.path.join(folder, f"{case_id}_seg.nii.gz")
+    nifti_io.save(seg_path, np.ascontiguousarray(seg_xyz.transpose(2, 1, 0)).astype(np.uint8),
+                  nifti_io.new_header(seg_xyz.shape[::-1], zooms, dtype=np.uint8))
+    return seg_path
+
+
+def driver_fixtures():
+    """The reference's file-level step drivers (step3_multiplicity.py:445-546, step4_morphology.py:602-687) on a case
+    folder built from the voxelops fixture volumes.  nibabel is absent: the reference modules' `load_nifti` is
+    replaced by a reader over the package's NIfTI parser that returns what nibabel would ((x, y, z) float64 data,
+    header.get_zooms()); everything after the load is the reference's own code.  `text_summary` (report text) is
+    dropped."""
+    import contextlib
+    import io
+    import tempfile
+
+    from brainseg_b200.feature_extraction import utils as BU
+
+    ns = R.load_reference()
+    vols = np.load(os.path.join(OUT, "voxelops.npz"))
+    out = {}
+    for seed in (0, 1):
+        with tempfile.TemporaryDirectory() as tmp:
+            case = f"BraTS2021_{seed:05d}"
+            folder = os.path.join(tmp, case)
+            mri = {k: vols[f"{k}{seed}"].astype(np.float32) for k in ("t1", "t1ce", "t2", "flair")}
+            zooms = (1.0, 1.0, 1.0) if seed == 0 else (0.9, 1.1, 1.25)  # BraTS spacing / an anisotropic header
+            seg_path = write_case_folder(folder, case, vols[f"seg{seed}"], mri, zooms)
+            for mod in (ns.step3, ns.step4):
+                mod.load_nifti = BU.load_nifti
+            with contextlib.redirect_stdout(io.StringIO()):
+                r3 = ns.step3.analyze_multiplicity(folder, seg_path)
+                r4 = ns.step4.analyze_morphology(folder, seg_path)
+            r3.pop("text_summary")
+            r4.pop("text_summary")
+            out[str(seed)] = jsonable({"step3": r3, "step4": r4})
+    with open(os.path.join(OUT, "step_drivers.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
 def sliding_window_facts():
     g = SW.get_gaussian((128, 128, 128), 1.0 / 8)
     facts = {
@@ -203,10 +252,13 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     if sys.argv[1:] == ["voxelops"]:
         voxelops_fixtures()
+    elif sys.argv[1:] == ["drivers"]:
+        driver_fixtures()
     else:
         unet_fixtures()
         postproc_fixtures()
         sliding_window_facts()
         voxelops_fixtures()
+        driver_fixtures()
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))
