@@ -65,6 +65,11 @@ class UNetEngine:
         self.step_info = []   # per step: name, algorithmic flops, plan geometry (diagnostics / bench breakdown)
         self.plans = []       # per step: the conv plan (bench.py times the dominant layer's launch alone)
         self.keep = []        # tensors the plans point at
+        # norm statistics of every IN / GN layer live in one arena, zeroed by ONE fill at the start of a forward
+        # (run()); a step called on its own (diagnostics) zeroes its slice itself
+        self._stats_arena = None
+        self._stats_used = 0
+        self._in_run = False
         self.launches_per_forward = 0
         self.flops = 0.0
         self.final_norm = None  # (scale_shift [batch][C][2], slope) when the last block's norm is left to the head
@@ -96,7 +101,7 @@ class UNetEngine:
                 self.device).float()
             act = L.BSG_ACT_LRELU
         elif isinstance(norm, (nn.InstanceNorm3d, nn.GroupNorm)):
-            stats = torch.zeros(self.batch, cout, 2, dtype=torch.float32, device=self.device)
+            stats = self._carve_stats(cout)
             act = L.BSG_ACT_NONE
         else:
             raise NotImplementedError(f"norm {type(norm).__name__}")
@@ -132,7 +137,8 @@ class UNetEngine:
 
         def run(stream=None, plan=plan, stats=stats, ss=ss):
             sp = L.stream_ptr(stream)
-            stats.zero_()
+            if not self._in_run:
+                stats.zero_()
             plan.run(stream)
             if self.sub_events is not None:  # diagnostics: split the step into conv | norm passes
                 ev = torch.cuda.Event(enable_timing=True)
@@ -144,7 +150,7 @@ class UNetEngine:
                                                  1, self.f16, sp))
 
         self.steps.append(run)
-        self.launches_per_forward += 3 if defer_apply else 4
+        self.launches_per_forward += 2 if defer_apply else 3  # conv, norm_finalize(, norm_apply): the library's own kernels
         if defer_apply:  # the consumer (head kernel / forward_logits) normalises on the fly
             self.final_norm = (ss, slope)
 
@@ -220,17 +226,36 @@ class UNetEngine:
             self.patch[0] * self.patch[1] * self.patch[2])
 
     # ------------------------------------------------------------------ execution
+    def _carve_stats(self, cout):
+        """(batch, cout, 2) fp32 slice of the statistics arena"""
+        if self._stats_arena is None:
+            self._stats_arena = torch.zeros(1 << 20, dtype=torch.float32, device=self.device)  # 4 MB: > 60 layers of 512 ch
+        n = self.batch * cout * 2
+        if self._stats_used + n > self._stats_arena.numel():
+            raise L.BsgError("norm statistics arena exhausted")
+        view = self._stats_arena[self._stats_used:self._stats_used + n].view(self.batch, cout, 2)
+        self._stats_used += (n + 63) // 64 * 64  # 256-byte aligned slices
+        return view
+
+    def _run_steps(self, stream):
+        self._in_run = True
+        try:
+            if self._stats_used:
+                self._stats_arena[:self._stats_used].zero_()
+            for step in self.steps:
+                step(stream)
+        finally:
+            self._in_run = False
+
     def run(self, stream=None):
         """All conv / norm launches of one forward over the resident input batch `self.x`."""
         if self.event_log is None:
-            for step in self.steps:
-                step(stream)
+            self._run_steps(stream)
             return
         s = stream if stream is not None else torch.cuda.current_stream()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(s)
-        for step in self.steps:
-            step(stream)
+        self._run_steps(stream)
         e1.record(s)
         self.event_log.append((e0, e1))
 
