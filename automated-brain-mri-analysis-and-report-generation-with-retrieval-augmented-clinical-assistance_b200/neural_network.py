@@ -77,17 +77,26 @@ class SegmentationNetwork(nn.Module):
             raise ValueError("mirror axes. duh")
         x = np.asarray(x) if not torch.is_tensor(x) else x
         assert len(x.shape) == 4, "data must have shape (c,x,y,z)"
-        if not use_sliding_window:
-            raise NotImplementedError("the reference always predicts with use_sliding_window=True")
-        assert patch_size is not None, "patch_size cannot be None for tiled prediction"
-        seg, probs = self.predict_3D_device(x, do_mirroring, mirror_axes, step_size, patch_size, regions_class_order,
-                                            use_gaussian)
+        if use_sliding_window:
+            assert patch_size is not None, "patch_size cannot be None for tiled prediction"
+            seg, probs = self.predict_3D_device(x, do_mirroring, mirror_axes, step_size, patch_size,
+                                                regions_class_order, use_gaussian)
+        else:
+            # upstream _internal_predict_3D_3Dconv: pad to >= patch_size (its `min_size`) and to a multiple of
+            # input_shape_must_be_divisible_by, ONE mirrored forward over the whole volume (no Gaussian), crop back —
+            # i.e. a single tile that is the padded volume itself
+            div = [int(d) for d in self.input_shape_must_be_divisible_by]
+            floor = [int(p) for p in patch_size] if patch_size is not None else [0, 0, 0]
+            whole = [max(s, f) for s, f in zip(x.shape[1:], floor)]
+            whole = [w if w % d == 0 else w + d - w % d for w, d in zip(whole, div)]
+            seg, probs = self.predict_3D_device(x, do_mirroring, mirror_axes, 1.0, whole, regions_class_order, False,
+                                                engine_batch=1)
         seg = seg.cpu().numpy()
         seg = seg.astype(np.float32) if regions_class_order is not None else seg.astype(np.int64)
         return seg, probs.cpu().numpy()
 
     def predict_3D_device(self, x, do_mirroring=True, mirror_axes=(0, 1, 2), step_size=0.5, patch_size=None,
-                          regions_class_order=None, use_gaussian=True, want_probs=True):
+                          regions_class_order=None, use_gaussian=True, want_probs=True, engine_batch=None):
         """predict_3D without the final device->host copies: returns (uint8 seg, fp32 probs) cuda tensors."""
         dev = torch.device("cuda", torch.cuda.current_device())
         vol = (torch.from_numpy(np.ascontiguousarray(x)) if not torch.is_tensor(x) else x).to(dev, torch.float32)
@@ -103,7 +112,7 @@ class SegmentationNetwork(nn.Module):
             vol = torch.nn.functional.pad(vol, (pads[2][0], pads[2][1], pads[1][0], pads[1][1], pads[0][0], pads[0][1]))
         vol = vol.contiguous()
         codes = sliding.mirror_codes_for(mirror_axes, do_mirroring)
-        pred = sliding.SlidingWindowPredictor(self.engines_for(patch), step_size, use_gaussian, codes,
+        pred = sliding.SlidingWindowPredictor(self.engines_for(patch, engine_batch), step_size, use_gaussian, codes,
                                               self._nonlin_name())
         acc = pred.accumulate(vol)
         seg, probs = pred.finalize([acc], tuple(vol.shape[1:]), regions_class_order, want_probs)

@@ -39,12 +39,16 @@ def get_gaussian(patch_size, sigma_scale=1.0 / 8):
     return g
 
 
-def pad_nd_image(image, new_shape, mode="constant", kwargs=None):
+def pad_nd_image(image, new_shape, mode="constant", kwargs=None, shape_must_be_divisible_by=None):
     """batchgenerators `pad_nd_image` restricted to what predict_3D uses: symmetric pad of the trailing dims up to
-    new_shape (floor on the low side), returns (padded, slicer)."""
+    new_shape (floor on the low side) and, when `shape_must_be_divisible_by` is given (the non-tiled path), further up
+    to the next multiple per axis; returns (padded, slicer)."""
     kwargs = kwargs or {"constant_values": 0}
     old = np.array(image.shape[-len(new_shape):])
     new = np.array([max(a, b) for a, b in zip(new_shape, old)])
+    if shape_must_be_divisible_by is not None:
+        div = np.array(shape_must_be_divisible_by)
+        new = np.array([n if n % d == 0 else n + d - n % d for n, d in zip(new, div)])
     diff = new - old
     below = diff // 2
     above = diff // 2 + diff % 2
@@ -121,6 +125,19 @@ def predict_3d_tiled(forward_fn, nonlin, x, num_classes, patch_size, do_mirrorin
     probs = agg / nb
     seg = decide(probs, regions_class_order)
     return seg, probs
+
+
+def predict_3d_full(forward_fn, nonlin, x, num_classes, min_size, divisible_by, do_mirroring=True,
+                    mirror_axes=(0, 1, 2), regions_class_order=None):
+    """nnU-Net v1 `_internal_predict_3D_3Dconv` (predict_3D with use_sliding_window=False; UPSTREAM, restated —
+    parity unpinned): pad to >= min_size and to a multiple of `input_shape_must_be_divisible_by`, ONE mirrored forward
+    over the whole padded volume, crop back, decide."""
+    assert x.ndim == 4
+    data, slicer = pad_nd_image(x, min_size, "constant", {"constant_values": 0}, divisible_by)
+    pred = mirror_and_predict(forward_fn, nonlin, torch.from_numpy(np.ascontiguousarray(data[None])), mirror_axes,
+                              do_mirroring, None, num_classes)[0].numpy()
+    probs = pred[(slice(None),) + slicer[1:]]
+    return decide(probs, regions_class_order), probs
 
 
 def decide(probs, regions_class_order):

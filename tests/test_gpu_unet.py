@@ -195,3 +195,24 @@ def test_case_pipeline_kaist_probability_ensemble():
         got = out["segmentation"].cpu().numpy()
         assert np.array_equal(got[decisive], ref[decisive])
         assert (4 in np.unique(got)) == (n_et >= thr) or abs(n_et - thr) < (~decisive).sum()
+
+
+@pytest.mark.parametrize("variant,shape,min_size", [("bn", (37, 45, 50), None), ("gn", (20, 33, 26), (32, 32, 32)),
+                                                    ("in", (40, 48, 56), (16, 16, 16))])
+def test_predict_3d_without_sliding_window(variant, shape, min_size):
+    """use_sliding_window=False (upstream _internal_predict_3D_3Dconv): the whole volume, padded to a multiple of
+    input_shape_must_be_divisible_by (and to >= patch_size when one is given), in ONE mirrored forward."""
+    net = build_dropin_unet(variant, base=16, num_pool=2, groups=4, seed=31)
+    fwd, _, _ = oracle_fns(net)
+    vol = torch.randn(4, *shape, generator=torch.Generator().manual_seed(6)).numpy()
+    div = [int(d) for d in net.input_shape_must_be_divisible_by]
+    seg_ref, probs_ref = SW.predict_3d_full(fwd, torch.sigmoid, vol, 3, min_size or (0, 0, 0), div, True, (0, 1, 2),
+                                            (1, 2, 3))
+    seg, probs = net.predict_3D(vol, True, (0, 1, 2), False, 0.5, min_size, (1, 2, 3), False, "constant",
+                                {"constant_values": 0}, False, False, True)
+    assert probs.shape == probs_ref.shape == (3,) + shape and seg.dtype == seg_ref.dtype
+    perr = np.abs(probs - probs_ref).max()
+    decisive = np.all(np.abs(probs_ref - 0.5) > PROB_TOL, axis=0)
+    print(f"whole-volume forward: prob max err {perr:.4g}, {decisive.mean() * 100:.1f}% decisive voxels")
+    assert perr < PROB_TOL
+    assert np.array_equal(seg[decisive], seg_ref[decisive])
