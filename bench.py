@@ -267,6 +267,8 @@ def run_ours(args):
                                 rank=rank if args.mode == "latency" else 0,
                                 world_size=world if args.mode == "latency" else 1, reduce_fn=reduce_fn)
     eng1, eng2 = pipe.predictors[0].engine, pipe.predictors[1].engine
+    kinds = sorted({"fp16" if e.f16 else "bf16" for e in (eng1, eng2)})
+    act_dtype = kinds[0] if len(kinds) == 1 else "+".join(kinds)  # 16-bit operands, fp32 accumulation in TMEM
     log(f"engines ready: {len(pipe.predictors[0].engines)} lane(s) x batch {eng1.batch}; "
         f"{eng1.launches_per_forward} + {eng2.launches_per_forward} launches per forward batch, "
         f"{eng1.flops_per_item / 1e9:.1f} + {eng2.flops_per_item / 1e9:.1f} GF per tile-mirror")
@@ -406,7 +408,7 @@ def run_ours(args):
         d2h = seg_host.numel() + 257 * 8 + 4 + 2 * 4096 * 88 + 2 * 8 * 120  # labels + hist + ncomp + stats + moments
         line = {"metric": METRIC, "value": cases / t_res, "unit": "cases/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True,
-                "scaling": "weak" if args.mode == "throughput" else "strong", "vs_baseline": None, "dtype": "bf16",
+                "scaling": "weak" if args.mode == "throughput" else "strong", "vs_baseline": None, "dtype": act_dtype,
                 "data": "synthetic", "config": workload_config(args),
                 "e2e": {"value": cases / t_e2e, "unit": "cases/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e / args.steps * 1e3,

@@ -216,3 +216,14 @@ def test_predict_3d_without_sliding_window(variant, shape, min_size):
     print(f"whole-volume forward: prob max err {perr:.4g}, {decisive.mean() * 100:.1f}% decisive voxels")
     assert perr < PROB_TOL
     assert np.array_equal(seg[decisive], seg_ref[decisive])
+
+
+def test_config1_full_case_brats_architecture():
+    """BASELINE configs[0] in full: the synthetic 4x155x240x240 case, ONE model of the BraTS-2021 shape (31.2 M
+    parameters), no mirroring, patch 128^3, step 0.5 (18 tiles), Gaussian weighting, regions export — against the fp32
+    oracle running the same 18 forwards on the host (about a minute of CPU time on the GPU box).  north_star's bars:
+    probabilities within 1e-2 absolute, label volume agreement >= 99.9 %."""
+    net = build_dropin_unet("bn", base=32, num_pool=5, seed=1)
+    vol = torch.randn(4, 155, 240, 240, generator=torch.Generator().manual_seed(0)).numpy()
+    perr, agree = _check_predict(net, vol, (128, 128, 128), (0, 1, 2), False, 0.5, (1, 2, 3), torch.sigmoid)
+    assert agree >= 0.999, f"label agreement {agree * 100:.4f}% < 99.9%"
