@@ -178,3 +178,114 @@ def test_network_config_is_inferred_from_the_checkpoint():
         sd = build_dropin_unet(**kw).state_dict()
         sd2 = NC.build_network(NC.infer_network_config(sd, name)).state_dict()
         assert list(sd) == list(sd2) and all(sd[k].shape == sd2[k].shape for k in sd)
+
+
+def test_run_full_pipeline_host_logic(tmp_path, capsys):
+    """Step 1 (BraTS-2025 -> BraTS-2021 file names, .nii compression) and the exit-code / marker contract of the
+    orchestrator (reference run_full_pipeline.py:89-144, :460-470, :714-732) — the parts that need no GPU."""
+    import gzip
+
+    from brainseg_b200 import run_full_pipeline as RP
+    from brainseg_b200.feature_extraction import utils as U
+
+    case = tmp_path / "BraTS-GLI-00003-000"
+    case.mkdir()
+    for suffix in ("t1n", "t1c", "t2w"):
+        (case / f"BraTS-GLI-00003-000-{suffix}.nii").write_bytes(b"raw-nifti-bytes")
+    (case / "BraTS-GLI-00003-000-t2f.nii.gz").write_bytes(gzip.compress(b"flair"))
+    (case / "notes.txt").write_text("ignored")
+    assert RP.rename_brats2025_files(case) == ("BraTS-GLI-00003-000", 4, 0)
+    names = sorted(p.name for p in case.iterdir())
+    assert names == ["BraTS-GLI-00003-000_flair.nii.gz", "BraTS-GLI-00003-000_t1.nii.gz",
+                     "BraTS-GLI-00003-000_t1ce.nii.gz", "BraTS-GLI-00003-000_t2.nii.gz", "notes.txt"]
+    assert gzip.decompress((case / "BraTS-GLI-00003-000_t1.nii.gz").read_bytes()) == b"raw-nifti-bytes"
+    assert RP.rename_brats2025_files(case) == ("BraTS-GLI-00003-000", 0, 4)  # second run: already converted
+    assert U.get_case_id(case) == "BraTS-GLI-00003-000"
+    assert sorted(U.get_mri_paths(case)) == ["flair", "t1", "t1ce", "t2"]
+    capsys.readouterr()
+
+    # missing ground truth: STAGE:error + ERROR: line, exit code 1; the segmentation stage is never announced
+    with pytest.raises(SystemExit) as stop:
+        RP.main([str(case), "--results-root", str(tmp_path / "results")])
+    out = capsys.readouterr().out
+    assert stop.value.code == 1
+    assert "STAGE:error" in out and "ERROR:Ground truth segmentation not found" in out and "STAGE:segmenting" not in out
+    # a folder that does not exist: exit code 1 without any stage marker (the reference checks before its try block)
+    with pytest.raises(SystemExit) as stop:
+        RP.main([str(tmp_path / "nowhere")])
+    out = capsys.readouterr().out
+    assert stop.value.code == 1 and "STAGE:" not in out and "Case folder not found" in out
+
+
+def test_step3_lesion_bookkeeping():
+    """calculate_inter_lesion_distances / detect_satellite_lesions / classify_distribution_pattern on hand-made
+    component lists (reference step3_multiplicity.py:155-205, :266-375)."""
+    from brainseg_b200.feature_extraction import step3_multiplicity as S3
+
+    def comp(i, x, vol=1.0, enh=True):
+        return {"id": i, "centroid_mm": {"x": float(x), "y": 0.0, "z": 0.0}, "volume_cm3": vol, "has_enhancement": enh}
+
+    one = [comp(1, 0)]
+    assert S3.calculate_inter_lesion_distances(one, (1, 1, 1)) == {"distances": [], "min_distance_mm": None,
+                                                                 "max_distance_mm": None, "mean_distance_mm": None}
+    assert S3.detect_satellite_lesions(one, one[0], (1, 1, 1))["description"] == "Single lesion, no satellites"
+    three = [comp(1, 0), comp(2, 15), comp(3, 50, enh=False)]
+    d = S3.calculate_inter_lesion_distances(three, (1, 1, 1))
+    assert [p["distance_mm"] for p in d["distances"]] == [15.0, 50.0, 35.0]
+    assert [p["relationship"] for p in d["distances"]] == ["Satellite/adjacent", "Distant/separate", "Regional spread"]
+    assert d["min_distance_mm"] == 15.0 and d["max_distance_mm"] == 50.0 and abs(d["mean_distance_mm"] - 100 / 3) < 1e-12
+    sat = S3.detect_satellite_lesions(three, three[0], (1, 1, 1))
+    assert sat["satellite_count"] == 1 and sat["satellites"][0]["component_id"] == 2 and sat["has_satellites"]
+    pattern = S3.classify_distribution_pattern({"num_components": 3}, d, sat, {"num_enhancing_foci": 5})
+    assert pattern["pattern"] == "Primary with satellites" and pattern["lesion_count"] == 3
+    assert pattern["enhancement_note"].startswith("Multiple enhancing foci")
+    far = [comp(1, 0), comp(2, 30), comp(3, 90)]
+    dfar = S3.calculate_inter_lesion_distances(far, (1, 1, 1))
+    nosat = S3.detect_satellite_lesions(far, far[0], (1, 1, 1))
+    assert S3.classify_distribution_pattern({"num_components": 3}, dfar, nosat, {"num_enhancing_foci": 0})["pattern"] == \
+        "Distant multifocal"
+    near = [comp(1, 0), comp(2, 25), comp(3, 39)]
+    dnear = S3.calculate_inter_lesion_distances(near, (1, 1, 1))
+    assert S3.classify_distribution_pattern({"num_components": 3}, dnear, S3.detect_satellite_lesions(near, near[0], (1, 1, 1)),
+                                            {"num_enhancing_foci": 3})["pattern"] == "Regional multifocal"
+    assert S3.classify_distribution_pattern({"num_components": 5}, dnear, nosat, {"num_enhancing_foci": 1})["pattern"] == \
+        "Diffuse/scattered"
+    assert S3.classify_distribution_pattern({"num_components": 0}, None, None, None)["pattern"] == "No tumor"
+
+
+@pytest.mark.parametrize("seed", ["0", "1"])
+def test_step3_bookkeeping_matches_reference_drivers(seed):
+    """The same functions fed with the reference's own component lists reproduce the reference's distance, satellite and
+    distribution sections (tests/golden/step_drivers.json, produced by the reference's analyze_multiplicity)."""
+    import json
+    import os
+
+    from brainseg_b200.feature_extraction import step3_multiplicity as S3
+    from tests.conftest import GOLDEN
+
+    def approx_equal_tree(a, b, path):
+        """exact for structure / strings / ints; floats to float32 resolution: the reference's centroid_mm values are
+        np.float32 under nibabel + NumPy >= 2, so its distances are float32 arithmetic"""
+        if isinstance(a, dict):
+            assert set(a) == set(b), path
+            for k in a:
+                approx_equal_tree(a[k], b[k], f"{path}/{k}")
+        elif isinstance(a, list):
+            assert len(a) == len(b), path
+            for i, (x, y) in enumerate(zip(a, b)):
+                approx_equal_tree(x, y, f"{path}[{i}]")
+        elif isinstance(a, float) and isinstance(b, (int, float)) and not isinstance(b, bool):
+            assert abs(a - b) <= 2e-6 * max(abs(a), abs(b)), f"{path}: {a} != {b}"
+        else:
+            assert a == b, f"{path}: {a!r} != {b!r}"
+
+    with open(os.path.join(GOLDEN, "step_drivers.json")) as f:
+        ref = json.load(f)[seed]["step3"]
+    comps = ref["component_analysis"]
+    dims = ref["voxel_info"]["dimensions_mm"]
+    dist = S3.calculate_inter_lesion_distances(comps["components"], dims)
+    approx_equal_tree(dist, ref["distance_analysis"], "distance_analysis")
+    sat = S3.detect_satellite_lesions(comps["components"], comps["components"][0], dims)
+    approx_equal_tree(sat, ref["satellite_analysis"], "satellite_analysis")
+    approx_equal_tree(S3.classify_distribution_pattern(comps, dist, sat, ref["enhancing_analysis"]),
+                      ref["distribution_pattern"], "distribution_pattern")
