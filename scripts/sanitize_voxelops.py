@@ -3,6 +3,9 @@ odd-shaped volumes (shapes that are not multiples of any tile / vector width), r
 
   python scripts/sanitize_voxelops.py                                   # plain run first
   compute-sanitizer --tool memcheck python scripts/sanitize_voxelops.py
+
+Round 1: the plain run passes on a B200; compute-sanitizer is closed on this GPU pool (runs under it left GPUs needing
+a reset), so memory safety rests on these odd-shape comparisons and the parity tests.
 """
 import os
 import sys
