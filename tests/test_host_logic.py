@@ -289,3 +289,31 @@ def test_step3_bookkeeping_matches_reference_drivers(seed):
     approx_equal_tree(sat, ref["satellite_analysis"], "satellite_analysis")
     approx_equal_tree(S3.classify_distribution_pattern(comps, dist, sat, ref["enhancing_analysis"]),
                       ref["distribution_pattern"], "distribution_pattern")
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference`: ONE JSON line with the contract's keys, produced on the host cores only; ranks other
+    than 0 exit 0 without output (torchrun launches the arm on every rank)."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    quiet = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "0"], cwd=root,
+                           env=dict(env, RANK="1", WORLD_SIZE="2"), capture_output=True, text=True, timeout=120)
+    assert quiet.returncode == 0 and quiet.stdout.strip() == ""
+    run = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "0"], cwd=root,
+                         env=env, capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0, run.stderr[-2000:]
+    lines = [l for l in run.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["unit"] == "cases/s" and line["higher_is_better"] is True
+    assert line["metric"].startswith("cases/sec") and line["n_gpus"] == 1 and line["vs_baseline"] is None
+    assert line["value"] > 0 and abs(line["ms_per_step"] * line["value"] - 1e3) < 1e-6 * 1e3
+    assert line["e2e"] == {"value": line["value"], "unit": "cases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    base = line["cpu_baseline"]
+    assert base["kind"] == "port" and base["cores"] >= 1 and base["value"] == line["value"] and "sample" in base
+    assert "workload" in line["config"] and "model" not in line["config"]
