@@ -304,6 +304,7 @@ __global__ void __launch_bounds__(brick_threads(CC), 1) conv_brick_kernel(const 
         const int iw = row & 7, ih = row >> 3;
         EpiParams epi;
         epi.sbias = sbias;
+        epi.has_bias = a.bias != nullptr;
         epi.stats = a.stats;
         epi.cout = a.cout;
         epi.No = a.tn;

@@ -17,6 +17,7 @@ __device__ __forceinline__ void st_global_v8(void* p, uint32_t a0, uint32_t a1, 
 
 struct EpiParams {
     const float* sbias;  // shared memory, [cout_pad]
+    int has_bias;        // 0: the layer has no bias (nnU-Net's transposed convs): skip the loads and adds
     float* stats;        // [No][cout][2] running (sum, sum of squares) of the pre-activation output, or null
     int cout;            // valid output channels
     int No;              // batch extent
@@ -72,7 +73,7 @@ template <bool THREAD_ACC>
 __device__ __forceinline__ void epilogue_32cols(const uint32_t (&v)[32], const EpiParams& e, int co, bool valid, int lane,
                                                 StatAcc& acc, __nv_bfloat16* orow, float (&t1)[32], float (&t2)[32]) {
     float f[32];
-    {
+    if (e.has_bias) {
         // bias: 8 x ld.shared.v4 (warp-wide broadcast); `e.sbias` is a generic pointer, which would compile to 32
         // generic loads per chunk
         const uint32_t baddr = static_cast<uint32_t>(__cvta_generic_to_shared(e.sbias + co));
@@ -87,6 +88,9 @@ __device__ __forceinline__ void epilogue_32cols(const uint32_t (&v)[32], const E
             f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b2;
             f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b3;
         }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
     }
     if (e.stats != nullptr) {
         if (THREAD_ACC) {

@@ -273,6 +273,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int in = r;
         EpiParams epi;
         epi.sbias = sbias;
+        epi.has_bias = a.bias != nullptr;
         epi.stats = a.stats;
         epi.cout = a.cout;
         epi.No = a.No;
@@ -310,21 +311,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + acc * static_cast<uint32_t>(a.ntile) + (static_cast<uint32_t>(q * 32) << 16);
+            // This warp's chunks: half, half + 2, ...  ONE copy of the chunk body in the instruction stream (a runtime
+            // loop): unrolled over the 8 chunk positions it was ~110 KB of SASS per warp flavour and the epilogue
+            // warps spent a quarter of their time waiting for instruction fetches (ncu: stall_no_inst, transposed conv).
+            // The running statistics stay in registers: the chunk's result is added to sacc[j] by a predicated,
+            // unrolled select instead of a dynamic index.  (Issuing the next chunk's tcgen05.ld ahead of this chunk's
+            // conversion + stores was tried on top: slower, 0.613 -> 0.682 ms on the 64->64 transposed conv.)
+            const int nchunk = a.ntile >> 5;
             int par = 0, cpar = 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int cb = j * 32;
-                if (cb >= a.ntile) break;
-                if (a.out_mul == 2) {  // advance the (parity, channel) cursor for every chunk, also the skipped ones
-                    if (j == 0) {
-                        par = q0 / a.cout_pad;
-                        cpar = q0 - par * a.cout_pad;
-                    } else if ((cpar += 32) >= a.cout_pad) {
-                        cpar = 0;
-                        ++par;
-                    }
+            if (a.out_mul == 2) {  // (parity, channel) of this warp's first chunk
+                par = q0 / a.cout_pad;
+                cpar = q0 - par * a.cout_pad;
+                if (half && (cpar += 32) >= a.cout_pad) {
+                    cpar = 0;
+                    ++par;
                 }
-                if ((j & 1) != half) continue;
+            }
+#pragma unroll 1
+            for (int j = half; j < nchunk; j += 2) {
+                const int cb = j * 32;
                 uint32_t v[32];
                 tmem_ld_32x32(t_addr + cb, v);
                 tmem_ld_wait();
@@ -332,13 +337,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 if (a.out_mul == 2) {
                     // transposed conv: GEMM columns enumerate (parity (pd, ph, pw), channel); an N tile may span
                     // several parities, so the output voxel is re-derived per 32-column chunk (no division: the
-                    // parity / channel pair of the tile's first column is advanced chunk by chunk)
+                    // parity / channel pair is advanced chunk by chunk)
                     co = cpar;
                     orow = obase + static_cast<long long>(2 * d + ((par >> 2) & 1)) * a.os_d +
                            static_cast<long long>(2 * h + ((par >> 1) & 1)) * a.os_h +
                            static_cast<long long>(2 * w + (par & 1)) * a.os_w;
+#pragma unroll
+                    for (int step = 0; step < 2; ++step)  // on to this warp's next chunk: two positions further
+                        if ((cpar += 32) >= a.cout_pad) {
+                            cpar = 0;
+                            ++par;
+                        }
                 }
-                epilogue_32cols<false>(v, epi, co, valid, lane, sacc[j], orow, unused1, unused2);
+                StatAcc chunk_stats;
+                chunk_stats.s1 = chunk_stats.s2 = 0.f;
+                epilogue_32cols<false>(v, epi, co, valid, lane, chunk_stats, orow, unused1, unused2);
+                if (a.stats != nullptr) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (k == j) {
+                            sacc[k].s1 += chunk_stats.s1;
+                            sacc[k].s2 += chunk_stats.s2;
+                        }
+                }
             }
             tc_fence_before();
             __syncwarp();
