@@ -282,25 +282,45 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
     a.tmem_cols = 32;
     while (a.tmem_cols < static_cast<uint32_t>(2 * a.ntile)) a.tmem_cols *= 2;
 
+    // pair mode: 2-CTA clusters share every weight stage (each CTA fetches half of the N rows and multicasts them), which
+    // halves the L2 -> SM weight traffic of the layers that re-read their weights once per 128-voxel tile
+    a.pair = 0;
+    {
+        const long long mtiles = static_cast<long long>(a.tw) * a.th * a.td * a.tn;
+        // measured (gpurun_out/bringup16.log): +3 % on the stride-1 layers with N >= 128, nothing on the stride-2 layers
+        // (they are bound by the per-stage issue overhead of their 1-tap stages, not by weight traffic)
+        const bool wanted = d->pair == 1 || (d->pair != 0 && a.ntile >= 128 && stride == 1);
+        if (wanted && d->kind != BSG_CONVT_K2S2 && a.ntile % 16 == 0 && mtiles % 2 == 0 &&
+            (d->pair == 1 || mtiles * a.n_ntiles >= 2ll * sm_count_cached()))
+            a.pair = 1;
+    }
     // kh halo reuse: needs the canonical 8 x 16 x 1 x 1 box, stride 1, 27 taps and >= 3 pipeline stages
     const uint32_t budget = 227 * 1024 - 4096 - 6144;  // barriers + bias + alignment slack + room for co-resident CTAs
-    auto stage_bytes = [&](int khs, uint32_t* ab, uint32_t* bb) {
+    auto stage_bytes = [&](int khs, int taps3, uint32_t* ab, uint32_t* bb) {
         const uint32_t rows = khs ? static_cast<uint32_t>((a.bh + 2) * 8) : 128u;
-        *ab = round_up(rows * a.cc * 2, 1024);
-        *bb = round_up(static_cast<uint32_t>(a.ntile) * a.cc * 2 * (khs ? 3 : 1), 1024);
+        *ab = round_up(rows * a.cc * 2, 1024) * (taps3 ? 3 : 1);
+        *bb = round_up(static_cast<uint32_t>(a.ntile) * a.cc * 2 * ((khs || taps3) ? 3 : 1), 1024);
         return *ab + *bb;
     };
     int khs = 0;
     if (a.ntaps == 27 && stride == 1 && a.bw == 8 && a.bd == 1 && a.bn == 1 && d->use_khshift != 0) {
         uint32_t ab, bb;
-        const uint32_t sb = stage_bytes(1, &ab, &bb);
+        const uint32_t sb = stage_bytes(1, 0, &ab, &bb);
         if (budget / sb >= 3 || d->use_khshift == 1) khs = 1;
         if (budget / sb < 2) khs = 0;
     }
     a.khshift = khs;
-    const uint32_t sb = stage_bytes(khs, &a.a_stage_bytes, &a.b_stage_bytes);
-    a.stage_tx_bytes = (khs ? static_cast<uint32_t>((a.bh + 2) * 8) : 128u) * a.cc * 2 +
-                       static_cast<uint32_t>(a.ntile) * a.cc * 2 * (khs ? 3 : 1);
+    // three kh taps per stage as three separate boxes (any box shape, either stride) where the haloed box is not
+    // available: a third of the pipeline steps.  Only with >= 3 stages in flight, and never in pair mode.
+    int taps3 = 0;
+    if (!khs && !a.pair && a.ntaps == 27 && d->use_khshift != 0) {
+        uint32_t ab, bb;
+        if (budget / stage_bytes(0, 1, &ab, &bb) >= 3) taps3 = 1;
+    }
+    a.taps3 = taps3;
+    const uint32_t sb = stage_bytes(khs, taps3, &a.a_stage_bytes, &a.b_stage_bytes);
+    a.stage_tx_bytes = (khs ? static_cast<uint32_t>((a.bh + 2) * 8) : 128u) * a.cc * 2 * (taps3 ? 3 : 1) +
+                       static_cast<uint32_t>(a.ntile) * a.cc * 2 * ((khs || taps3) ? 3 : 1);
     a.nstages = static_cast<int>(budget / sb);
     if (a.nstages > 12) a.nstages = 12;
     if (a.nstages < 2) {
@@ -339,20 +359,8 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
         const uint64_t rows = static_cast<uint64_t>(a.cout_pad) * (a.out_mul == 2 ? 8 : 1);
         uint64_t dims[3] = {static_cast<uint64_t>(d->cin), rows, static_cast<uint64_t>(a.ntaps)};
         uint64_t str[2] = {static_cast<uint64_t>(d->cin) * 2, static_cast<uint64_t>(d->cin) * 2 * rows};
-        uint32_t box[3] = {static_cast<uint32_t>(a.cc), static_cast<uint32_t>(a.ntile), khs ? 3u : 1u};
+        uint32_t box[3] = {static_cast<uint32_t>(a.cc), static_cast<uint32_t>(a.ntile), (khs || taps3) ? 3u : 1u};
         rc = encode_map(&a.mapW, d->weights, 3, dims, str, box, a.cc);
-    }
-    // pair mode: 2-CTA clusters share every weight stage (each CTA fetches half of the N rows and multicasts them), which
-    // halves the L2 -> SM weight traffic of the layers that re-read their weights once per 128-voxel tile
-    a.pair = 0;
-    {
-        const long long mtiles = static_cast<long long>(a.tw) * a.th * a.td * a.tn;
-        // measured (gpurun_out/bringup16.log): +3 % on the stride-1 layers with N >= 128, nothing on the stride-2 layers
-        // (they are bound by the per-stage issue overhead of their 1-tap stages, not by weight traffic)
-        const bool wanted = d->pair == 1 || (d->pair != 0 && a.ntile >= 128 && stride == 1);
-        if (wanted && d->kind != BSG_CONVT_K2S2 && a.ntile % 16 == 0 && mtiles % 2 == 0 &&
-            (d->pair == 1 || mtiles * a.n_ntiles >= 2ll * sm_count_cached()))
-            a.pair = 1;
     }
     if (rc == BSG_OK && a.pair) {
         const uint64_t rows = static_cast<uint64_t>(a.cout_pad);
@@ -434,7 +442,7 @@ int bsg_conv_plan_info(const bsg_conv_plan* plan, bsg_conv_info* info) {
     info->n_ntiles = a.n_ntiles;
     info->cc = a.cc;
     info->nstages = a.nstages;
-    info->khshift = a.khshift + (a.pair ? 100 : 0);  /* +100: 2-CTA pair mode (multicast weight stages) */
+    info->khshift = a.khshift + (a.taps3 ? 3 : 0) + (a.pair ? 100 : 0);  /* 1: kh halo reuse, 3: three kh taps per stage, +100: 2-CTA pair mode */
     info->grid = plan->grid;
     info->smem_bytes = plan->smem_bytes;
     info->flops = plan->flops;

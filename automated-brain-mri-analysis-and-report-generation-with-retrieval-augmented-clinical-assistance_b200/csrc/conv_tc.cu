@@ -47,7 +47,10 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvArgs& a, int tile) {
 // unrolled so that the parity view and the coordinate offsets of every tap are compile-time constants — ncu showed the
 // generic producer thread spending ~105 dependent instructions = ~470 cycles per one-tap stage, 2..4x the stage's
 // MMA time).
-constexpr int kModeGeneric = 0, kModeKhs = 1, kModeS2 = 2, kModeS1 = 3;
+// kModeS1x3 / kModeS2x3: as kModeS1 / kModeS2 with the three kh taps of a (kd, kw) in ONE stage (three activation boxes,
+// one 3-tap weight box): the layers whose one-tap stages are bound by the per-stage round trip rather than by MMA time
+// (stride-2 32->64, the <= 8^3 levels) run a third of the stages.
+constexpr int kModeGeneric = 0, kModeKhs = 1, kModeS2 = 2, kModeS1 = 3, kModeS2x3 = 4, kModeS1x3 = 5;
 template <int CC, int MODE>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvArgs a) {
     constexpr bool KHS = MODE == kModeKhs;
@@ -102,9 +105,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     auto tile_of = [&](int item) {
         return a.pair ? (2 * (item / a.n_ntiles) + static_cast<int>(crank)) * a.n_ntiles + item % a.n_ntiles : item;
     };
-    const int ntg = KHS ? 9 : a.ntaps;  // pipeline steps per chunk: (kd,kw) pairs or single taps
+    constexpr bool X3 = MODE == kModeS1x3 || MODE == kModeS2x3;
+    const int ntg = (KHS || X3) ? 9 : a.ntaps;  // pipeline steps per chunk: (kd,kw) pairs or single taps
     const int ksteps = ntg * a.nchunks;
-    constexpr int NKH = KHS ? 3 : 1;
+    constexpr int NKH = (KHS || X3) ? 3 : 1;
     constexpr uint32_t kRowBytes = CC * 2u;
     constexpr uint32_t kSbo = 8u * kRowBytes;
     const int nstages = a.nstages;
@@ -114,7 +118,37 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            if constexpr (MODE == kModeS2 || MODE == kModeS1) {
+            if constexpr (X3) {
+                const uint32_t a_bytes = a.a_stage_bytes, a_tap_bytes = a.a_stage_bytes / 3, tx_bytes = a.stage_tx_bytes;
+                const int nchunks = a.nchunks;
+                for (int item = item0; item < nitems; item += item_step) {
+                    const TileCoord t = decode_tile(a, tile_of(item));
+                    const int nrow0 = t.nt * a.ntile;
+#pragma unroll
+                    for (int tg = 0; tg < 9; ++tg) {  // (kd, kw); the stage's taps are kh = 0, 1, 2
+                        const int kd = tg / 3, kw = tg % 3;
+                        constexpr bool S2 = MODE == kModeS2x3;
+                        const int cw = S2 ? t.w0 - (kw == 0) : t.w0 + kw - 1;
+                        const int cd = S2 ? t.d0 - (kd == 0) : t.d0 + kd - 1;
+                        for (int c = 0; c < nchunks; ++c) {
+                            mbar_wait(&empty_bar[stage], phase ^ 1u);
+                            uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+                            mbar_expect_tx(&full_bar[stage], tx_bytes);
+#pragma unroll
+                            for (int kh = 0; kh < 3; ++kh) {
+                                const int mi = S2 ? ((kw + 1) & 1) | (((kh + 1) & 1) << 1) | (((kd + 1) & 1) << 2) : 0;
+                                const int ch = S2 ? t.h0 - (kh == 0) : t.h0 + kh - 1;
+                                tma_load_5d(sa + kh * a_tap_bytes, &a.mapA[mi], &full_bar[stage], c * CC, cw, ch, cd, t.n0);
+                            }
+                            tma_load_3d(sa + a_bytes, &a.mapW, &full_bar[stage], c * CC, nrow0, tg * 3);
+                            if (++stage == nstages) {
+                                stage = 0;
+                                phase ^= 1u;
+                            }
+                        }
+                    }
+                }
+            } else if constexpr (MODE == kModeS2 || MODE == kModeS1) {
                 const uint32_t a_bytes = a.a_stage_bytes, tx_bytes = a.stage_tx_bytes;
                 const int nchunks = a.nchunks;
                 for (int item = item0; item < nitems; item += item_step) {
@@ -217,6 +251,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const uint32_t b_tap16 = (static_cast<uint32_t>(a.ntile) * kRowBytes) >> 4;
             const uint32_t smem0_16 = static_cast<uint32_t>(desc_base) + (smem_u32(smem) >> 4);  // LBO field + address
             const uint32_t stage16 = stage_bytes >> 4, a16 = a.a_stage_bytes >> 4;
+            // distance between the A operands of consecutive kh taps inside a stage: one row group of the haloed box
+            // (KHS) or one whole 128-row box (three boxes per stage)
+            const uint32_t a_kh16 = X3 ? (a.a_stage_bytes / 3) >> 4 : kSbo >> 4;
             int stage = 0;
             uint32_t phase = 0;
             uint32_t tcount = 0;
@@ -238,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     for (int kh = 0; kh < NKH; ++kh) {
 #pragma unroll
                         for (int k = 0; k < CC / 16; ++k) {
-                            const uint32_t ad = sa16 + ((kh * kSbo + k * 32) >> 4);
+                            const uint32_t ad = sa16 + kh * a_kh16 + ((k * 32) >> 4);
                             const uint32_t bd = sb16 + kh * b_tap16 + ((k * 32) >> 4);
                             umma_bf16_lo(d_tmem, ad, bd, desc_hi, idesc, (kh | k) != 0 ? 1u : (ks != 0 ? 1u : 0u));
                             // probe the next stage's barrier behind the first MMA: its latency overlaps queued work
@@ -420,6 +457,16 @@ cudaError_t launch_conv_tc(const ConvArgs& a, int grid, size_t smem_bytes, cudaS
         if (a.cc == 64) return launch_variant<64, kModeKhs>(a, grid, smem_bytes, stream);
         if (a.cc == 32) return launch_variant<32, kModeKhs>(a, grid, smem_bytes, stream);
         return launch_variant<16, kModeKhs>(a, grid, smem_bytes, stream);
+    }
+    if (a.taps3 && a.ntaps == 27 && !a.pair) {
+        if (a.stride == 2) {
+            if (a.cc == 64) return launch_variant<64, kModeS2x3>(a, grid, smem_bytes, stream);
+            if (a.cc == 32) return launch_variant<32, kModeS2x3>(a, grid, smem_bytes, stream);
+            return launch_variant<16, kModeS2x3>(a, grid, smem_bytes, stream);
+        }
+        if (a.cc == 64) return launch_variant<64, kModeS1x3>(a, grid, smem_bytes, stream);
+        if (a.cc == 32) return launch_variant<32, kModeS1x3>(a, grid, smem_bytes, stream);
+        return launch_variant<16, kModeS1x3>(a, grid, smem_bytes, stream);
     }
     if (a.stride == 2 && a.ntaps == 27 && !a.pair) {
         if (a.cc == 64) return launch_variant<64, kModeS2>(a, grid, smem_bytes, stream);

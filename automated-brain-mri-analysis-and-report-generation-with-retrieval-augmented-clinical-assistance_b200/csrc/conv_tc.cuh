@@ -23,6 +23,8 @@ struct ConvArgs {
     int ntaps;            // 27 or 1
     int stride;           // 1 or 2
     int khshift;          // 1: an A stage holds bh+2 rows of h (box (cc, 8, bh+2, 1, 1)) and serves 3 kh taps
+    int taps3;            // 1: a stage holds the three kh taps of one (kd, kw) as three separate activation boxes and one
+                          //    3-tap weight box (any box shape, stride 1 or 2): 3x fewer, larger pipeline steps
     int nstages;
     uint32_t a_stage_bytes, b_stage_bytes;  // smem footprint of one stage, both multiples of 1024
     uint32_t stage_tx_bytes;                // bytes the two TMA boxes of a stage actually deliver
