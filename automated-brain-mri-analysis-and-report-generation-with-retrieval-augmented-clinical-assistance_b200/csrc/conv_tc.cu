@@ -168,7 +168,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                             uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
                             mbar_expect_tx(&full_bar[stage], tx_bytes);
                             tma_load_5d(sa, &a.mapA[mi], &full_bar[stage], c * CC, cw, ch, cd, t.n0);
-                            tma_load_3d(sa + a_bytes, &a.mapW, &full_bar[stage], c * CC, nrow0, tap);
+                            if (a.pair) {  // my half of the weight rows, to both CTAs of the pair
+                                const int half = a.ntile >> 1, r0 = static_cast<int>(crank) * half;
+                                tma_load_3d_mc(sa + a_bytes + r0 * kRowBytes, &a.mapWh, &full_bar[stage], c * CC, nrow0 + r0,
+                                               tap, static_cast<uint16_t>(3));
+                            } else {
+                                tma_load_3d(sa + a_bytes, &a.mapW, &full_bar[stage], c * CC, nrow0, tap);
+                            }
                             if (++stage == nstages) {
                                 stage = 0;
                                 phase ^= 1u;
@@ -468,12 +474,12 @@ cudaError_t launch_conv_tc(const ConvArgs& a, int grid, size_t smem_bytes, cudaS
         if (a.cc == 32) return launch_variant<32, kModeS1x3>(a, grid, smem_bytes, stream);
         return launch_variant<16, kModeS1x3>(a, grid, smem_bytes, stream);
     }
-    if (a.stride == 2 && a.ntaps == 27 && !a.pair) {
+    if (a.stride == 2 && a.ntaps == 27) {
         if (a.cc == 64) return launch_variant<64, kModeS2>(a, grid, smem_bytes, stream);
         if (a.cc == 32) return launch_variant<32, kModeS2>(a, grid, smem_bytes, stream);
         return launch_variant<16, kModeS2>(a, grid, smem_bytes, stream);
     }
-    if (a.stride == 1 && a.ntaps == 27 && !a.pair) {
+    if (a.stride == 1 && a.ntaps == 27) {
         if (a.cc == 64) return launch_variant<64, kModeS1>(a, grid, smem_bytes, stream);
         if (a.cc == 32) return launch_variant<32, kModeS1>(a, grid, smem_bytes, stream);
         return launch_variant<16, kModeS1>(a, grid, smem_bytes, stream);
