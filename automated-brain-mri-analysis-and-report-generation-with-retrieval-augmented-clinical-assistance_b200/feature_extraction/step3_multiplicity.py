@@ -233,3 +233,20 @@ def analyze_multiplicity(input_folder, segmentation_path, output_path=None):
     if output_path:
         U.save_results(results, output_path)
     return results
+
+
+def main(argv=None):
+    """`python -m brainseg_b200.feature_extraction.step3_multiplicity --input DIR --segmentation FILE [--output JSON]`
+    (the reference script's command line, :549-562)."""
+    import argparse
+
+    cli = argparse.ArgumentParser(description="Step 3: Analyze lesion multiplicity and distribution")
+    cli.add_argument("--input", required=True, help="Input folder containing MRI sequences")
+    cli.add_argument("--segmentation", required=True, help="Path to segmentation mask (NIfTI)")
+    cli.add_argument("--output", default=None, help="Output path for JSON results")
+    args = cli.parse_args(argv)
+    return analyze_multiplicity(args.input, args.segmentation, args.output)
+
+
+if __name__ == "__main__":
+    main()

@@ -276,3 +276,20 @@ def analyze_morphology(input_folder, segmentation_path, output_path=None):
     if output_path:
         U.save_results(results, output_path)
     return results
+
+
+def main(argv=None):
+    """`python -m brainseg_b200.feature_extraction.step4_morphology --input DIR --segmentation FILE [--output JSON]`
+    (the reference script's command line, :690-703)."""
+    import argparse
+
+    cli = argparse.ArgumentParser(description="Step 4: Analyze tumor morphology and margins")
+    cli.add_argument("--input", required=True, help="Input folder containing MRI sequences")
+    cli.add_argument("--segmentation", required=True, help="Path to segmentation mask (NIfTI)")
+    cli.add_argument("--output", default=None, help="Output path for JSON results")
+    args = cli.parse_args(argv)
+    return analyze_morphology(args.input, args.segmentation, args.output)
+
+
+if __name__ == "__main__":
+    main()
