@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbrainseg_b200.so")
+# the library is built next to the import shim (brainseg_b200/), i.e. under a short in-tree path (see build.py)
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "brainseg_b200", "libbrainseg_b200.so")
 
 BSG_CONV_K3, BSG_CONVT_K2S2, BSG_CONV_K1 = 0, 1, 2
 BSG_ACT_NONE, BSG_ACT_LRELU = 0, 1
@@ -25,6 +26,7 @@ class ConvDesc(C.Structure):
         ("weights", C.c_void_p), ("bias", C.c_void_p),
         ("act", C.c_int), ("slope", C.c_float), ("stats", C.c_void_p), ("out_f16", C.c_int),
         ("use_khshift", C.c_int), ("max_ctas", C.c_int), ("in_f16", C.c_int), ("algo", C.c_int), ("pair", C.c_int),
+        ("overflow", C.c_void_p),
     ]
 
 
@@ -62,6 +64,11 @@ def _declare(lib):
     lib.bsg_ccl26_workspace_bytes.argtypes = [i, i, i]
     lib.bsg_select_workspace_bytes.restype = C.c_size_t
     lib.bsg_select_workspace_bytes.argtypes = []
+    lib.bsg_conv_desc_size.restype = C.c_size_t
+    lib.bsg_conv_desc_size.argtypes = []
+    if lib.bsg_conv_desc_size() != C.sizeof(ConvDesc):
+        raise BsgError(f"bsg_conv_desc layout mismatch: library {lib.bsg_conv_desc_size()} bytes, binding "
+                       f"{C.sizeof(ConvDesc)} (stale libbrainseg_b200.so? rebuild with __graft_entry__.build())")
 
 
 _vp, _i, _sz, _u32, _f, _d = C.c_void_p, C.c_int, C.c_size_t, C.c_uint32, C.c_float, C.c_double
@@ -92,6 +99,12 @@ _EXTRA_SIGS = {
     "bsg_head_tta_accumulate": [_vp, _i, _i, _i, _i, _i, _i, C.POINTER(_i), _i, _f, C.POINTER(_f), C.POINTER(_f), _i, _i,
                                 _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _f, _vp],
     "bsg_finalize": [C.POINTER(_vp), _i, _vp, _i, _sz, _i, C.POINTER(_i), _vp, _vp, _vp],
+    "bsg_finalize_peer": [_vp, _i, _i, _vp, _i, _sz, _sz, _sz, _i, C.POINTER(_i), _vp, _i, _vp],
+    "bsg_enable_peer_access": [_i],
+    "bsg_nccl_unique_id": [_vp],
+    "bsg_nccl_comm_create": [_vp, _i, _i, C.POINTER(_vp)],
+    "bsg_nccl_reduce_accumulator": [_vp, _vp, _sz, _i, _vp],
+    "bsg_nccl_comm_destroy": [_vp],
 }
 
 

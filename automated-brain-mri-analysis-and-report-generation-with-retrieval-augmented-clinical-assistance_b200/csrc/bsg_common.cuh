@@ -23,15 +23,31 @@ int set_error(int code, const char* fmt, ...);
     } while (0)
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+// SM count of the CURRENT device (one process may drive several: engines are keyed by device on the Python side)
 inline int sm_count_cached() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
+    static int n[kMaxDevices] = {0};
+    const int dev = current_device();
+    if (n[dev] == 0) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        n[dev] = v > 0 ? v : 148;
     }
-    return n;
+    return n[dev];
+}
+// cudaFuncAttributeMaxDynamicSharedMemorySize applies per device: `done` is the per-kernel bit set of devices served
+template <typename K>
+inline cudaError_t ensure_max_smem(K kernel, unsigned long long* done, int bytes) {
+    const int dev = current_device();
+    if ((*done >> dev) & 1ull) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) *done |= 1ull << dev;
+    return e;
 }
 
 // Blocks for a grid-stride kernel: enough to cover `work` items at `per_block` each, capped at `waves` resident

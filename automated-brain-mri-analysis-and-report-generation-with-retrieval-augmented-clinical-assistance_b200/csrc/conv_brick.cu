@@ -23,6 +23,7 @@
 // groups take alternate planes).  With one group the issuer is the highest warp id of its scheduler partition: the
 // warp arbiter favours the highest id, so the latency-critical tcgen05.mma stream is never queued behind the
 // instruction-heavy epilogue warp it shares the partition with.
+#include "bsg_common.cuh"
 #include "bsg_ptx.cuh"
 #include "conv_brick.cuh"
 #include "conv_epilogue.cuh"
@@ -312,6 +313,9 @@ __global__ void __launch_bounds__(brick_threads(CC), 1) conv_brick_kernel(const 
         epi.slope = a.slope;
         epi.out_f16 = a.out_f16;
         epi.stats = STATS ? a.stats : nullptr;
+        epi.guard = (a.overflow != nullptr && a.out_f16) ? 1 : 0;
+        EpiGuard guard;
+        guard.init();
         StatAcc sacc[NT / 32];
         float t1[NT / 32][32], t2[NT / 32][32];  // per-thread sums over the planes of one brick (STATS only)
 #pragma unroll
@@ -343,7 +347,7 @@ __global__ void __launch_bounds__(brick_threads(CC), 1) conv_brick_kernel(const 
                     uint32_t v[32];
                     tmem_ld_32x32(t_addr + cb, v);
                     tmem_ld_wait();
-                    epilogue_32cols<kThreadAcc>(v, epi, cb, true, lane, sacc[cb / 32], orow, t1[cb / 32], t2[cb / 32]);
+                    epilogue_32cols<kThreadAcc>(v, epi, cb, true, lane, sacc[cb / 32], orow, t1[cb / 32], t2[cb / 32], guard);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -362,6 +366,7 @@ __global__ void __launch_bounds__(brick_threads(CC), 1) conv_brick_kernel(const 
 #pragma unroll
             for (int j = 0; j < NT / 32; ++j) flush_stats(epi, sacc[j], j * 32, lane, stat_n);
         }
+        if (epi.guard) guard.flush(a.overflow);
     }
 
     tc_fence_before();
@@ -374,13 +379,9 @@ __global__ void __launch_bounds__(brick_threads(CC), 1) conv_brick_kernel(const 
 
 template <int CC, int NT, bool STATS, bool KWF>
 cudaError_t launch_variant(const BrickArgs& a, int grid, size_t smem_bytes, cudaStream_t stream) {
-    static bool attr_set = false;  // one process drives one device
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_brick_kernel<CC, NT, STATS, KWF>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static unsigned long long attr_done = 0;  // per device
+    if (cudaError_t e = ensure_max_smem(conv_brick_kernel<CC, NT, STATS, KWF>, &attr_done, 232448); e != cudaSuccess)
+        return e;
     conv_brick_kernel<CC, NT, STATS, KWF><<<grid, brick_threads(CC), smem_bytes, stream>>>(a);
     return cudaGetLastError();
 }

@@ -37,6 +37,7 @@ struct BrickArgs {
     int act;
     float* stats;
     int out_f16;
+    int* overflow;  // device flag, set when a stored fp16 value left the fp16 range (null: no guard)
     int in_f16;  // 1: activations and weights are IEEE fp16 instead of bf16
 };
 

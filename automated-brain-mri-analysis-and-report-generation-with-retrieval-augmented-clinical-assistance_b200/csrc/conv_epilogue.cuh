@@ -24,6 +24,19 @@ struct EpiParams {
     int act;             // 1: LeakyReLU(slope)
     float slope;
     int out_f16;         // 1: store IEEE fp16 instead of bf16
+    int guard;           // 1: track the largest stored magnitude (fp16 range guard, see EpiGuard)
+};
+
+// fp16 range guard: IEEE fp16 saturates at 65504 and nothing downstream would notice an inf (the reference's CUDA path
+// has the same exposure under autocast).  Every epilogue thread keeps the largest magnitude it stored; at the end of
+// its role a value beyond the fp16 range sets *flag, which the engine reads back once per case and answers by
+// re-planning the network in bf16 (engine.py).  16 FMNMX3 per 32 columns.
+struct EpiGuard {
+    float amax;
+    __device__ __forceinline__ void init() { amax = 0.f; }
+    __device__ __forceinline__ void flush(int* flag) const {
+        if (flag != nullptr && !(amax <= 65504.f)) atomicOr(flag, 1);
+    }
 };
 
 // Per-lane running norm statistics of one 32-column chunk: after the transpose-reduce lane l owns channel co + l.
@@ -64,6 +77,30 @@ __device__ __forceinline__ void stats_transpose_reduce(float (&s1)[32], float (&
     acc.s2 += s2[0];
 }
 
+// Norm statistics of one 32-column chunk when the rows of a warp span SEVERAL batch items (tile boxes with fewer than
+// 32 voxels per item: the <= 2^3 levels of a deep net run with batch > 4 per tile).  One masked transpose-reduce and
+// one flush per batch item of the warp; cold path (tiny layers only), kept out of line.
+static __device__ __noinline__ void stats_chunk_grouped(const uint32_t (&v)[32], const EpiParams& e, int co, bool valid, int lane,
+                                                 int vox_per_item, int n_first) {
+    float f[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + (e.has_bias ? e.sbias[co + i] : 0.f);
+    for (int g = 0; g * vox_per_item < 32; ++g) {
+        const bool mine = valid && (lane / vox_per_item == g);
+        float s1[32], s2[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const float x = mine ? f[i] : 0.f;
+            s1[i] = x;
+            s2[i] = x * x;
+        }
+        StatAcc acc;
+        acc.s1 = acc.s2 = 0.f;
+        stats_transpose_reduce(s1, s2, lane, acc);
+        flush_stats(e, acc, co, lane, n_first + g);
+    }
+}
+
 // v: the 32 accumulator columns [co, co+32) of this thread's voxel; orow: the voxel's first output channel;
 // valid: voxel inside the tensor.  Norm statistics (when e.stats != null): THREAD_ACC = false reduces this tile's
 // values over the warp right away into `acc`; THREAD_ACC = true only adds them to the caller's per-thread sums
@@ -71,7 +108,8 @@ __device__ __forceinline__ void stats_transpose_reduce(float (&s1)[32], float (&
 // 64 FMAs per tile and chunk instead of 62 shuffles + ~190 selects/adds.
 template <bool THREAD_ACC>
 __device__ __forceinline__ void epilogue_32cols(const uint32_t (&v)[32], const EpiParams& e, int co, bool valid, int lane,
-                                                StatAcc& acc, __nv_bfloat16* orow, float (&t1)[32], float (&t2)[32]) {
+                                                StatAcc& acc, __nv_bfloat16* orow, float (&t1)[32], float (&t2)[32],
+                                                EpiGuard& guard) {
     float f[32];
     if (e.has_bias) {
         // bias: 8 x ld.shared.v4 (warp-wide broadcast); `e.sbias` is a generic pointer, which would compile to 32
@@ -116,6 +154,12 @@ __device__ __forceinline__ void epilogue_32cols(const uint32_t (&v)[32], const E
         for (int i = 0; i < 32; ++i) f[i] = f[i] > 0.f ? f[i] : f[i] * e.slope;
     }
     if (!valid) return;
+    if (e.guard) {
+        float m = guard.amax;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) m = fmaxf(m, fmaxf(fabsf(f[2 * i]), fabsf(f[2 * i + 1])));
+        guard.amax = m;
+    }
     if (co + 32 <= e.cout) {
         // one uniform branch around the whole block: a per-element `out_f16 ? half : bf16` is if-converted into BOTH
         // F2FP conversions plus a select, and the conversion pipe is what bounds the store-heavy epilogues (ncu on the

@@ -140,6 +140,7 @@ int plan_brick(const bsg_conv_desc* d, bsg_conv_plan* p) {
     a.stats = d->stats;
     a.out_f16 = d->out_f16;
     a.in_f16 = d->in_f16;
+    a.overflow = d->overflow;
 
     p->brick = 1;
     p->brick_cc = cc;
@@ -180,6 +181,8 @@ int bsg_check_device(void) {
 }
 
 int bsg_sm_count(void) { return sm_count_cached(); }
+
+size_t bsg_conv_desc_size(void) { return sizeof(bsg_conv_desc); }
 
 int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
     BSG_REQUIRE(d != nullptr && out_plan != nullptr, "null argument");
@@ -388,6 +391,7 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
     a.stats = d->stats;
     a.out_f16 = d->out_f16;
     a.in_f16 = d->in_f16;
+    a.overflow = d->overflow;
 
     const int total_tiles = a.tn * a.td * a.th * a.tw * a.n_ntiles;
     int max_ctas = d->max_ctas > 0 ? d->max_ctas : sm_count_cached();

@@ -8,6 +8,7 @@
 //   warp 4      TMA producer   (activation halo boxes + weight slabs -> swizzled smem ring)
 //   warp 5      MMA issuer     (one elected lane, tcgen05.mma kind::f16, fp32 accumulators in TMEM, 2 buffers)
 #include <cuda_fp16.h>
+#include "bsg_common.cuh"
 #include "bsg_ptx.cuh"
 #include "conv_epilogue.cuh"
 #include "conv_tc.cuh"
@@ -323,8 +324,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         epi.act = a.act;
         epi.slope = a.slope;
         epi.out_f16 = a.out_f16;
+        epi.guard = (a.overflow != nullptr && a.out_f16) ? 1 : 0;
+        EpiGuard guard;
+        guard.init();
         // running norm statistics of the (up to 8) 32-column chunks of the current N tile, flushed when the batch item
-        // of this warp's rows or the N tile changes (rows of one warp always share the batch index)
+        // of this warp's rows or the N tile changes.  The rows of one warp share the batch index as long as a tile holds
+        // >= 32 voxels per item (bn <= 4); smaller boxes take the grouped path (stats_chunk_grouped).
+        const int vox_per_item = a.bw * a.bh * a.bd;
+        const bool grouped = a.stats != nullptr && vox_per_item < 32;
+        EpiParams epi_plain = epi;  // the chunk body without statistics (grouped path)
+        epi_plain.stats = nullptr;
         StatAcc sacc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) sacc[j].s1 = sacc[j].s2 = 0.f;
@@ -336,7 +345,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const uint32_t acc = tcount & 1u;
             const uint32_t acc_phase = (tcount >> 1) & 1u;
             const int w = t.w0 + iw, h = t.h0 + ih, d = t.d0 + id, n = t.n0 + in;
-            if (a.stats != nullptr) {
+            if (a.stats != nullptr && !grouped) {
                 const int n_warp = __shfl_sync(0xffffffffu, n, 0);
                 if (n_warp != stat_n || t.nt != stat_nt) {
 #pragma unroll
@@ -394,8 +403,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 }
                 StatAcc chunk_stats;
                 chunk_stats.s1 = chunk_stats.s2 = 0.f;
-                epilogue_32cols<false>(v, epi, co, valid, lane, chunk_stats, orow, unused1, unused2);
-                if (a.stats != nullptr) {
+                epilogue_32cols<false>(v, grouped ? epi_plain : epi, co, valid, lane, chunk_stats, orow, unused1, unused2,
+                                       guard);
+                if (grouped) {
+                    stats_chunk_grouped(v, epi, co, valid, lane, vox_per_item, t.n0 + (q * 32) / vox_per_item);
+                } else if (a.stats != nullptr) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
                         if (k == j) {
@@ -408,10 +420,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
-        if (a.stats != nullptr) {
+        if (a.stats != nullptr && !grouped) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) flush_stats(epi, sacc[j], stat_nt * a.ntile + j * 32, lane, stat_n);
         }
+        if (epi.guard) guard.flush(a.overflow);
     }
 
     tc_fence_before();
@@ -432,13 +445,8 @@ size_t conv_tc_smem_bytes(const ConvArgs& a) {
 
 template <int CC, int MODE>
 static cudaError_t launch_variant(const ConvArgs& a, int grid, size_t smem_bytes, cudaStream_t stream) {
-    static bool attr_set = false;  // one process drives one device
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<CC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             232448);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static unsigned long long attr_done = 0;  // per device
+    if (cudaError_t e = ensure_max_smem(conv_tc_kernel<CC, MODE>, &attr_done, 232448); e != cudaSuccess) return e;
     if (a.pair) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(static_cast<unsigned>(grid));

@@ -375,11 +375,8 @@ int bsg_edt(const uint8_t* mask, int d0, int d1, int d2, const double* sampling,
     const int nmax = d0 > d1 ? (d0 > d2 ? d0 : d2) : (d1 > d2 ? d1 : d2);
     const size_t smem_max = (static_cast<size_t>(nmax) * kPitch + nmax) * sizeof(double);
     BSG_REQUIRE(smem_max <= 200 * 1024, "extent %d too large for the EDT line buffer", nmax);
-    static bool attr_set = false;
-    if (!attr_set) {
-        BSG_CUDA_OK(cudaFuncSetAttribute(edt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    static unsigned long long attr_done = 0;  // per device
+    BSG_CUDA_OK(ensure_max_smem(edt_pass_kernel, &attr_done, 200 * 1024));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const long long D0 = d0, D1 = d1, D2 = d2;
     const double sm[3] = {sampling ? sampling[0] : 1.0, sampling ? sampling[1] : 1.0, sampling ? sampling[2] : 1.0};

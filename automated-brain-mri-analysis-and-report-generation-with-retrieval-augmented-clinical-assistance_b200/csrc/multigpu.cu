@@ -1,0 +1,218 @@
+// Exchange step of the sharded sliding window (BASELINE configs[2]: the (tile, mirror) work items of ONE case are dealt
+// to R GPUs, each accumulates its share into a private fp32 accumulator; reference call site being sharded:
+// run_brats2021_inference_singlethread.py:97-106 per-fold predict, :113-128 fold mean, :144-156 regions decision).
+//
+//   peer_finalize_kernel   ONE kernel = reduce over ranks + finalize: every rank owns a slab of the voxel range, reads
+//                          that slab of ALL ranks' accumulators through NVLink peer pointers (plain ld.global on
+//                          mapped peer memory), sums them in rank order (deterministic), divides by the weight sum,
+//                          averages the folds, takes the regions / argmax decision and writes the uint8 labels into
+//                          EVERY rank's label volume (peer stores).  Replaces all-reduce (2 x 107 MB on the wire per
+//                          rank) + finalize + broadcast by (R-1)/R x 107 MB of peer reads + 9 MB of peer writes, and no
+//                          rank ever holds or finalizes more than its 1/R slab.
+//   bsg_nccl_*             the plain-NCCL route (one ncclAllReduce / ncclReduce of the accumulator) over the library's
+//                          own communicator; libnccl is resolved at run time (dlopen), so the library loads without it.
+#include <dlfcn.h>
+#include <nccl.h>
+#include "bsg_common.cuh"
+
+namespace bsg {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxClasses = 8;
+constexpr int kMaxPtrs = 128;  // K folds x R ranks
+
+struct PeerFinalizeParams {
+    const float* const* acc_table;  // device [K][R]: accumulator of fold k on rank r, each [ncls][nvox]
+    uint8_t* const* seg_table;      // device [nseg]: label volumes to write (every rank's, or just the local one)
+    int K, R, nseg, ncls, mode;
+    int order[kMaxClasses];
+};
+
+__global__ void __launch_bounds__(kThreads) peer_finalize_kernel(const PeerFinalizeParams fp, const float* __restrict__ wsum,
+                                                                 size_t nvox, size_t v0, size_t nv) {
+    __shared__ const float* s_acc[kMaxPtrs];
+    __shared__ uint8_t* s_seg[16];
+    for (int i = threadIdx.x; i < fp.K * fp.R; i += blockDim.x) s_acc[i] = fp.acc_table[i];
+    for (int i = threadIdx.x; i < fp.nseg; i += blockDim.x) s_seg[i] = fp.seg_table[i];
+    __syncthreads();
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    const size_t ngroups = nv / 4;
+    for (size_t g = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
+        const size_t i = v0 + g * 4;
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(wsum + i));
+        float p[4][kMaxClasses];
+#pragma unroll
+        for (int k = 0; k < kMaxClasses; ++k) {
+            if (k < fp.ncls) {
+                float s[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int j = 0; j < fp.K; ++j) {
+                    // sum over ranks in rank order: the same fp32 additions on every rank and in every run
+                    float4 a = __ldg(reinterpret_cast<const float4*>(s_acc[j * fp.R] + k * nvox + i));
+                    for (int r = 1; r < fp.R; ++r) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(s_acc[j * fp.R + r] + k * nvox + i));
+                        a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+                    }
+                    const float q[4] = {__fdiv_rn(a.x, wv.x), __fdiv_rn(a.y, wv.y), __fdiv_rn(a.z, wv.z),
+                                        __fdiv_rn(a.w, wv.w)};
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) s[v] = j == 0 ? q[v] : s[v] + q[v];
+                }
+#pragma unroll
+                for (int v = 0; v < 4; ++v) p[v][k] = fp.K > 1 ? __fdiv_rn(s[v], static_cast<float>(fp.K)) : s[v];
+            }
+        }
+        uint32_t packed = 0;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            int lab = 0;
+            if (fp.mode == 0) {
+                float best = p[v][0];
+#pragma unroll
+                for (int k = 1; k < kMaxClasses; ++k)
+                    if (k < fp.ncls && p[v][k] > best) {
+                        best = p[v][k];
+                        lab = k;
+                    }
+            } else {
+#pragma unroll
+                for (int k = 0; k < kMaxClasses; ++k)
+                    if (k < fp.ncls && p[v][k] > 0.5f) lab = fp.order[k];
+            }
+            packed |= static_cast<uint32_t>(lab & 255) << (8 * v);
+        }
+        for (int t = 0; t < fp.nseg; ++t) *reinterpret_cast<uint32_t*>(s_seg[t] + i) = packed;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- NCCL (dlopen)
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t);
+    const char* (*GetErrorString)(ncclResult_t);
+    bool ok;
+};
+
+const NcclApi* nccl_api() {
+    static NcclApi api = {};
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        // by soname: inside a PyTorch process this resolves to the libnccl torch already loaded
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (h == nullptr) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (h != nullptr) {
+            api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+            api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+            api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+            api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(h, "ncclAllReduce"));
+            api.Reduce = reinterpret_cast<decltype(api.Reduce)>(dlsym(h, "ncclReduce"));
+            api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+            api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.Reduce &&
+                     api.GetErrorString;
+        }
+    }
+    return api.ok ? &api : nullptr;
+}
+
+#define BSG_NCCL_OK(api, expr)                                                                     \
+    do {                                                                                           \
+        ncclResult_t _r = (expr);                                                                  \
+        if (_r != ncclSuccess)                                                                     \
+            return ::bsg::set_error(BSG_ECUDA, "%s failed: %s", #expr, (api)->GetErrorString(_r)); \
+    } while (0)
+
+}  // namespace
+}  // namespace bsg
+
+using namespace bsg;
+
+extern "C" {
+
+int bsg_finalize_peer(const float* const* acc_table_dev, int K, int R, const float* wsum, int ncls, size_t nvox, size_t v0,
+                      size_t nv, int mode, const int* order_host, uint8_t* const* seg_table_dev, int nseg, void* stream) {
+    BSG_REQUIRE(acc_table_dev != nullptr && wsum != nullptr && seg_table_dev != nullptr, "null argument");
+    BSG_REQUIRE(K >= 1 && R >= 1 && K * R <= kMaxPtrs, "K %d x R %d accumulators (<= %d)", K, R, kMaxPtrs);
+    BSG_REQUIRE(nseg >= 1 && nseg <= 16, "nseg %d (1..16)", nseg);
+    BSG_REQUIRE(ncls >= 1 && ncls <= kMaxClasses, "ncls %d", ncls);
+    BSG_REQUIRE(mode == 0 || (mode == 1 && order_host != nullptr), "mode %d", mode);
+    BSG_REQUIRE(nvox % 4 == 0 && v0 % 4 == 0 && nv % 4 == 0 && v0 + nv <= nvox,
+                "voxel range [%zu, %zu) of %zu must be 4-aligned", v0, v0 + nv, nvox);
+    BSG_REQUIRE((reinterpret_cast<uintptr_t>(wsum) & 15) == 0, "wsum must be 16-byte aligned");
+    if (nv == 0) return BSG_OK;
+    PeerFinalizeParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.acc_table = acc_table_dev;
+    fp.seg_table = seg_table_dev;
+    fp.K = K;
+    fp.R = R;
+    fp.nseg = nseg;
+    fp.ncls = ncls;
+    fp.mode = mode;
+    for (int k = 0; k < ncls; ++k) fp.order[k] = order_host ? order_host[k] : k;
+    peer_finalize_kernel<<<grid_for(nv / 4, kThreads, 8), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(fp, wsum, nvox,
+                                                                                                          v0, nv);
+    BSG_CUDA_OK(cudaGetLastError());
+    return BSG_OK;
+}
+
+int bsg_enable_peer_access(int peer_device) {
+    int dev = 0, can = 0;
+    BSG_CUDA_OK(cudaGetDevice(&dev));
+    if (peer_device == dev) return BSG_OK;
+    BSG_CUDA_OK(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+    if (!can) return set_error(BSG_ECUDA, "device %d cannot access peer %d", dev, peer_device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();  // clear the sticky-free error state
+        return BSG_OK;
+    }
+    BSG_CUDA_OK(e);
+    return BSG_OK;
+}
+
+int bsg_nccl_unique_id(void* id128_host) {
+    BSG_REQUIRE(id128_host != nullptr, "null argument");
+    const NcclApi* api = nccl_api();
+    if (api == nullptr) return set_error(BSG_ECUDA, "libnccl.so.2 could not be loaded");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    BSG_NCCL_OK(api, api->GetUniqueId(static_cast<ncclUniqueId*>(id128_host)));
+    return BSG_OK;
+}
+
+int bsg_nccl_comm_create(const void* id128_host, int nranks, int rank, void** comm_out) {
+    BSG_REQUIRE(id128_host != nullptr && comm_out != nullptr && nranks >= 1 && rank >= 0 && rank < nranks, "bad argument");
+    const NcclApi* api = nccl_api();
+    if (api == nullptr) return set_error(BSG_ECUDA, "libnccl.so.2 could not be loaded");
+    ncclUniqueId id;
+    memcpy(&id, id128_host, sizeof(id));
+    ncclComm_t comm = nullptr;
+    BSG_NCCL_OK(api, api->CommInitRank(&comm, nranks, id, rank));
+    *comm_out = comm;
+    return BSG_OK;
+}
+
+int bsg_nccl_reduce_accumulator(void* comm, float* acc, size_t count, int root, void* stream) {
+    BSG_REQUIRE(comm != nullptr && acc != nullptr, "null argument");
+    const NcclApi* api = nccl_api();
+    if (api == nullptr) return set_error(BSG_ECUDA, "libnccl.so.2 could not be loaded");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (root < 0)
+        BSG_NCCL_OK(api, api->AllReduce(acc, acc, count, ncclFloat, ncclSum, static_cast<ncclComm_t>(comm), s));
+    else
+        BSG_NCCL_OK(api, api->Reduce(acc, acc, count, ncclFloat, ncclSum, root, static_cast<ncclComm_t>(comm), s));
+    return BSG_OK;
+}
+
+int bsg_nccl_comm_destroy(void* comm) {
+    if (comm == nullptr) return BSG_OK;
+    const NcclApi* api = nccl_api();
+    if (api == nullptr) return set_error(BSG_ECUDA, "libnccl.so.2 could not be loaded");
+    BSG_NCCL_OK(api, api->CommDestroy(static_cast<ncclComm_t>(comm)));
+    return BSG_OK;
+}
+
+}  // extern "C"

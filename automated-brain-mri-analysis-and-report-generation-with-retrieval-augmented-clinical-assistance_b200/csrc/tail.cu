@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(kThreads) head_tta_accumulate_kernel(
 
 // ---------------------------------------------------------------------------------------------- finalize
 struct FinalizeParams {
-    const float* acc[8];  // K accumulators (folds / models to average), each [ncls][nvox]
+    const float* acc[16];  // K accumulators (folds / models to average), each [ncls][nvox]
     int K;
     int ncls;
     int mode;                // 0: argmax, 1: ordered threshold > 0.5 (regions)
@@ -474,7 +474,7 @@ int bsg_head_tta_accumulate(const void* feat_bf16, int feat_f16, int cfeat, int 
 int bsg_finalize(const float* const* acc_list_host, int K, const float* wsum, int ncls, size_t nvox, int mode,
                  const int* order_host, float* probs, uint8_t* seg, void* stream) {
     BSG_REQUIRE(acc_list_host != nullptr && wsum != nullptr, "null argument");
-    BSG_REQUIRE(K >= 1 && K <= 8, "K %d (1..8)", K);
+    BSG_REQUIRE(K >= 1 && K <= 16, "K %d (1..16)", K);
     BSG_REQUIRE(ncls >= 1 && ncls <= kMaxClasses, "ncls %d", ncls);
     BSG_REQUIRE(mode == 0 || (mode == 1 && order_host != nullptr), "mode %d", mode);
     FinalizeParams fp;

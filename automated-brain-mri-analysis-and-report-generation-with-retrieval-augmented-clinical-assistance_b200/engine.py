@@ -45,8 +45,19 @@ class _Act:
         return self.buf[..., self.coff:self.coff + self.c]
 
 
+_overflow_flags = {}
+
+
+def overflow_flag(device):
+    """The device's fp16-overflow flag (one int32): set by any guarded conv epilogue, cleared by whoever handles it."""
+    device = torch.device(device)
+    if device not in _overflow_flags:
+        _overflow_flags[device] = torch.zeros(1, dtype=torch.int32, device=device)
+    return _overflow_flags[device]
+
+
 class UNetEngine:
-    def __init__(self, net, patch_size, batch, device=None):
+    def __init__(self, net, patch_size, batch, device=None, act_dtype=None):
         if not torch.cuda.is_available():
             raise L.BsgError("brainseg_b200 needs a CUDA device (sm_100); there is no CPU fallback")
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -56,13 +67,20 @@ class UNetEngine:
         div = [int(v) for v in net.input_shape_must_be_divisible_by]
         if any(p % d for p, d in zip(self.patch, div)):
             raise ValueError(f"patch size {self.patch} must be divisible by {div}")
-        norms = [m for m in net.modules() if isinstance(m, (nn.InstanceNorm3d, nn.GroupNorm))]
-        mode = os.environ.get("BSG_ACT_DTYPE", "auto").lower()  # auto | bf16 | fp16
+        # activation dtype: the network's own setting (SegmentationNetwork.engine_dtype — the fp16 range guard flips it
+        # to "bf16" after an overflow) wins over the BSG_ACT_DTYPE environment default
+        mode = (act_dtype or getattr(net, "engine_dtype", None) or os.environ.get("BSG_ACT_DTYPE", "auto")).lower()
         if mode not in ("auto", "bf16", "fp16"):
-            raise ValueError(f"BSG_ACT_DTYPE={mode!r}: expected auto, bf16 or fp16")
+            raise ValueError(f"activation dtype {mode!r}: expected auto, bf16 or fp16")
         # auto = fp16 for every stack.  (The InstanceNorm / GroupNorm stacks need it outright: bf16 activations miss the
         # 1e-2 probability bar there.)
         self.f16 = int(mode != "bf16")
+        # fp16 range guard: one device flag (shared by all engines of the device), raised by a conv epilogue when a value
+        # it stored left the fp16 range (bsg_conv_desc.overflow); the pipeline reads it back once per case
+        self.guard = bool(self.f16) and os.environ.get("BSG_OVERFLOW_GUARD", "1") != "0"
+        self._overflow = overflow_flag(self.device) if self.guard else None
+        self._weight_slots = []  # (kind, module, packed tensors): reload_weights() re-packs into them in place
+        self.flops_algo = 0.0    # algorithmic FLOPs on the real channel counts (the 4 input channels are padded to 16)
         self.act_dtype = torch.float16 if self.f16 else torch.bfloat16
         self.steps = []       # callables, in launch order
         self.step_info = []   # per step: name, algorithmic flops, plan geometry (diagnostics / bench breakdown)
@@ -86,15 +104,13 @@ class UNetEngine:
         self.keep.append(t)
         return t
 
-    def _add_block(self, blk, src, dst, spatial_in, defer_apply=False):
+    def _pack_block(self, blk, cin_pad):
+        """Packed 16-bit weights + fp32 bias of one conv block (eval BatchNorm folded in), norm affine parameters."""
         conv, norm = blk.conv, blk.instnorm
-        stride = int(conv.stride[0])
         w = conv.weight.detach().to(self.device, torch.float32)
         b = conv.bias.detach().to(self.device, torch.float32) if conv.bias is not None else torch.zeros(
             w.shape[0], device=self.device)
-        slope = float(blk.lrelu.negative_slope)
-        cout = w.shape[0]
-        stats = None
+        gamma = beta = None
         if isinstance(norm, nn.BatchNorm3d):
             # eval BatchNorm == per-channel affine: fold into the conv (generic_UNet.py:72 with network.eval())
             scale = norm.weight.detach().to(self.device).float() / torch.sqrt(
@@ -102,24 +118,42 @@ class UNetEngine:
             w = w * scale.view(-1, 1, 1, 1, 1)
             b = (b - norm.running_mean.detach().to(self.device).float()) * scale + norm.bias.detach().to(
                 self.device).float()
-            act = L.BSG_ACT_LRELU
         elif isinstance(norm, (nn.InstanceNorm3d, nn.GroupNorm)):
-            stats = self._carve_stats(cout)
-            act = L.BSG_ACT_NONE
+            gamma = norm.weight.detach().to(self.device).float().contiguous() if norm.weight is not None else None
+            beta = norm.bias.detach().to(self.device).float().contiguous() if norm.bias is not None else None
         else:
             raise NotImplementedError(f"norm {type(norm).__name__}")
+        return (P.pack_conv3_weight(w, cin_pad, self.act_dtype), P.pad_bias(b, w.shape[0]).to(self.device), gamma, beta)
+
+    def _overflow_slot(self):
+        return self._overflow.data_ptr() if self._overflow is not None else None
+
+    def _add_block(self, blk, src, dst, spatial_in, defer_apply=False):
+        conv, norm = blk.conv, blk.instnorm
+        stride = int(conv.stride[0])
+        slope = float(blk.lrelu.negative_slope)
+        cout = conv.out_channels
+        stats = None
+        if isinstance(norm, nn.BatchNorm3d):
+            act = L.BSG_ACT_LRELU
+        else:
+            act = L.BSG_ACT_NONE
         cin_pad = src.c
-        wp = P.pack_conv3_weight(w, cin_pad, self.act_dtype)
-        bp = P.pad_bias(b, cout).to(self.device)
+        wp, bp, gamma, beta = self._pack_block(blk, cin_pad)
+        if act == L.BSG_ACT_NONE:
+            stats = self._carve_stats(cout)
         self.keep += [wp, bp]
+        self._weight_slots.append(("block", blk, cin_pad, (wp, bp, gamma, beta)))
         d, h, wd = spatial_in
         plan = L.ConvPlan(kind=L.BSG_CONV_K3, stride=stride, N=self.batch, D=d, H=h, W=wd, cin=cin_pad,
                           in_ptr=src.ptr(), in_ctot=src.ctot, cout=cout, out_ptr=dst.buf.data_ptr(),
                           out_ctot=dst.ctot, out_coff=dst.coff, weights=wp.data_ptr(), bias=bp.data_ptr(), act=act,
                           slope=slope, stats=stats.data_ptr() if stats is not None else None,
-                          out_f16=1 if (stats is not None or self.f16) else 0, in_f16=self.f16, use_khshift=-1,
-                          max_ctas=0)
+                          out_f16=self.f16, in_f16=self.f16, use_khshift=-1,
+                          max_ctas=0, overflow=self._overflow_slot())
         self.flops += plan.info().flops
+        so_ = tuple(s // stride for s in spatial_in)
+        self.flops_algo += 2.0 * 27 * conv.in_channels * cout * so_[0] * so_[1] * so_[2] * self.batch
         self._note(f"conv3 s{stride} {cin_pad}->{cout} @{'x'.join(map(str, spatial_in))}"
                    f"{' +norm' if stats is not None else ''}", plan)
         lib = L.lib()
@@ -128,8 +162,6 @@ class UNetEngine:
             self.launches_per_forward += 1
             return
         groups = norm.num_groups if isinstance(norm, nn.GroupNorm) else 0
-        gamma = norm.weight.detach().to(self.device).float().contiguous() if norm.weight is not None else None
-        beta = norm.bias.detach().to(self.device).float().contiguous() if norm.bias is not None else None
         ss = torch.empty(self.batch, cout, 2, dtype=torch.float32, device=self.device)
         self.keep += [stats, ss, gamma, beta]
         so = tuple(s // stride for s in spatial_in)
@@ -150,7 +182,7 @@ class UNetEngine:
             L.check(lib.bsg_norm_finalize(_ptr(stats), self.batch, cout, groups, float(vox), eps, gp, bp2, _ptr(ss), sp))
             if not defer_apply:
                 L.check(lib.bsg_norm_apply_lrelu(_ptr(dst.buf), vox, self.batch, cout, dst.ctot, dst.coff, _ptr(ss), slope,
-                                                 1, self.f16, sp))
+                                                 self.f16, self.f16, sp))
 
         self.steps.append(run)
         self.launches_per_forward += 2 if defer_apply else 3  # conv, norm_finalize(, norm_apply): the library's own kernels
@@ -161,12 +193,15 @@ class UNetEngine:
         w = tu.weight.detach().to(self.device, torch.float32)
         wp = P.pack_convT2_weight(w, src.c, self.act_dtype)
         self.keep.append(wp)
+        self._weight_slots.append(("tu", tu, src.c, (wp,)))
         d, h, wd = spatial_in
         plan = L.ConvPlan(kind=L.BSG_CONVT_K2S2, stride=1, N=self.batch, D=d, H=h, W=wd, cin=src.c, in_ptr=src.ptr(),
                           in_ctot=src.ctot, cout=w.shape[1], out_ptr=dst.buf.data_ptr(), out_ctot=dst.ctot,
                           out_coff=dst.coff, weights=wp.data_ptr(), bias=None, act=L.BSG_ACT_NONE, slope=0.0,
-                          stats=None, out_f16=self.f16, in_f16=self.f16, use_khshift=0, max_ctas=0)
+                          stats=None, out_f16=self.f16, in_f16=self.f16, use_khshift=0, max_ctas=0,
+                          overflow=self._overflow_slot())
         self.flops += plan.info().flops
+        self.flops_algo += plan.info().flops
         self._note(f"convT2 {src.c}->{w.shape[1]} @{'x'.join(map(str, spatial_in))}", plan)
         self.steps.append(plan.run)
         self.launches_per_forward += 1
@@ -221,12 +256,37 @@ class UNetEngine:
                 self._add_block(blk, cur, dst, spatial, defer_apply=last)
                 cur = dst
         self.features = cur
-        head = net.seg_outputs[num_pool - 1]
+        self._head = net.seg_outputs[num_pool - 1]
+        self._load_head()
+        self.num_classes = self._head.out_channels
+        head_flops = 2.0 * self.num_classes * self.head_w.shape[1] * (self.patch[0] * self.patch[1] * self.patch[2])
+        self.flops_per_item = self.flops / self.batch + head_flops            # as launched (input channels padded to 16)
+        self.flops_algo_per_item = self.flops_algo / self.batch + head_flops  # algorithmic (965.5 / 3342.2 GF)
+
+    def _load_head(self):
+        head = self._head
         self.head_w = head.weight.detach().float().reshape(head.out_channels, -1).cpu().contiguous()
         self.head_b = head.bias.detach().float().cpu().contiguous() if head.bias is not None else None
-        self.num_classes = head.out_channels
-        self.flops_per_item = self.flops / self.batch + 2.0 * self.num_classes * self.head_w.shape[1] * (
-            self.patch[0] * self.patch[1] * self.patch[2])
+
+    def reload_weights(self):
+        """Re-packs the module tree's current parameters into the engine's EXISTING device tensors (plans and tensor
+        maps point at fixed buffers, so they stay valid): what load_state_dict / load_checkpoint_ram need per fold,
+        instead of rebuilding activation buffers, plans and tensor maps."""
+        for kind, mod, cin_pad, tensors in self._weight_slots:
+            if kind == "block":
+                for dst, src in zip(tensors, self._pack_block(mod, cin_pad)):
+                    if dst is not None:
+                        dst.copy_(src)
+            else:
+                tensors[0].copy_(P.pack_convT2_weight(mod.weight.detach().to(self.device, torch.float32), cin_pad,
+                                                      self.act_dtype))
+        self._load_head()
+
+    def close(self):
+        """Drops plans, buffers and the step closures (which reference the engine): frees the device memory now
+        instead of at the next cyclic garbage collection."""
+        self.steps, self.plans, self.keep, self._weight_slots = [], [], [], []
+        self.x = self.features = self._stats_arena = self._overflow = None
 
     # ------------------------------------------------------------------ execution
     def _carve_stats(self, cout):

@@ -19,6 +19,7 @@ class SegmentationNetwork(nn.Module):
         self._engines = {}
         self.engine_batch = 8  # (tile, mirror) forwards in flight, split evenly over `engine_lanes` CUDA streams
         self.engine_lanes = 2  # >1: HBM-bound passes of one lane overlap the tensor-bound convs of the other
+        self.engine_dtype = None  # None: BSG_ACT_DTYPE / auto (fp16); "bf16" after the fp16 range guard fired
 
     # ------------------------------------------------------------------ engine cache
     def engine_for(self, patch_size, batch=None, slot=0):
@@ -28,7 +29,7 @@ class SegmentationNetwork(nn.Module):
         if not torch.cuda.is_available():
             raise L.BsgError("brainseg_b200 needs a CUDA device (sm_100); there is no CPU fallback")
         batch = int(batch or self.engine_batch)
-        key = (tuple(int(p) for p in patch_size), batch, torch.cuda.current_device(), int(slot))
+        key = (tuple(int(p) for p in patch_size), batch, torch.cuda.current_device(), int(slot), self.engine_dtype)
         if key not in self._engines:
             self._engines[key] = UNetEngine(self, key[0], batch)
         return self._engines[key]
@@ -41,12 +42,28 @@ class SegmentationNetwork(nn.Module):
         return [self.engine_for(patch_size, per, slot) for slot in range(lanes)]
 
     def invalidate_engines(self):
-        """Call after loading new weights (load_state_dict / load_checkpoint_ram): packed weights are cached."""
+        """Drops every cached engine (device buffers, plans, tensor maps) — after a change of ARCHITECTURE or of the
+        activation dtype.  New weights alone do not need it: see refresh_engines()."""
+        for eng in self._engines.values():
+            eng.close()
         self._engines = {}
 
+    def refresh_engines(self):
+        """Call after the parameters changed in place (load_state_dict / load_checkpoint_ram per fold): re-packs the
+        weights into the cached engines' existing device tensors; activation buffers, plans and tensor maps stay."""
+        for eng in self._engines.values():
+            eng.reload_weights()
+
+    def use_bf16_activations(self):
+        """Answer to the fp16 range guard: re-plan this network with bf16 activations and weights (8 exponent bits)."""
+        if self.engine_dtype != "bf16":
+            self.engine_dtype = "bf16"
+            self.invalidate_engines()
+
     def load_state_dict(self, *a, **k):
-        self.invalidate_engines()
-        return super().load_state_dict(*a, **k)
+        out = super().load_state_dict(*a, **k)
+        self.refresh_engines()
+        return out
 
     def _nonlin_name(self):
         f = self.inference_apply_nonlin

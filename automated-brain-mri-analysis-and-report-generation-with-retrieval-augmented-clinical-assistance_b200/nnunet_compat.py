@@ -83,6 +83,19 @@ class BratsTrainer:
         self.data_aug_params = {"mirror_axes": (0, 1, 2)}
         self.patch_size = self._patch_size_from_plans()
         self.use_mask_for_norm = self._plan_value("use_mask_for_norm", {0: True})
+        # this drop-in covers the BraTS geometry: identity axis order and images already at the plans' target spacing
+        # (1 mm isotropic -> upstream's resampling is a no-op).  Anything else must fail loudly, not silently mis-scale.
+        for key in ("transpose_forward", "transpose_backward"):
+            axes = self._plan_value(key, [0, 1, 2])
+            if list(axes) != [0, 1, 2]:
+                raise NotImplementedError(f"plans[{key!r}] = {list(axes)}: only the identity axis order is supported")
+
+    def _target_spacing(self):
+        try:
+            stages = self.plans["plans_per_stage"]
+            return tuple(float(v) for v in stages[max(stages.keys())]["current_spacing"])
+        except (KeyError, TypeError, ValueError):
+            return None
 
     def _plan_value(self, key, default):
         return self.plans.get(key, default) if isinstance(self.plans, dict) else default
@@ -103,7 +116,7 @@ class BratsTrainer:
         if self.network is None or getattr(self, "_cfg_key", None) != key:
             self.network = build_network(cfg)
             self._cfg_key = key
-        self.network.load_state_dict(sd)  # drops the cached engines (packed weights)
+        self.network.load_state_dict(sd)  # re-packs the weights into the cached engines in place
         self.network.eval()
         self.network.inference_apply_nonlin = nn.Sigmoid() if self.regions_class_order is not None else (
             lambda x: torch.softmax(x, 1))
@@ -114,8 +127,17 @@ class BratsTrainer:
         device.  Returns (d, s, properties) like upstream: `d` a cuda fp32 tensor (C, z, y, x), `s` None."""
         imgs = [nifti_io.load(f) for f in input_files]
         data = np.stack([im.get_fdata().astype(np.float32) for im in imgs])
-        use_mask = all(bool(v) for v in self.use_mask_for_norm.values()) if isinstance(self.use_mask_for_norm, dict) \
-            else bool(self.use_mask_for_norm)
+        if isinstance(self.use_mask_for_norm, dict):  # per channel, as upstream's GenericPreprocessor applies it
+            use_mask = [bool(self.use_mask_for_norm.get(c, self.use_mask_for_norm.get(str(c), True)))
+                        for c in range(data.shape[0])]
+        else:
+            use_mask = bool(self.use_mask_for_norm)
+        target = self._target_spacing()
+        if target is not None:
+            have = tuple(float(v) for v in imgs[0].zooms[:3])[::-1]  # NIfTI (x, y, z) zooms -> array order (z, y, x)
+            if not np.allclose(have, target, atol=1e-3):
+                raise NotImplementedError(f"image spacing {have} differs from the plans' target spacing {target}: "
+                                          "resampling is outside this drop-in (BraTS data is 1 mm isotropic)")
         d, props = preprocessing.preprocess_case(data, use_mask_for_norm=use_mask)
         props["list_of_data_files"] = list(input_files)
         props["nifti_like"] = imgs[0]

@@ -24,11 +24,12 @@ class BratsCasePipeline:
     def __init__(self, models, patch_size=(128, 128, 128), step_size=0.5, mirror_axes=(0, 1, 2), do_mirroring=True,
                  use_gaussian=True, regions_class_order=(1, 2, 3), label_format="brats2025", batch=8, rank=0,
                  world_size=1, reduce_fn=None, lanes=None, ensemble="label_round", small_et_threshold=None,
-                 small_et_replace=2):
+                 small_et_replace=2, shard=None):
         """models: one entry per ensemble member — a drop-in Generic_UNet, or a list of them = the folds of that model,
         whose probabilities are averaged before the decision (np.mean over folds, reference :128);
         `reduce_fn(acc)` sums an accumulator over ranks when the (tile, mirror) work items of ONE case are sharded
-        (latency mode)."""
+        (latency mode); `shard` (a sharded.ShardedExchange) replaces it by the peer-memory / NCCL exchange of that
+        module: accumulators and label volumes then live in buffers the exchange owns."""
         if ensemble not in ("label_round", "prob_mean"):
             raise ValueError("ensemble must be 'label_round' (run_brats2021_inference_singlethread.py:305) or 'prob_mean' "
                              "(archived/kaist_original_inference.py:29-33)")
@@ -41,7 +42,20 @@ class BratsCasePipeline:
         self.regions = regions_class_order
         self.lut = CL.LUT_BRATS2025 if label_format == "brats2025" else CL.LUT_BRATS2021
         self.reduce_fn = reduce_fn
+        self.shard = shard
+        self._build_args = (step_size, use_gaussian, batch, rank, world_size, lanes)
         codes = sliding.mirror_codes_for(mirror_axes, do_mirroring)
+        self._codes = codes
+        self._build_predictors()
+        self._post_stream = None
+        self._copy_stream = None
+        self.extra_launches = 0
+        self.fp16_overflows = 0  # times the fp16 range guard switched the networks to bf16 engines
+        self._gen = 0            # bumped at every such switch: cases submitted before it are re-run
+
+    def _build_predictors(self):
+        step_size, use_gaussian, batch, rank, world_size, lanes = self._build_args
+        codes = self._codes
         self.fold_predictors = []  # [model][fold]
         for folds in self.models:
             row = []
@@ -52,7 +66,6 @@ class BratsCasePipeline:
             self.fold_predictors.append(row)
         self.predictors = [row[0] for row in self.fold_predictors]  # first fold of every model (bench / diagnostics)
         self.device = self.predictors[0].device
-        self._post_stream = None
 
     def kernel_launches(self):
         return sum(p.kernel_launches for row in self.fold_predictors for p in row)
@@ -61,6 +74,8 @@ class BratsCasePipeline:
         """vol: fp32 cuda tensor (C, Z, Y, X), extents >= patch.  Returns the per-model uint8 label volumes."""
         shape = tuple(vol.shape[1:])
         segs = []
+        if self.shard is not None:
+            return self._segment_sharded(vol, shape)
         if self.ensemble == "prob_mean":
             # every member (model x fold) weighs the same, as np.mean over the folds' means does for equal fold counts
             accs = []
@@ -81,6 +96,39 @@ class BratsCasePipeline:
             segs.append(seg)
         return segs
 
+    def _segment_sharded(self, vol, shape):
+        """One case over all ranks: this rank's share of every member's (tile, mirror) forwards goes into accumulators
+        the exchange owns; each ensemble member's exchange + finalize runs on a side stream while the next member's
+        forwards are already being issued; every rank ends up with the complete label volumes."""
+        sh = self.shard
+        main = torch.cuda.current_stream(self.device)
+        side = sh.side_stream()
+        members = [[p for row in self.fold_predictors for p in row]] if self.ensemble == "prob_mean" else \
+            [list(row) for row in self.fold_predictors]
+        segs = []
+        for mi, row in enumerate(members):
+            keys = []
+            for fi, pred in enumerate(row):
+                key = ("acc", mi, fi, shape)
+                acc, _ = sh.shared(key, (pred.engine.num_classes,) + shape, torch.float32)
+                acc.zero_()
+                pred.accumulate(vol, acc)
+                keys.append(key)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            side.wait_event(ready)
+            _, _, wsum = row[0].geometry(shape)
+            with torch.cuda.stream(side):
+                seg = sh.finalize(keys, wsum, row[0].engine.num_classes, self.regions, ("seg", mi, shape))
+            segs.append(seg.view(shape))
+        done = torch.cuda.Event()
+        done.record(side)
+        main.wait_event(done)
+        return segs
+
+    def _engines(self):
+        return [eng for row in self.fold_predictors for pred in row for eng in pred.engines]
+
     # ------------------------------------------------------------------ two-phase API (cohort throughput)
     # submit() enqueues the inference of a case and returns at once; finish() runs the post-processing on a second
     # stream, whose host-side glue and small device->host reads then overlap the inference of the NEXT submitted case:
@@ -90,7 +138,19 @@ class BratsCasePipeline:
         host->device copies, both models' sliding-window inference and the ensemble + remap; no host synchronisation."""
         if isinstance(volume, np.ndarray):
             volume = torch.from_numpy(volume)
-        vol = volume.to(self.device, torch.float32, non_blocking=True).contiguous()
+        if volume.is_cuda:
+            vol = volume.to(self.device, torch.float32).contiguous()
+        else:
+            # host -> device on a copy stream: the upload of case i+1 overlaps the kernels of case i still in flight
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(self.device)
+            main = torch.cuda.current_stream(self.device)
+            with torch.cuda.stream(self._copy_stream):
+                vol = volume.to(self.device, torch.float32, non_blocking=True).contiguous()
+                up = torch.cuda.Event()
+                up.record(self._copy_stream)
+            main.wait_event(up)
+            vol.record_stream(main)
         segs = self.segment(vol)
         if len(segs) == 1:
             seg = segs[0]
@@ -117,18 +177,50 @@ class BratsCasePipeline:
                 gt_dev = gt  # let evaluate_arrays report the mismatch the way the reference does
         done = torch.cuda.Event()
         done.record()
-        return {"vol": vol, "segs": segs, "brats": brats, "gt": gt_dev, "done": done}
+        return {"vol": vol, "segs": segs, "brats": brats, "gt": gt_dev, "gt_in": gt, "done": done, "gen": self._gen}
 
-    def finish(self, pending, voxel_dims=(1.0, 1.0, 1.0), features=True):
-        """Post-processing of a submitted case (Dice, components, morphology) on the pipeline's second stream."""
+    def finish(self, pending, voxel_dims=(1.0, 1.0, 1.0), features=True, post=True, labels=None):
+        """Post-processing of a submitted case (Dice, components, morphology) on the pipeline's second stream.
+        `post=False` (sharded mode: a rank that does not own this case's post-processing) only waits for the case.
+        `labels` (device uint8 volume): run the post-processing on THIS label volume instead of the case's own
+        output — benchmarks of the post-processing leg on realistic (blobby) label volumes; the returned
+        `segmentation` is still the case's own."""
         if self._post_stream is None:
             self._post_stream = torch.cuda.Stream(self.device)
         s = self._post_stream
         s.wait_event(pending["done"])
+        if self._guarded() or pending["gen"] != self._gen:
+            # fp16 range guard: a conv epilogue stored a value beyond 65504 -> label volumes computed by the fp16 engines
+            # are not trustworthy.  Re-plan the networks in bf16 (8 exponent bits) and run the case again — this one and
+            # any case submitted before the switch (their `gen` is stale).
+            from .engine import overflow_flag
+            hit = False
+            if self._guarded():
+                with torch.cuda.stream(s):
+                    hit = bool(overflow_flag(self.device).item())  # 4-byte read on the post stream, after `done`
+            if hit:
+                torch.cuda.synchronize(self.device)  # nothing in flight may still use the engines being dropped
+                overflow_flag(self.device).zero_()
+                self.fp16_overflows += 1
+                self._gen += 1
+                for folds in self.models:
+                    for net in folds:
+                        net.use_bf16_activations()
+                self._build_predictors()
+            if hit or pending["gen"] != self._gen:
+                pending = self.submit(pending["vol"], pending["gt_in"])
+                s.wait_event(pending["done"])
+        if not post:
+            pending["done"].synchronize()
+            return {"segmentation": pending["brats"], "model_segmentations": pending["segs"]}
         brats, segs, gt = pending["brats"], pending["segs"], pending["gt"]
         for t in [brats] + list(segs) + ([gt] if torch.is_tensor(gt) and gt.is_cuda else []):
             t.record_stream(s)
         out = {"segmentation": brats, "model_segmentations": segs}
+        if labels is not None:
+            if tuple(labels.shape) != tuple(brats.shape):
+                labels = labels.reshape(brats.shape) if labels.numel() == brats.numel() else labels
+            brats = labels
         self.extra_launches = 1
         with torch.cuda.stream(s):
             if gt is not None:
@@ -146,6 +238,9 @@ class BratsCasePipeline:
                 self.extra_launches += 2 * 8 + 2
             s.synchronize()
         return out
+
+    def _guarded(self):
+        return any(eng.guard for eng in self._engines())
 
     def run_case(self, volume, gt=None, voxel_dims=(1.0, 1.0, 1.0), features=True):
         """One case start to finish: submit() + finish().  Returns a dict with the ensemble label volume in BraTS

@@ -67,25 +67,39 @@ def preprocess_case(data, use_mask_for_norm=True):
     cz, cy, cx = z1 - z0, y1 - y0, x1 - x0
     n = Z * Y * X
     # with the mask driving the normalisation the statistics run over the mask (all inside the box); without it upstream
-    # normalises over the whole cropped array
-    if use_mask_for_norm:
-        norm_mask = mask
-    else:
-        norm_mask = torch.zeros_like(mask)
-        norm_mask[z0:z1, y0:y1, x0:x1] = 1
-    sums = torch.empty(Cn * 3, dtype=torch.float64, device=dev)
-    L.check(lib.bsg_masked_channel_stats(_ptr(vol), Cn, n, _ptr(norm_mask), _ptr(sums), L.stream_ptr()))
-    s = sums.cpu().numpy().reshape(Cn, 3)
-    cnt = np.maximum(s[:, 2], 1.0)
-    mean = s[:, 0] / cnt
-    var = np.maximum(s[:, 1] / cnt - mean * mean, 0.0)
-    mean_std = torch.from_numpy(np.stack([mean, np.sqrt(var)], axis=1).astype(np.float32)).to(dev)
+    # normalises over the whole cropped array.  `use_mask_for_norm` may differ per channel (the plans hold a dict).
+    flags = [bool(use_mask_for_norm)] * Cn if isinstance(use_mask_for_norm, (bool, int)) else [bool(v) for v in use_mask_for_norm]
+    if len(flags) != Cn:
+        raise ValueError(f"use_mask_for_norm has {len(flags)} entries for {Cn} channels")
+    box_mask = None
+    if not all(flags):
+        box_mask = torch.zeros_like(mask)
+        box_mask[z0:z1, y0:y1, x0:x1] = 1
     out = torch.empty((Cn, cz, cy, cx), dtype=torch.float32, device=dev)
-    L.check(lib.bsg_crop_normalize(_ptr(vol), Cn, Z, Y, X, _ptr(norm_mask), z0, y0, x0, cz, cy, cx, _ptr(mean_std), _ptr(out),
-                                   None, L.stream_ptr()))
+    mean_std_all = np.zeros((Cn, 2), dtype=np.float32)
+    # channels sharing a setting go through one call each (all four BraTS modalities use the mask: one call)
+    runs, c0 = [], 0
+    for c in range(1, Cn + 1):
+        if c == Cn or flags[c] != flags[c0]:
+            runs.append((c0, c))
+            c0 = c
+    for (ca, cb) in runs:
+        norm_mask = mask if flags[ca] else box_mask
+        nc = cb - ca
+        sums = torch.empty(nc * 3, dtype=torch.float64, device=dev)
+        L.check(lib.bsg_masked_channel_stats(_ptr(vol[ca:cb]), nc, n, _ptr(norm_mask), _ptr(sums), L.stream_ptr()))
+        s = sums.cpu().numpy().reshape(nc, 3)
+        cnt = np.maximum(s[:, 2], 1.0)
+        mean = s[:, 0] / cnt
+        var = np.maximum(s[:, 1] / cnt - mean * mean, 0.0)
+        ms = np.stack([mean, np.sqrt(var)], axis=1).astype(np.float32)
+        mean_std_all[ca:cb] = ms
+        mean_std = torch.from_numpy(ms).to(dev)
+        L.check(lib.bsg_crop_normalize(_ptr(vol[ca:cb]), nc, Z, Y, X, _ptr(norm_mask), z0, y0, x0, cz, cy, cx, _ptr(mean_std),
+                                       _ptr(out[ca:cb]), None, L.stream_ptr()))
     mask_c = mask[z0:z1, y0:y1, x0:x1].contiguous()
     props = {"crop_bbox": bbox, "original_size_of_raw_data": np.array([Z, Y, X]),
-             "size_after_cropping": (cz, cy, cx), "nonzero_mask": mask_c, "channel_mean_std": mean_std.cpu().numpy()}
+             "size_after_cropping": (cz, cy, cx), "nonzero_mask": mask_c, "channel_mean_std": mean_std_all}
     return out, props
 
 

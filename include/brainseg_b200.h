@@ -77,10 +77,14 @@ typedef struct bsg_conv_desc {
                             suits it (stride-1 k3, Cout <= 64, W % 8 == 0, H % 16 == 0, D % (256/Cout_pad) == 0) */
     int pair;            /* tile kernel only: -1 auto, 0 off, 1 on when possible — launch as 2-CTA clusters whose CTAs work
                             on neighbouring tiles in lock-step and share every weight stage through TMA multicast */
+    int* overflow;       /* device int or NULL: set to 1 when a value stored as fp16 (out_f16) left the fp16 range
+                            (|x| > 65504): the caller's cue to re-plan the network in bf16 */
 } bsg_conv_desc;
 
 typedef struct bsg_conv_plan bsg_conv_plan;
 
+/* sizeof(bsg_conv_desc) as the library was compiled: lets a binding check its own struct layout. */
+size_t bsg_conv_desc_size(void);
 int bsg_conv_plan_create(const bsg_conv_desc* desc, bsg_conv_plan** plan);
 int bsg_conv_plan_run(const bsg_conv_plan* plan, void* stream);
 void bsg_conv_plan_destroy(bsg_conv_plan* plan);
@@ -265,6 +269,34 @@ int bsg_head_tta_accumulate(const void* feat16, int feat_f16, int cfeat, int cto
  * each be NULL. */
 int bsg_finalize(const float* const* acc_list_host, int K, const float* wsum, int ncls, size_t nvox, int mode,
                  const int* order_host, float* probs, uint8_t* seg, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Multi-GPU: the (tile, mirror) work items of ONE case sharded over R GPUs (BASELINE configs[2]; the per-model predict
+ * calls run_brats2021_inference_singlethread.py:97-106,113-124 are what is split).  Every rank accumulates its share
+ * into a private fp32 accumulator [ncls][nvox]; the exchange step is one of:
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* Peer-memory route — reduce over ranks + bsg_finalize in ONE kernel.  The calling rank owns the voxel range
+ * [v0, v0 + nv): it reads that range of all K*R accumulators (acc_table_dev: DEVICE array [K][R] of device pointers,
+ * R-1 of every R of them peer memory mapped over NVLink), sums over ranks in rank order, divides by wsum (local,
+ * geometry-only), averages the K folds, decides (mode / order_host as bsg_finalize) and stores the uint8 labels of the
+ * range into each of the nseg label volumes of seg_table_dev (DEVICE array of device pointers: every rank's label
+ * volume, so that all ranks end up with the whole volume, or just the local one).  nvox, v0, nv multiples of 4.
+ * The caller orders the ranks around the call (a stream-ordered barrier before: all accumulators complete; after: all
+ * slabs written) — e.g. two tiny NCCL all-reduces. */
+int bsg_finalize_peer(const float* const* acc_table_dev, int K, int R, const float* wsum, int ncls, size_t nvox, size_t v0,
+                      size_t nv, int mode, const int* order_host, uint8_t* const* seg_table_dev, int nseg, void* stream);
+/* cudaDeviceEnablePeerAccess(current -> peer_device), idempotent. */
+int bsg_enable_peer_access(int peer_device);
+
+/* NCCL route — `ncclAllReduce(sum)` (root < 0) or `ncclReduce(sum)` to `root` of the fp32 accumulator in place, over
+ * a communicator the library owns: rank 0 calls bsg_nccl_unique_id (128 bytes, host), ships the id to the other ranks
+ * by any means (torch.distributed broadcast), every rank calls bsg_nccl_comm_create.  libnccl.so.2 is resolved with
+ * dlopen at first use (inside a PyTorch process: the copy torch loaded). */
+int bsg_nccl_unique_id(void* id128_host);
+int bsg_nccl_comm_create(const void* id128_host, int nranks, int rank, void** comm_out);
+int bsg_nccl_reduce_accumulator(void* comm, float* acc, size_t count, int root, void* stream);
+int bsg_nccl_comm_destroy(void* comm);
 
 #ifdef __cplusplus
 }

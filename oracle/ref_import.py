@@ -123,18 +123,4 @@ def build_reference_unet(variant="bn", base=32, num_pool=5, in_ch=4, num_classes
     return net
 
 
-def randomize_norm_params(net, seed):
-    """Random-init leaves every norm at weight=1, bias=0, running stats (0,1): randomise them (seeded) so that BN
-    folding and the affine terms are actually exercised by the parity tests."""
-    g = torch.Generator().manual_seed(seed)
-    with torch.no_grad():
-        for m in net.modules():
-            if isinstance(m, (nn.BatchNorm3d, nn.GroupNorm, nn.InstanceNorm3d)):
-                if m.weight is not None:
-                    m.weight.copy_(1.0 + 0.2 * torch.randn(m.weight.shape, generator=g))
-                    m.bias.copy_(0.1 * torch.randn(m.bias.shape, generator=g))
-                if isinstance(m, nn.BatchNorm3d):
-                    m.running_mean.copy_(0.1 * torch.randn(m.running_mean.shape, generator=g))
-                    m.running_var.copy_(1.0 + 0.3 * torch.rand(m.running_var.shape, generator=g))
-            if isinstance(m, nn.Conv3d) and m.bias is not None:
-                m.bias.copy_(0.05 * torch.randn(m.bias.shape, generator=g))
+from synthetic_case import randomize_norm_params  # noqa: E402,F401  (shared with bench.py / tests)
