@@ -26,7 +26,7 @@ class ConvDesc(C.Structure):
         ("weights", C.c_void_p), ("bias", C.c_void_p),
         ("act", C.c_int), ("slope", C.c_float), ("stats", C.c_void_p), ("out_f16", C.c_int),
         ("use_khshift", C.c_int), ("max_ctas", C.c_int), ("in_f16", C.c_int), ("algo", C.c_int), ("pair", C.c_int),
-        ("overflow", C.c_void_p),
+        ("overflow", C.c_void_p), ("in_norm", C.c_void_p), ("in_norm_c", C.c_int),
     ]
 
 
@@ -76,6 +76,7 @@ _vp, _i, _sz, _u32, _f, _d = C.c_void_p, C.c_int, C.c_size_t, C.c_uint32, C.c_fl
 _EXTRA_SIGS = {
     "bsg_label_lut_u8": [_vp, _vp, _sz, C.c_char_p, _vp],
     "bsg_label_pair_round_u8": [_vp, _vp, _vp, _sz, C.c_char_p, _vp],
+    "bsg_label_pair_round_hist_u8": [_vp, _vp, _vp, _vp, _sz, C.c_char_p, _vp, _vp, _vp],
     "bsg_round_to_u8": [_vp, _i, _vp, _sz, _vp],
     "bsg_joint_hist_u8": [_vp, _vp, _sz, _vp, _vp, _vp],
     "bsg_ccl26_stats": [_vp, _i, _i, _i, _u32, _vp, _vp, _vp, _i, _vp, _sz, _vp],
@@ -95,6 +96,7 @@ _EXTRA_SIGS = {
     "bsg_masked_threshold_count": [_vp, _vp, _vp, _vp, _sz, _d, _d, _d, _vp, _vp],
     "bsg_gather_patch_tta": [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(_i), _i, _vp, _i, _i, _vp],
     "bsg_norm_finalize": [_vp, _i, _i, _i, _d, _f, _vp, _vp, _vp, _vp],
+    "bsg_norm_finalize_table": [_vp, _i, _i, _i, _d, _f, _vp, _vp, _f, _vp, _i, _i, _vp],
     "bsg_norm_apply_lrelu": [_vp, _sz, _i, _i, _i, _i, _vp, _f, _i, _i, _vp],
     "bsg_head_tta_accumulate": [_vp, _i, _i, _i, _i, _i, _i, C.POINTER(_i), _i, _f, C.POINTER(_f), C.POINTER(_f), _i, _i,
                                 _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _f, _vp],

@@ -38,12 +38,17 @@ struct BrickArgs {
     float* stats;
     int out_f16;
     int* overflow;  // device flag, set when a stored fp16 value left the fp16 range (null: no guard)
+    const float* in_norm;  // XF: [N][in_norm_c][4] (scale, shift, LeakyReLU slope, 0) applied to the INPUT in shared
+                           // memory (the producer's deferred norm pass); mapA then carries NaN out-of-bounds fill
+    int in_norm_c;         // channels per batch item of that table (the input buffer's slice width)
     int in_f16;  // 1: activations and weights are IEEE fp16 instead of bf16
 };
 
 constexpr int kBrickThreads = 224;  // 4 epilogue warps + activation producer + weight producer + MMA issuer
 // CC == 16 instantiations run a second epilogue warp group (see conv_brick.cu)
-constexpr int brick_threads(int cc) { return cc == 16 ? kBrickThreads + 128 : kBrickThreads; }
+// ... and so do the XF instantiations (warps 7-10: in-consumer norm transform)
+constexpr int brick_threads(int cc, bool xf = false) { return (cc == 16 || xf) ? kBrickThreads + 128 : kBrickThreads; }
+cudaError_t launch_conv_brick_xf(const BrickArgs& a, int cc, int nt, int grid, size_t smem_bytes, cudaStream_t stream);
 cudaError_t launch_conv_brick(const BrickArgs& a, int cc, int nt, int grid, size_t smem_bytes, cudaStream_t stream);
 size_t conv_brick_smem_bytes(const BrickArgs& a);
 

@@ -34,7 +34,7 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-               const uint32_t* box, int cc) {
+               const uint32_t* box, int cc, bool oob_nan = false) {
     auto fn = get_encode_fn();
     if (fn == nullptr) return set_error(BSG_ECUDA, "cuTensorMapEncodeTiled entry point not available");
     uint32_t estr[5] = {1, 1, 1, 1, 1};
@@ -45,7 +45,7 @@ int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dim
                     reinterpret_cast<const cuuint64_t*>(dims), reinterpret_cast<const cuuint64_t*>(strides_bytes),
                     reinterpret_cast<const cuuint32_t*>(box), reinterpret_cast<const cuuint32_t*>(estr),
                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    oob_nan ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA : CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return set_error(BSG_ECUDA,
                          "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu,%llu,%llu box %u,%u,%u cc %d",
@@ -77,6 +77,7 @@ int plan_brick(const bsg_conv_desc* d, bsg_conv_plan* p) {
     if (d->kind != BSG_CONV_K3 || d->stride != 1 || d->algo == 0) return 0;
     const int cout_pad = static_cast<int>(round_up(d->cout, 32));
     if (cout_pad != 32 && cout_pad != 64) return 0;
+    if (d->in_norm != nullptr && d->cin % 32 != 0) return 0;  // the in-consumer transform needs K chunks of >= 32 channels
     const int P = 256 / cout_pad;
     if (d->W % 8 != 0 || d->H % 16 != 0 || d->D % P != 0) return 0;
     BrickArgs& a = p->bargs;
@@ -115,7 +116,8 @@ int plan_brick(const bsg_conv_desc* d, bsg_conv_plan* p) {
                         static_cast<uint64_t>(d->D), static_cast<uint64_t>(d->N)};
     uint64_t str[4] = {ct * 2, ct * 2 * d->W, ct * 2 * d->W * d->H, ct * 2 * d->W * d->H * d->D};
     uint32_t box[5] = {static_cast<uint32_t>(cc), box_w, 18u, 1u, 1u};
-    int rc = encode_map(&a.mapA, d->in, 5, dims, str, box, cc);
+    // XF: padding arrives as NaN and is zeroed by the transform (after the norm, as the reference pads)
+    int rc = encode_map(&a.mapA, d->in, 5, dims, str, box, cc, d->in_norm != nullptr);
     if (rc != BSG_OK) return rc;
     // weights [27 taps (kd, kw, kh)][cout_pad][cin] seen as (cin, row, kh, kw, kd): a box of the 3 kd taps of one
     // (kh, kw) lands as [kd][cout_pad][cc] = the B operand of one N = 3*cout_pad MMA
@@ -141,6 +143,8 @@ int plan_brick(const bsg_conv_desc* d, bsg_conv_plan* p) {
     a.out_f16 = d->out_f16;
     a.in_f16 = d->in_f16;
     a.overflow = d->overflow;
+    a.in_norm = d->in_norm;
+    a.in_norm_c = d->in_norm_c;
 
     p->brick = 1;
     p->brick_cc = cc;
@@ -211,6 +215,11 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
             *out_plan = p;
             return BSG_OK;
         }
+    }
+    if (d->in_norm != nullptr) {
+        delete p;
+        return set_error(BSG_EINVAL, "in_norm: the in-consumer norm transform exists for the brick kernel only (stride-1 k3, "
+                                     "Cout <= 64, Cin %% 32 == 0, W %% 8 == 0, H %% 16 == 0)");
     }
     ConvArgs& a = p->args;
     memset(&a, 0, sizeof(a));
@@ -431,7 +440,7 @@ int bsg_conv_plan_info(const bsg_conv_plan* plan, bsg_conv_info* info) {
         info->n_ntiles = 1;
         info->cc = plan->brick_cc;
         info->nstages = b.nstages;
-        info->khshift = 2 + b.nslabbuf + (b.kwf ? 10 : 0);  /* brick marker: 2 + slab buffers (+10: kw-fused) */
+        info->khshift = 2 + b.nslabbuf + (b.kwf ? 10 : 0) + (b.in_norm ? 1000 : 0);  /* brick marker: 2 + slab buffers (+10: kw-fused, +1000: in-consumer norm) */
         info->grid = plan->grid;
         info->smem_bytes = plan->smem_bytes;
         info->flops = plan->flops;

@@ -47,11 +47,23 @@ __global__ void __launch_bounds__(kThreads) peer_finalize_kernel(const PeerFinal
             if (k < fp.ncls) {
                 float s[4] = {0.f, 0.f, 0.f, 0.f};
                 for (int j = 0; j < fp.K; ++j) {
-                    // sum over ranks in rank order: the same fp32 additions on every rank and in every run
-                    float4 a = __ldg(reinterpret_cast<const float4*>(s_acc[j * fp.R] + k * nvox + i));
-                    for (int r = 1; r < fp.R; ++r) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(s_acc[j * fp.R + r] + k * nvox + i));
-                        a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+                    // sum over ranks in rank order: the same fp32 additions on every rank and in every run.  All (up
+                    // to 8 per batch) peer loads of a class are in flight before the first addition.
+                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int r0 = 0; r0 < fp.R; r0 += 8) {
+                        float4 b[8];
+#pragma unroll
+                        for (int r = 0; r < 8; ++r)
+                            if (r0 + r < fp.R)
+                                b[r] = __ldg(reinterpret_cast<const float4*>(s_acc[j * fp.R + r0 + r] + k * nvox + i));
+#pragma unroll
+                        for (int r = 0; r < 8; ++r)
+                            if (r0 + r < fp.R) {
+                                if (r0 + r == 0)
+                                    a = b[r];
+                                else
+                                    a.x += b[r].x, a.y += b[r].y, a.z += b[r].z, a.w += b[r].w;
+                            }
                     }
                     const float q[4] = {__fdiv_rn(a.x, wv.x), __fdiv_rn(a.y, wv.y), __fdiv_rn(a.z, wv.z),
                                         __fdiv_rn(a.w, wv.w)};

@@ -144,6 +144,80 @@ __global__ void __launch_bounds__(kThreads) joint_hist_kernel(const uint8_t* __r
     if (threadIdx.x == 0 && sbad) atomicAdd(bad, static_cast<unsigned long long>(sbad));
 }
 
+// ---------------------------------------------------------------------------------------------- fused label pass
+// out = post[round_half_even((a + b) / 2)] (run_brats2021_inference_singlethread.py:305 + convert_labels_to_brats.py)
+// AND the joint histogram of (out, gt) (evaluate_segmentation.py:25-32) in ONE read of the three label volumes: the
+// three separate passes are launch-bound at BraTS size (24 us each for 18-27 MB).  Two 16-byte groups per thread and
+// step (six independent loads in flight).
+__global__ void __launch_bounds__(kThreads) ensemble_hist_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
+                                                                 const uint8_t* __restrict__ gt, uint8_t* __restrict__ out,
+                                                                 size_t n, const Lut256 post,
+                                                                 unsigned long long* __restrict__ hist,
+                                                                 unsigned long long* __restrict__ bad) {
+    __shared__ uint8_t s[256];
+    __shared__ unsigned int sh[256];
+    __shared__ unsigned int sbad;
+    s[threadIdx.x] = post.v[threadIdx.x];
+    sh[threadIdx.x] = 0;
+    if (threadIdx.x == 0) sbad = 0;
+    __syncthreads();
+    unsigned int zero_pairs = 0, nbad = 0;
+    auto tally = [&](uint32_t p, uint32_t g) {
+        if ((p | g) == 0u)
+            ++zero_pairs;
+        else if ((p | g) < 16u)
+            atomicAdd(&sh[p * 16 + g], 1u);
+        else
+            ++nbad;
+    };
+    auto group = [&](const uint4 xa, const uint4 xb, const uint4 xg, size_t i) {
+        const uint32_t wa[4] = {xa.x, xa.y, xa.z, xa.w}, wb[4] = {xb.x, xb.y, xb.z, xb.w}, wg[4] = {xg.x, xg.y, xg.z, xg.w};
+        uint32_t wo[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t o = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                o |= static_cast<uint32_t>(s[mean_half_even((wa[k] >> (8 * j)) & 255u, (wb[k] >> (8 * j)) & 255u)])
+                     << (8 * j);
+            wo[k] = o;
+            if ((o | wg[k]) == 0u) {
+                zero_pairs += 4;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) tally((o >> (8 * j)) & 255u, (wg[k] >> (8 * j)) & 255u);
+            }
+        }
+        reinterpret_cast<uint4*>(out)[i] = make_uint4(wo[0], wo[1], wo[2], wo[3]);
+    };
+    const size_t nvec = n / 16;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    const uint4 *a4 = reinterpret_cast<const uint4*>(a), *b4 = reinterpret_cast<const uint4*>(b),
+                *g4 = reinterpret_cast<const uint4*>(gt);
+    size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    for (; i + stride < nvec; i += 2 * stride) {
+        const uint4 xa0 = ld_stream(a4 + i), xb0 = ld_stream(b4 + i), xg0 = ld_stream(g4 + i);
+        const uint4 xa1 = ld_stream(a4 + i + stride), xb1 = ld_stream(b4 + i + stride), xg1 = ld_stream(g4 + i + stride);
+        group(xa0, xb0, xg0, i);
+        group(xa1, xb1, xg1, i + stride);
+    }
+    if (i < nvec) group(ld_stream(a4 + i), ld_stream(b4 + i), ld_stream(g4 + i), i);
+    for (size_t t = nvec * 16 + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += stride) {
+        const uint32_t o = s[mean_half_even(a[t], b[t])];
+        out[t] = static_cast<uint8_t>(o);
+        tally(o, gt[t]);
+    }
+    zero_pairs = __reduce_add_sync(0xffffffffu, zero_pairs);
+    nbad = __reduce_add_sync(0xffffffffu, nbad);
+    if ((threadIdx.x & 31) == 0) {
+        if (zero_pairs) atomicAdd(&sh[0], zero_pairs);
+        if (nbad) atomicAdd(&sbad, nbad);
+    }
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], static_cast<unsigned long long>(sh[threadIdx.x]));
+    if (threadIdx.x == 0 && sbad) atomicAdd(bad, static_cast<unsigned long long>(sbad));
+}
+
 // ---------------------------------------------------------------------------------------------- CCL (26-conn)
 // Foreground test: bit v of maskbits set <=> label value v (< 32) is foreground; labels >= 32 are background.
 __device__ __forceinline__ bool is_fg(uint8_t v, uint32_t maskbits) { return v < 32 && ((maskbits >> v) & 1u); }
@@ -596,6 +670,25 @@ int bsg_label_pair_round_u8(const uint8_t* a, const uint8_t* b, uint8_t* out, si
     for (int i = 0; i < 256; ++i) lut.v[i] = post_lut_host ? post_lut_host[i] : static_cast<uint8_t>(i);
     pair_round_kernel<<<grid_for(n / 16 + 1, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a, b, out, n,
                                                                                                           lut);
+    BSG_CUDA_OK(cudaGetLastError());
+    return BSG_OK;
+}
+
+int bsg_label_pair_round_hist_u8(const uint8_t* a, const uint8_t* b, const uint8_t* gt, uint8_t* out, size_t n,
+                                 const uint8_t* post_lut_host, unsigned long long* hist256, unsigned long long* bad,
+                                 void* stream) {
+    BSG_REQUIRE(a != nullptr && b != nullptr && gt != nullptr && out != nullptr && hist256 != nullptr && bad != nullptr,
+                "null argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    BSG_CUDA_OK(cudaMemsetAsync(hist256, 0, 256 * sizeof(unsigned long long), s));
+    BSG_CUDA_OK(cudaMemsetAsync(bad, 0, sizeof(unsigned long long), s));
+    if (n == 0) return BSG_OK;
+    BSG_REQUIRE(((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(gt) |
+                  reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+                "label volumes must be 16-byte aligned");
+    Lut256 lut;
+    for (int i = 0; i < 256; ++i) lut.v[i] = post_lut_host ? post_lut_host[i] : static_cast<uint8_t>(i);
+    ensemble_hist_kernel<<<grid_for(n / 32 + 1, kThreads, 8), kThreads, 0, s>>>(a, b, gt, out, n, lut, hist256, bad);
     BSG_CUDA_OK(cudaGetLastError());
     return BSG_OK;
 }

@@ -80,6 +80,10 @@ class UNetEngine:
         self.guard = bool(self.f16) and os.environ.get("BSG_OVERFLOW_GUARD", "1") != "0"
         self._overflow = overflow_flag(self.device) if self.guard else None
         self._weight_slots = []  # (kind, module, packed tensors): reload_weights() re-packs into them in place
+        # InstanceNorm / GroupNorm blocks whose only consumer is a brick-kernel conv hand their normalise + LeakyReLU to
+        # that conv (applied in shared memory on the way to the tensor core) instead of a separate HBM pass
+        self.fuse_norm = os.environ.get("BSG_FUSE_NORM", "1") != "0"
+        self.fused_norms = 0
         self.flops_algo = 0.0    # algorithmic FLOPs on the real channel counts (the 4 input channels are padded to 16)
         self.act_dtype = torch.float16 if self.f16 else torch.bfloat16
         self.steps = []       # callables, in launch order
@@ -128,7 +132,11 @@ class UNetEngine:
     def _overflow_slot(self):
         return self._overflow.data_ptr() if self._overflow is not None else None
 
-    def _add_block(self, blk, src, dst, spatial_in, defer_apply=False):
+    def _add_block(self, blk, src, dst, spatial_in, defer_apply=False, claim=None):
+        """One ConvDropoutNormNonlin block.  `claim`: the norm state of the block that produced `src`, when this conv is
+        its only consumer — if the planner can run this conv with the in-consumer transform (brick kernel), the
+        producer's normalise + LeakyReLU pass is dropped and its statistics go to this conv's input table instead.
+        Returns the block's own norm state (None for BatchNorm-folded blocks)."""
         conv, norm = blk.conv, blk.instnorm
         stride = int(conv.stride[0])
         slope = float(blk.lrelu.negative_slope)
@@ -145,22 +153,38 @@ class UNetEngine:
         self.keep += [wp, bp]
         self._weight_slots.append(("block", blk, cin_pad, (wp, bp, gamma, beta)))
         d, h, wd = spatial_in
-        plan = L.ConvPlan(kind=L.BSG_CONV_K3, stride=stride, N=self.batch, D=d, H=h, W=wd, cin=cin_pad,
-                          in_ptr=src.ptr(), in_ctot=src.ctot, cout=cout, out_ptr=dst.buf.data_ptr(),
-                          out_ctot=dst.ctot, out_coff=dst.coff, weights=wp.data_ptr(), bias=bp.data_ptr(), act=act,
-                          slope=slope, stats=stats.data_ptr() if stats is not None else None,
-                          out_f16=self.f16, in_f16=self.f16, use_khshift=-1,
-                          max_ctas=0, overflow=self._overflow_slot())
+        desc = dict(kind=L.BSG_CONV_K3, stride=stride, N=self.batch, D=d, H=h, W=wd, cin=cin_pad,
+                    in_ptr=src.ptr(), in_ctot=src.ctot, cout=cout, out_ptr=dst.buf.data_ptr(),
+                    out_ctot=dst.ctot, out_coff=dst.coff, weights=wp.data_ptr(), bias=bp.data_ptr(), act=act,
+                    slope=slope, stats=stats.data_ptr() if stats is not None else None,
+                    out_f16=self.f16, in_f16=self.f16, use_khshift=-1,
+                    max_ctas=0, overflow=self._overflow_slot())
+        plan = None
+        if claim is not None and self.fuse_norm and src.coff == 0 and src.c == src.ctot:
+            table = torch.zeros(self.batch, cin_pad, 4, dtype=torch.float32, device=self.device)
+            try:
+                plan = L.ConvPlan(in_norm=table.data_ptr(), in_norm_c=cin_pad, **desc)
+            except L.BsgError:
+                plan = None  # layer does not suit the brick kernel: the producer keeps its separate pass
+            if plan is not None:
+                claim["table"] = table
+                claim["apply"] = False
+                self.keep.append(table)
+                self.launches_per_forward -= 1
+                self.fused_norms += 1
+        if plan is None:
+            plan = L.ConvPlan(**desc)
         self.flops += plan.info().flops
         so_ = tuple(s // stride for s in spatial_in)
         self.flops_algo += 2.0 * 27 * conv.in_channels * cout * so_[0] * so_[1] * so_[2] * self.batch
         self._note(f"conv3 s{stride} {cin_pad}->{cout} @{'x'.join(map(str, spatial_in))}"
-                   f"{' +norm' if stats is not None else ''}", plan)
+                   f"{' +norm' if stats is not None else ''}{' (input normalised in shared memory)' if plan.desc.in_norm else ''}",
+                   plan)
         lib = L.lib()
         if stats is None:
             self.steps.append(plan.run)
             self.launches_per_forward += 1
-            return
+            return None
         groups = norm.num_groups if isinstance(norm, nn.GroupNorm) else 0
         ss = torch.empty(self.batch, cout, 2, dtype=torch.float32, device=self.device)
         self.keep += [stats, ss, gamma, beta]
@@ -170,7 +194,11 @@ class UNetEngine:
         gp = _ptr(gamma) if gamma is not None else None
         bp2 = _ptr(beta) if beta is not None else None
 
-        def run(stream=None, plan=plan, stats=stats, ss=ss):
+        # apply: this block runs its own normalise + LeakyReLU pass; table: the consuming conv applies it on the fly
+        # (set by the consumer's _add_block when it claims this block), the statistics then go to its input table
+        state = {"apply": not defer_apply, "table": None}
+
+        def run(stream=None, plan=plan, stats=stats, ss=ss, state=state):
             sp = L.stream_ptr(stream)
             if not self._in_run:
                 stats.zero_()
@@ -179,8 +207,12 @@ class UNetEngine:
                 ev = torch.cuda.Event(enable_timing=True)
                 ev.record()
                 self.sub_events.append(ev)
+            if state["table"] is not None:
+                L.check(lib.bsg_norm_finalize_table(_ptr(stats), self.batch, cout, groups, float(vox), eps, gp, bp2, slope,
+                                                    _ptr(state["table"]), cout, 0, sp))
+                return
             L.check(lib.bsg_norm_finalize(_ptr(stats), self.batch, cout, groups, float(vox), eps, gp, bp2, _ptr(ss), sp))
-            if not defer_apply:
+            if state["apply"]:
                 L.check(lib.bsg_norm_apply_lrelu(_ptr(dst.buf), vox, self.batch, cout, dst.ctot, dst.coff, _ptr(ss), slope,
                                                  self.f16, self.f16, sp))
 
@@ -188,6 +220,8 @@ class UNetEngine:
         self.launches_per_forward += 2 if defer_apply else 3  # conv, norm_finalize(, norm_apply): the library's own kernels
         if defer_apply:  # the consumer (head kernel / forward_logits) normalises on the fly
             self.final_norm = (ss, slope)
+            return None
+        return state
 
     def _add_tu(self, tu, src, dst, spatial_in):
         w = tu.weight.detach().to(self.device, torch.float32)
@@ -225,6 +259,7 @@ class UNetEngine:
         for d in range(num_pool + 1):
             stage = net.conv_blocks_context[d]
             blocks = list(stage.blocks) if d < num_pool else list(stage[0].blocks) + list(stage[1].blocks)
+            prev = None  # norm state of the previous block of this stage: its output has exactly one consumer
             for i, blk in enumerate(blocks):
                 cout, stride = blk.conv.out_channels, int(blk.conv.stride[0])
                 if cout % 16:
@@ -234,9 +269,13 @@ class UNetEngine:
                     cat = self._alloc(out_spatial, 2 * cout)  # [0,C): transposed-conv output, [C,2C): this skip
                     cats.append(cat)
                     dst = _Act(cat, cout, cout)
+                    is_skip = True
                 else:
                     dst = _Act(self._alloc(out_spatial, cout), 0, cout)
-                self._add_block(blk, cur, dst, spatial)
+                    is_skip = False
+                prev = self._add_block(blk, cur, dst, spatial, claim=prev if i > 0 else None)
+                if is_skip:
+                    prev = None  # a skip tensor also feeds the decoder: it must be materialised
                 cur, spatial = dst, out_spatial
         for u in range(num_pool):
             cat = cats[-(u + 1)]
@@ -249,11 +288,12 @@ class UNetEngine:
             cur = _Act(cat, 0, 2 * cskip)
             loc = net.conv_blocks_localization[u]
             blks = list(loc[0].blocks) + list(loc[1].blocks)
+            prev = None
             for j, blk in enumerate(blks):
                 dst = _Act(self._alloc(spatial, blk.conv.out_channels), 0, blk.conv.out_channels)
                 # the very last block's norm + LeakyReLU is applied by its only consumer, the head
                 last = (u == num_pool - 1) and (j == len(blks) - 1) and blk.conv.out_channels <= 64
-                self._add_block(blk, cur, dst, spatial, defer_apply=last)
+                prev = self._add_block(blk, cur, dst, spatial, defer_apply=last, claim=prev if j > 0 else None)
                 cur = dst
         self.features = cur
         self._head = net.seg_outputs[num_pool - 1]

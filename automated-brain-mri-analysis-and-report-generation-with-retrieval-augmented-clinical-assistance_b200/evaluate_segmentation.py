@@ -14,11 +14,13 @@ WT_LABELS, TC_LABELS = (1, 2, 3), (1, 3)  # evaluate_segmentation.py:130-131, :1
 class LabelPairHistogram:
     """Joint histogram of (prediction, ground truth), computed once on the device."""
 
-    def __init__(self, pred, gt):
-        p, g = V.as_label_volume(pred), V.as_label_volume(gt)
-        if p.shape != g.shape:
-            raise ValueError("shape mismatch")
-        self.hist = V.joint_hist(p, g)
+    def __init__(self, pred, gt, hist=None):
+        if hist is None:
+            p, g = V.as_label_volume(pred), V.as_label_volume(gt)
+            if p.shape != g.shape:
+                raise ValueError("shape mismatch")
+            hist = V.joint_hist(p, g)
+        self.hist = hist  # 16 x 16 int64, hist[p, g]; labels >= 16 are outside the histogram (V.joint_hist raises)
         self.total = int(self.hist.sum())
 
     def counts(self, labels):
@@ -63,15 +65,18 @@ def calculate_metrics_binary(pred_mask, gt_mask, _counts=None):
     return {"dice": m["dice"], "iou": m["iou"], "sensitivity": m["sensitivity"]}
 
 
-def evaluate_arrays(pred_data, gt_data):
+def evaluate_arrays(pred_data, gt_data, _hist=None):
     """The arithmetic of evaluate_segmentation() (:84-162) on in-memory label volumes.
 
     Returns None on a shape mismatch like the reference (:78-81), else
-    {"labels": {label: metrics}, "wt": ..., "tc": ..., "et": metrics | None, "mean_dice": ...}."""
+    {"labels": {label: metrics}, "wt": ..., "tc": ..., "et": metrics | None, "mean_dice": ...}.
+    Label values must lie in 0..15 (the joint histogram's range; BraTS uses 0..4) — larger labels raise BsgError,
+    where the reference would compare the raw values.  `_hist`: a joint histogram already computed on the device
+    (pipeline: fused with the ensemble pass)."""
     if tuple(pred_data.shape) != tuple(gt_data.shape):
         print("\n⚠️  WARNING: Shape mismatch! Attempting to resize...")
         return None
-    h = LabelPairHistogram(pred_data, gt_data)
+    h = LabelPairHistogram(pred_data, gt_data, hist=_hist)
     all_metrics = {}
     for label in h.present_labels():
         if label == 0:

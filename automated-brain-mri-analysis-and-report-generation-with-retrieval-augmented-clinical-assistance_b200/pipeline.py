@@ -166,18 +166,23 @@ class BratsCasePipeline:
                     brats = V.label_lut(seg, self.lut)
             else:
                 brats = V.label_lut(seg, self.lut)
-        elif len(segs) == 2:
-            brats = V.ensemble_round(segs[0], segs[1], post_lut=self.lut)  # ensemble + remap in one pass
-        else:
+        elif len(segs) != 2:
             raise NotImplementedError("the reference ensembles exactly two models")
-        gt_dev = None
+        gt_dev, hist_buf = None, None
         if gt is not None:
             gt_dev = V.as_label_volume(gt)
-            if tuple(gt_dev.shape) != tuple(brats.shape):
+            if tuple(gt_dev.shape) != tuple(segs[0].shape):
                 gt_dev = gt  # let evaluate_arrays report the mismatch the way the reference does
+        if len(segs) == 2:
+            if torch.is_tensor(gt_dev) and gt_dev.is_cuda and gt_dev.dtype == torch.uint8 and tuple(gt_dev.shape) == tuple(segs[0].shape):
+                # ensemble + remap + Dice bins against the ground truth in one pass over the label volumes
+                brats, hist_buf = V.ensemble_remap_hist(segs[0], segs[1], gt_dev, post_lut=self.lut)
+            else:
+                brats = V.ensemble_round(segs[0], segs[1], post_lut=self.lut)  # ensemble + remap in one pass
         done = torch.cuda.Event()
         done.record()
-        return {"vol": vol, "segs": segs, "brats": brats, "gt": gt_dev, "gt_in": gt, "done": done, "gen": self._gen}
+        return {"vol": vol, "segs": segs, "brats": brats, "gt": gt_dev, "gt_in": gt, "done": done, "gen": self._gen,
+                "hist": hist_buf}
 
     def finish(self, pending, voxel_dims=(1.0, 1.0, 1.0), features=True, post=True, labels=None):
         """Post-processing of a submitted case (Dice, components, morphology) on the pipeline's second stream.
@@ -224,8 +229,12 @@ class BratsCasePipeline:
         self.extra_launches = 1
         with torch.cuda.stream(s):
             if gt is not None:
-                out["evaluation"] = EV.evaluate_arrays(brats, gt)
-                self.extra_launches += 1
+                hist = None
+                if pending.get("hist") is not None and labels is None:
+                    pending["hist"].record_stream(s)
+                    hist = V.joint_hist_from_buffer(pending["hist"])
+                out["evaluation"] = EV.evaluate_arrays(brats, gt, _hist=hist)
+                self.extra_launches += 0 if hist is not None else 1
             if features:
                 lv = FU.LabelVolume(brats)
                 masks = FU.get_tumor_masks(lv)

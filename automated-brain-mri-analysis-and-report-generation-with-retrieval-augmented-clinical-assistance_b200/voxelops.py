@@ -81,6 +81,26 @@ def ensemble_round(a, b, post_lut=None):
     return out
 
 
+def ensemble_remap_hist(a, b, gt, post_lut=None):
+    """ensemble_round(a, b, post_lut) plus the joint histogram of the result against `gt`, one pass.  Returns
+    (labels, hist_buf): hist_buf is the DEVICE buffer (257 int64: 16x16 bins + the count of labels >= 16) —
+    joint_hist_from_buffer() reads it back when the metrics are wanted."""
+    assert a.shape == b.shape == gt.shape
+    out = torch.empty_like(a)
+    post = None if post_lut is None else np.ascontiguousarray(np.asarray(post_lut, dtype=np.uint8)).tobytes()
+    buf = torch.empty(257, dtype=torch.int64, device=a.device)
+    L.check(L.lib().bsg_label_pair_round_hist_u8(_ptr(a), _ptr(b), _ptr(gt), _ptr(out), a.numel(), post, _ptr(buf),
+                                                 C.c_void_p(buf.data_ptr() + 2048), L.stream_ptr()))
+    return out, buf
+
+
+def joint_hist_from_buffer(buf):
+    h = buf.cpu().numpy()
+    if h[256] != 0:
+        raise L.BsgError(f"{int(h[256])} voxels carry labels >= 16; the Dice histogram supports labels 0..15")
+    return h[:256].reshape(16, 16).copy()
+
+
 def joint_hist(pred, gt):
     """16x16 int64 joint label histogram hist[p, g]; raises on labels >= 16."""
     assert pred.shape == gt.shape

@@ -79,6 +79,13 @@ typedef struct bsg_conv_desc {
                             on neighbouring tiles in lock-step and share every weight stage through TMA multicast */
     int* overflow;       /* device int or NULL: set to 1 when a value stored as fp16 (out_f16) left the fp16 range
                             (|x| > 65504): the caller's cue to re-plan the network in bf16 */
+    const float* in_norm; /* NULL, or fp32 [N][in_norm_c][4] = (scale, shift, LeakyReLU slope, 0) per batch item and INPUT
+                            channel: `in` is then the RAW output of an InstanceNorm / GroupNorm block whose
+                            bsg_norm_apply_lrelu pass was skipped, and the conv applies y = lrelu(x*scale + shift) to
+                            its input on the fly, in shared memory (generic_UNet.py:68-72 of the producing block;
+                            rows written by bsg_norm_finalize_table).  Brick kernel only: bsg_conv_plan_create returns
+                            BSG_EINVAL when the layer does not qualify and the caller keeps the separate pass. */
+    int in_norm_c;       /* channels per batch item of the in_norm table (>= cin) */
 } bsg_conv_desc;
 
 typedef struct bsg_conv_plan bsg_conv_plan;
@@ -109,6 +116,13 @@ int bsg_label_lut_u8(const uint8_t* in, uint8_t* out, size_t n, const uint8_t* l
  * following label remap (post_lut_host: 256 host bytes, NULL = identity). */
 int bsg_label_pair_round_u8(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, const uint8_t* post_lut_host,
                             void* stream);
+
+/* bsg_label_pair_round_u8 and bsg_joint_hist_u8(out, gt) in ONE pass over the three label volumes: the two-model
+ * ensemble + remap (run_brats2021_inference_singlethread.py:305, convert_labels_to_brats.py:34-55) and the Dice bins of
+ * the result against a ground truth (evaluate_segmentation.py:25-32). */
+int bsg_label_pair_round_hist_u8(const uint8_t* a, const uint8_t* b, const uint8_t* gt, uint8_t* out, size_t n,
+                                 const uint8_t* post_lut_host, unsigned long long* hist256, unsigned long long* bad,
+                                 void* stream);
 
 /* np.round(x).astype(np.uint8) (convert_labels_to_brats.py:37, feature_extraction/utils.py:169);
  * dtype 0 = float32, 1 = float64. */
@@ -240,6 +254,11 @@ int bsg_gather_patch_tta(const float* vol, int C, int Z, int Y, int X, int z0, i
  * y = x*scale + shift == (x-mean)*rsqrt(var+eps)*gamma + beta.  groups = 0: per channel; > 0: GroupNorm. */
 int bsg_norm_finalize(const float* stats, int N, int C, int groups, double count, float eps, const float* gamma,
                       const float* beta, float* scale_shift, void* stream);
+/* Same statistics -> rows [coff, coff+C) of a consumer-side table [N][ctot][4] = (scale, shift, slope, 0): the input
+ * transform of the conv that consumes the raw tensor (bsg_conv_desc.in_norm).  Channels of the table that belong to an
+ * un-normalised producer (the transposed-conv half of a concat buffer) are preset by the caller to (1, 0, 1, 0). */
+int bsg_norm_finalize_table(const float* stats, int N, int C, int groups, double count, float eps, const float* gamma,
+                            const float* beta, float slope, float* table, int ctot, int coff, void* stream);
 /* In place on channels [coff, coff+C) of a (N, voxels, ctot) 16-bit buffer: x <- LeakyReLU(x*scale + shift), read as
  * fp16 when in_f16 = 1 (the conv stored its raw output as fp16, bsg_conv_desc.out_f16) else bf16, written back as fp16
  * when out_f16 = 1 else bf16. */

@@ -1,0 +1,109 @@
+"""Conv-kernel level parity (through the C ABI, bsg_conv_plan_*) against a plain PyTorch fp32 reference of the same op
+on the same 16-bit-rounded operands: the in-consumer norm transform of the brick kernel (every instantiation: K chunk
+32 / 64 channels x N tile 32 / 64 x streamed / resident weight slabs x with / without output statistics), the fp16
+range flag, and the tile-kernel variants round 2 added.  Reference op: ConvDropoutNormNonlin.forward,
+model_architecture/generic_UNet.py:68-72 (norm + LeakyReLU of the producing block, then the consuming Conv3d)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup():
+    from brainseg_b200 import _lib as L
+    from brainseg_b200 import packing as P
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return L, P, torch.device("cuda", torch.cuda.current_device())
+
+
+def _conv_case(cin, cout, N, D, H, W, stats, f16=True, in_norm=False, seed=0, scale_in=1.0, scale_w=1.0, want_flag=False):
+    L, P, dev = _setup()
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    dt = torch.float16 if f16 else torch.bfloat16
+    x = (torch.randn(N, cin, D, H, W, generator=g) * scale_in).to(dt)
+    xb = x.permute(0, 2, 3, 4, 1).contiguous().to(dev)
+    w = torch.randn(cout, cin, 3, 3, 3, generator=g) / (27 * cin) ** 0.5 * scale_w
+    wp = P.pack_conv3_weight(w.to(dev), cin, dt)
+    b = torch.randn(cout, generator=g).to(dev)
+    bp = P.pad_bias(b, cout).to(dev)
+    out = torch.zeros(N, D, H, W, cout, dtype=dt, device=dev)
+    st = torch.zeros(N, cout, 2, dtype=torch.float32, device=dev) if stats else None
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    kw = dict(kind=L.BSG_CONV_K3, stride=1, N=N, D=D, H=H, W=W, cin=cin, in_ptr=xb.data_ptr(), in_ctot=cin, cout=cout,
+              out_ptr=out.data_ptr(), out_ctot=cout, out_coff=0, weights=wp.data_ptr(), bias=bp.data_ptr(), act=0 if stats else 1,
+              slope=0.01, stats=st.data_ptr() if stats else None, use_khshift=-1, max_ctas=0, in_f16=int(f16), out_f16=int(f16),
+              overflow=flag.data_ptr() if want_flag else None)
+    xr = x.float().to(dev)
+    if in_norm:
+        table = torch.zeros(N, cin, 4, device=dev)
+        table[..., 0] = 0.5 + torch.rand(N, cin, generator=g).to(dev)       # scale
+        table[..., 1] = 0.5 * torch.randn(N, cin, generator=g).to(dev)      # shift
+        table[..., 2] = 0.01                                                # slope
+        table[:, : cin // 4, 2] = 1.0                                       # identity channels (slope 1) as a concat half has
+        kw.update(in_norm=table.data_ptr(), in_norm_c=cin)
+        y = xr * table[..., 0].view(N, cin, 1, 1, 1) + table[..., 1].view(N, cin, 1, 1, 1)
+        y = torch.where(y > 0, y, y * table[..., 2].view(N, cin, 1, 1, 1))
+        xr = y.to(dt).float()  # the transform writes the stage back in the activation dtype
+    plan = L.ConvPlan(**kw)
+    info = plan.info()
+    plan.run()
+    plan.run()  # idempotent on the input (the transform works on the shared-memory copy only)
+    torch.cuda.synchronize()
+    ref = F.conv3d(xr, w.to(dt).float().to(dev), b, padding=1)
+    pre = ref
+    if not stats:
+        ref = F.leaky_relu(ref, 0.01)
+    got = out.permute(0, 4, 1, 2, 3).float()
+    return L, info, got, ref, pre, st, flag
+
+
+@pytest.mark.parametrize("cin,cout,D,H,W,stats", [
+    (32, 32, 16, 16, 16, False),   # CC 32, NT 32, resident slabs (kw-fused boxes)
+    (32, 32, 8, 32, 24, True),
+    (64, 32, 16, 16, 16, False),   # CC 64, NT 32, resident
+    (64, 32, 8, 16, 32, True),
+    (32, 64, 8, 16, 16, False),    # CC 32, NT 64, resident
+    (32, 64, 4, 32, 16, True),
+    (64, 64, 8, 16, 16, False),    # CC 64, NT 64, streamed slabs (three kw-shifted boxes)
+    (64, 64, 4, 16, 24, True),
+    (128, 64, 4, 16, 16, True),    # two K chunks, streamed
+    (128, 32, 8, 16, 16, False),   # two K chunks, N tile 32, streamed
+])
+def test_brick_conv_with_in_consumer_norm(cin, cout, D, H, W, stats):
+    """y = conv3d(lrelu(x * scale[n, c] + shift[n, c])) with the affine + LeakyReLU applied to the activation boxes in
+    shared memory; zero padding is padding of the NORMALISED tensor (NaN out-of-bounds fill -> 0), batch items carry
+    different tables, and a channel range with slope 1 / identity passes through untouched."""
+    L, info, got, ref, pre, st, _ = _conv_case(cin, cout, 3, D, H, W, stats, in_norm=True, seed=cin + cout + D)
+    assert info.khshift >= 1000, "planner did not pick the in-consumer transform"
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    print(f"{cin}->{cout} @{D}x{H}x{W} stats={stats}: plan marker {info.khshift}, cc {info.cc}, max err {err:.4g} (ref max {scale:.3g})")
+    assert torch.isfinite(got).all()
+    assert err <= 3e-3 * max(scale, 1.0)
+    if stats:
+        s_ref = torch.stack([pre.sum(dim=(2, 3, 4)), (pre * pre).sum(dim=(2, 3, 4))], dim=-1)
+        assert ((st / 2 - s_ref).abs() / (s_ref.abs() + 1.0)).max().item() < 1e-3  # two runs accumulated
+
+
+def test_in_consumer_norm_is_refused_outside_the_brick_kernel():
+    L, P, dev = _setup()
+    x = torch.zeros(1, 8, 8, 8, 128, dtype=torch.float16, device=dev)
+    out = torch.zeros(1, 8, 8, 8, 128, dtype=torch.float16, device=dev)
+    wp = torch.zeros(27, 128, 128, dtype=torch.float16, device=dev)
+    table = torch.zeros(1, 128, 4, device=dev)
+    with pytest.raises(L.BsgError):  # Cout 128 -> tile kernel: no transform there
+        L.ConvPlan(kind=L.BSG_CONV_K3, stride=1, N=1, D=8, H=8, W=8, cin=128, in_ptr=x.data_ptr(), in_ctot=128, cout=128,
+                   out_ptr=out.data_ptr(), out_ctot=128, out_coff=0, weights=wp.data_ptr(), bias=None, act=1, slope=0.01,
+                   stats=None, use_khshift=-1, max_ctas=0, in_f16=1, out_f16=1, in_norm=table.data_ptr(), in_norm_c=128)
+
+
+@pytest.mark.parametrize("cin,cout,shape", [(32, 32, (16, 16, 16)), (64, 128, (8, 16, 16)), (64, 64, (4, 16, 16))])
+def test_fp16_range_flag(cin, cout, shape):
+    """The epilogue raises the overflow flag iff a stored fp16 value left the fp16 range (brick and tile kernels)."""
+    D, H, W = shape
+    _, _, got, _, _, _, flag = _conv_case(cin, cout, 1, D, H, W, False, seed=5, want_flag=True)
+    assert int(flag.item()) == 0 and torch.isfinite(got).all()
+    _, _, got, _, _, _, flag = _conv_case(cin, cout, 1, D, H, W, False, seed=5, scale_in=300.0, scale_w=300.0, want_flag=True)
+    assert int(flag.item()) == 1 and not torch.isfinite(got).all()

@@ -69,6 +69,25 @@ def test_remap_and_ensemble(mods, shape):
     assert np.array_equal(fused, OP.convert_labels_to_brats2021(OP.ensemble_labels_round(pred, gt)))
 
 
+@pytest.mark.parametrize("shape", SHAPES + [(5, 7, 3)])
+def test_fused_ensemble_remap_histogram(mods, shape):
+    """bsg_label_pair_round_hist_u8 == ensemble + remap followed by the joint histogram against the ground truth, and the
+    Dice metrics built from its bins equal the oracle's (evaluate_segmentation.py:84-162), bit for bit."""
+    CL, V, EV = mods["CL"], mods["V"], mods["EV"]
+    pred, gt = _pair(3, shape)
+    other = np.roll(pred, 2, axis=1).copy()
+    a, b, g = V.as_label_volume(pred), V.as_label_volume(other), V.as_label_volume(gt)
+    out, buf = V.ensemble_remap_hist(a, b, g, post_lut=CL.LUT_BRATS2025)
+    ref = OP.convert_labels_to_brats2025(OP.ensemble_labels_round(pred, other).astype(np.float64))
+    assert np.array_equal(out.cpu().numpy(), ref)
+    hist = V.joint_hist_from_buffer(buf)
+    assert np.array_equal(hist, V.joint_hist(out, g))
+    assert hist.sum() == pred.size
+    ev, ev_ref = EV.evaluate_arrays(out, g, _hist=hist), OP.evaluate_arrays(ref, gt)
+    assert float(ev["mean_dice"]) == float(ev_ref["mean_dice"])
+    assert sorted(ev["labels"]) == sorted(ev_ref["labels"])
+
+
 def test_ensemble_all_byte_pairs(mods):
     V = mods["V"]
     a = np.repeat(np.arange(256, dtype=np.uint8), 256).reshape(16, 64, 64)
