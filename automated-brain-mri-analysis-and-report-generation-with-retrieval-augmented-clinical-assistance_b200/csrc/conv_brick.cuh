@@ -35,7 +35,7 @@ struct BrickArgs {
     const float* bias;
     float slope;
     int act;
-    float* stats;
+    double* stats;
     int out_f16;
     int* overflow;  // device flag, set when a stored fp16 value left the fp16 range (null: no guard)
     const float* in_norm;  // XF: [N][in_norm_c][4] (scale, shift, LeakyReLU slope, 0) applied to the INPUT in shared

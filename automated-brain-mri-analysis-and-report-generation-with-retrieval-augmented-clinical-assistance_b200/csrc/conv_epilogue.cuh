@@ -18,7 +18,7 @@ __device__ __forceinline__ void st_global_v8(void* p, uint32_t a0, uint32_t a1, 
 struct EpiParams {
     const float* sbias;  // shared memory, [cout_pad]
     int has_bias;        // 0: the layer has no bias (nnU-Net's transposed convs): skip the loads and adds
-    float* stats;        // [No][cout][2] running (sum, sum of squares) of the pre-activation output, or null
+    double* stats;       // [No][cout][2] running (sum, sum of squares) of the pre-activation output, or null
     int cout;            // valid output channels
     int No;              // batch extent
     int act;             // 1: LeakyReLU(slope)
@@ -42,16 +42,20 @@ struct EpiGuard {
 // Per-lane running norm statistics of one 32-column chunk: after the transpose-reduce lane l owns channel co + l.
 // They stay in registers across tiles and go to global memory (one atomicAdd pair per lane) only when the batch item
 // or the channel block changes: per-tile atomics on the [N][C][2] table serialise in L2 (measured: +2.5..4.8 ms per
-// full-resolution layer).
+// full-resolution layer).  The table is fp64: every flushed partial sum is a deterministic fp32 value (a CTA's share
+// of the work and its summation order are static), and fp64 additions of a few hundred such values are exact to
+// ~1e-16 whatever order the atomics land in — so the fp32 (scale, shift) derived from them, and with them the whole
+// forward, are reproducible from run to run (fp32 atomics moved label decisions on ~3e-4 of the voxels of a GroupNorm
+// net between runs: a 1e-7 change of a mean flips fp16 roundings downstream).
 struct StatAcc {
     float s1, s2;
 };
 
 __device__ __forceinline__ void flush_stats(const EpiParams& e, StatAcc& acc, int co, int lane, int n) {
     if (co + lane < e.cout && n >= 0 && n < e.No && (acc.s1 != 0.f || acc.s2 != 0.f)) {
-        float* sp = e.stats + (static_cast<long long>(n) * e.cout + co + lane) * 2;
-        atomicAdd(sp, acc.s1);
-        atomicAdd(sp + 1, acc.s2);
+        double* sp = e.stats + (static_cast<long long>(n) * e.cout + co + lane) * 2;
+        atomicAdd(sp, static_cast<double>(acc.s1));
+        atomicAdd(sp + 1, static_cast<double>(acc.s2));
     }
     acc.s1 = 0.f;
     acc.s2 = 0.f;

@@ -39,7 +39,7 @@ struct ConvArgs {
     const float* bias;                 // [cout_pad] or null
     float slope;
     int act;       // 0: none, 1: LeakyReLU(slope)
-    float* stats;  // [No][cout][2] running (sum, sum of squares) of the pre-activation output, or null
+    double* stats;  // [No][cout][2] running (sum, sum of squares) of the pre-activation output, or null
     int out_f16;   // 1: store IEEE fp16 instead of bf16 (raw pre-norm outputs: 3 more mantissa bits, same bytes)
     int* overflow;  // device flag, set when a stored fp16 value left the fp16 range (null: no guard)
     int in_f16;    // 1: activations and weights are IEEE fp16 instead of bf16

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(kThreads) gather_patch_kernel(const float* __r
 // groups == 0: InstanceNorm (per channel); groups > 0: GroupNorm (C/groups channels share statistics).
 // out_stride == 2: scale_shift [N][C][2]; out_stride == 4: rows [coff, coff+C) of a consumer table [N][ctot][4] =
 // (scale, shift, slope, 0) (bsg_norm_finalize_table).
-__global__ void norm_finalize_kernel(const float* __restrict__ stats, int N, int C, int groups, double count, float eps,
+__global__ void norm_finalize_kernel(const double* __restrict__ stats, int N, int C, int groups, double count, float eps,
                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                      float* __restrict__ scale_shift, int out_stride, int ctot, int coff, float slope) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -417,7 +417,7 @@ int bsg_gather_patch_tta(const float* vol, int C, int Z, int Y, int X, int z0, i
     return BSG_OK;
 }
 
-int bsg_norm_finalize(const float* stats, int N, int C, int groups, double count, float eps, const float* gamma,
+int bsg_norm_finalize(const double* stats, int N, int C, int groups, double count, float eps, const float* gamma,
                       const float* beta, float* scale_shift, void* stream) {
     BSG_REQUIRE(stats != nullptr && scale_shift != nullptr, "null argument");
     BSG_REQUIRE(groups >= 0 && (groups == 0 || C % groups == 0), "C %d not divisible by groups %d", C, groups);
@@ -427,7 +427,7 @@ int bsg_norm_finalize(const float* stats, int N, int C, int groups, double count
     return BSG_OK;
 }
 
-int bsg_norm_finalize_table(const float* stats, int N, int C, int groups, double count, float eps, const float* gamma,
+int bsg_norm_finalize_table(const double* stats, int N, int C, int groups, double count, float eps, const float* gamma,
                             const float* beta, float slope, float* table, int ctot, int coff, void* stream) {
     BSG_REQUIRE(stats != nullptr && table != nullptr, "null argument");
     BSG_REQUIRE(groups >= 0 && (groups == 0 || C % groups == 0), "C %d not divisible by groups %d", C, groups);

@@ -330,14 +330,14 @@ class UNetEngine:
 
     # ------------------------------------------------------------------ execution
     def _carve_stats(self, cout):
-        """(batch, cout, 2) fp32 slice of the statistics arena"""
+        """(batch, cout, 2) fp64 slice of the statistics arena"""
         if self._stats_arena is None:
-            self._stats_arena = torch.zeros(1 << 20, dtype=torch.float32, device=self.device)  # 4 MB: > 60 layers of 512 ch
+            self._stats_arena = torch.zeros(1 << 20, dtype=torch.float64, device=self.device)  # 8 MB: > 60 layers of 512 ch
         n = self.batch * cout * 2
         if self._stats_used + n > self._stats_arena.numel():
             raise L.BsgError("norm statistics arena exhausted")
         view = self._stats_arena[self._stats_used:self._stats_used + n].view(self.batch, cout, 2)
-        self._stats_used += (n + 63) // 64 * 64  # 256-byte aligned slices
+        self._stats_used += (n + 31) // 32 * 32  # 256-byte aligned slices
         return view
 
     def _run_steps(self, stream):

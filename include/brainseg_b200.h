@@ -65,8 +65,9 @@ typedef struct bsg_conv_desc {
     const float* bias;   /* fp32 [cout_pad] or NULL */
     int act;             /* BSG_ACT_* applied after bias (used when the norm is folded / absent) */
     float slope;         /* LeakyReLU negative slope (generic_UNet.py:39) */
-    float* stats;        /* fp32 [N][cout][2] += (sum, sum of squares) of the pre-activation output, or NULL;
-                            feeds InstanceNorm / GroupNorm (generic_UNet.py:62-65) */
+    double* stats;       /* fp64 [N][cout][2] += (sum, sum of squares) of the pre-activation output, or NULL;
+                            feeds InstanceNorm / GroupNorm (generic_UNet.py:62-65).  fp64 so that the order in which
+                            the CTAs' partial sums arrive cannot change the result (run-to-run reproducibility) */
     int out_f16;         /* 1: store the output as IEEE fp16 instead of bf16 (raw pre-norm values that
                             bsg_norm_apply_lrelu then rewrites in place as bf16) */
     int use_khshift;     /* -1 auto, 0 off, 1 on: halo reuse of the h taps inside shared memory */
@@ -250,14 +251,14 @@ int bsg_gather_patch_tta(const float* vol, int C, int Z, int Y, int X, int z0, i
                          const int* mirror_codes_host, int nmirrors, void* out16, int cpad, int out_f16, void* stream);
 
 /* InstanceNorm3d / GroupNorm (generic_UNet.py:62-65,72) from the statistics the conv epilogue accumulated:
- * stats [N][C][2] = (sum, sum of squares) over `count` voxels -> scale_shift [N][C][2] with
+ * stats (fp64) [N][C][2] = (sum, sum of squares) over `count` voxels -> scale_shift (fp32) [N][C][2] with
  * y = x*scale + shift == (x-mean)*rsqrt(var+eps)*gamma + beta.  groups = 0: per channel; > 0: GroupNorm. */
-int bsg_norm_finalize(const float* stats, int N, int C, int groups, double count, float eps, const float* gamma,
+int bsg_norm_finalize(const double* stats, int N, int C, int groups, double count, float eps, const float* gamma,
                       const float* beta, float* scale_shift, void* stream);
 /* Same statistics -> rows [coff, coff+C) of a consumer-side table [N][ctot][4] = (scale, shift, slope, 0): the input
  * transform of the conv that consumes the raw tensor (bsg_conv_desc.in_norm).  Channels of the table that belong to an
  * un-normalised producer (the transposed-conv half of a concat buffer) are preset by the caller to (1, 0, 1, 0). */
-int bsg_norm_finalize_table(const float* stats, int N, int C, int groups, double count, float eps, const float* gamma,
+int bsg_norm_finalize_table(const double* stats, int N, int C, int groups, double count, float eps, const float* gamma,
                             const float* beta, float slope, float* table, int ctot, int coff, void* stream);
 /* In place on channels [coff, coff+C) of a (N, voxels, ctot) 16-bit buffer: x <- LeakyReLU(x*scale + shift), read as
  * fp16 when in_f16 = 1 (the conv stored its raw output as fp16, bsg_conv_desc.out_f16) else bf16, written back as fp16

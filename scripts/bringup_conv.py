@@ -50,7 +50,7 @@ def run_case(name, kind, N, D, H, W, cin, cout, stride=1, khshift=-1, act=0, sta
     bp = P.pad_bias(b, cout).to(dev) if b is not None else None
     out_ctot = P.round_up(cout, 8) + out_extra
     out = torch.full((N, Do, Ho, Wo, out_ctot), 5.0, dtype=dt, device=dev)
-    st = torch.zeros(N, cout, 2, dtype=torch.float32, device=dev) if stats else None
+    st = torch.zeros(N, cout, 2, dtype=torch.float64, device=dev) if stats else None
     plan = L.ConvPlan(kind=kind, stride=stride, N=N, D=D, H=H, W=W, cin=cin_pad, in_ptr=xb.data_ptr(),
                       in_ctot=in_ctot, cout=cout, out_ptr=out.data_ptr(), out_ctot=out_ctot, out_coff=out_coff,
                       weights=wp.data_ptr(), bias=bp.data_ptr() if bp is not None else None, act=act, slope=0.01,
@@ -84,7 +84,7 @@ def run_case(name, kind, N, D, H, W, cin, cout, stride=1, khshift=-1, act=0, sta
         msg += f" untouched={untouched}"
     if stats:
         s_ref = torch.stack([pre.sum(dim=(2, 3, 4)), (pre * pre).sum(dim=(2, 3, 4))], dim=-1)
-        serr = ((st - s_ref).abs() / (s_ref.abs() + 1.0)).max().item()
+        serr = ((st.float() - s_ref).abs() / (s_ref.abs() + 1.0)).max().item()
         ok = ok and serr < 1e-3
         msg += f" stats relerr {serr:.3g}"
     if time_it:

@@ -54,7 +54,8 @@ def main():
 
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
-    m1, m2 = B.build_models(model2)
+    import synthetic_case
+    m1, m2 = synthetic_case.build_benchmark_models(model2)
     log("models built")
     pipe = PL.BratsCasePipeline([m1, m2], B.PATCH, 0.5, (0, 1, 2), True, True, (1, 2, 3), "brats2025", batch=batch)
     torch.cuda.synchronize()

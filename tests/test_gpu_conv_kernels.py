@@ -29,7 +29,7 @@ def _conv_case(cin, cout, N, D, H, W, stats, f16=True, in_norm=False, seed=0, sc
     b = torch.randn(cout, generator=g).to(dev)
     bp = P.pad_bias(b, cout).to(dev)
     out = torch.zeros(N, D, H, W, cout, dtype=dt, device=dev)
-    st = torch.zeros(N, cout, 2, dtype=torch.float32, device=dev) if stats else None
+    st = torch.zeros(N, cout, 2, dtype=torch.float64, device=dev) if stats else None
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
     kw = dict(kind=L.BSG_CONV_K3, stride=1, N=N, D=D, H=H, W=W, cin=cin, in_ptr=xb.data_ptr(), in_ctot=cin, cout=cout,
               out_ptr=out.data_ptr(), out_ctot=cout, out_coff=0, weights=wp.data_ptr(), bias=bp.data_ptr(), act=0 if stats else 1,
@@ -84,7 +84,7 @@ def test_brick_conv_with_in_consumer_norm(cin, cout, D, H, W, stats):
     assert err <= 3e-3 * max(scale, 1.0)
     if stats:
         s_ref = torch.stack([pre.sum(dim=(2, 3, 4)), (pre * pre).sum(dim=(2, 3, 4))], dim=-1)
-        assert ((st / 2 - s_ref).abs() / (s_ref.abs() + 1.0)).max().item() < 1e-3  # two runs accumulated
+        assert ((st.float() / 2 - s_ref).abs() / (s_ref.abs() + 1.0)).max().item() < 1e-3  # two runs accumulated
 
 
 def test_in_consumer_norm_is_refused_outside_the_brick_kernel():
