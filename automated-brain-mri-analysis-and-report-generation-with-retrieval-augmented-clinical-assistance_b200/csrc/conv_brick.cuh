@@ -20,7 +20,8 @@ struct BrickArgs {
     int P;               // planes per brick = 256 / NT
     int D;
     int nchunks;   // Cin / CC
-    int nphases;   // 3 * nchunks, phase = chunk * 3 + kw
+    int kwn;       // taps along w: 3, or 1 for a 3x3x1 kernel (kw-packed first layer: the w neighbours sit in the channels)
+    int nphases;   // kwn * nchunks, phase = chunk * kwn + kw
     int nslabbuf;  // weight slab buffers in shared memory; >= nphases: resident for the whole launch
     int kwf;       // 1: kw-fused — one haloed 10 w x 18 h box per (plane, chunk) serves all 27 taps (needs resident slabs)
     int nstages;   // activation ring depth

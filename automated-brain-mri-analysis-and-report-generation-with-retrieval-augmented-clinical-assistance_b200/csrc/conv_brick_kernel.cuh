@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(brick_threads(CC, XF), 1) conv_brick_kernel(co
                 const Unit t = decode_unit(a, u, P);
                 const int nloads = KWF ? a.nchunks : nphases;  // KWF: one haloed box per (chunk, plane) for all kw
                 for (int ph = 0; ph < nloads; ++ph) {
-                    const int c = KWF ? ph : ph / 3, kw = KWF ? 1 : ph - c * 3;
+                    const int c = KWF ? ph : ph / a.kwn, kw = (KWF || a.kwn == 1) ? 1 : ph - c * 3;
                     for (int p = 0; p < P + 2; ++p) {
                         const int d = t.d0 + p - 1;  // d = -1 / D: the box is all out of bounds -> zeros (conv padding)
                         mbar_wait(&empty_bar[stage], phase ^ 1u);
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(brick_threads(CC, XF), 1) conv_brick_kernel(co
                         buf = su % static_cast<uint32_t>(a.nslabbuf);
                         mbar_wait(&wempty_bar[buf], ((su / static_cast<uint32_t>(a.nslabbuf)) & 1u) ^ 1u);
                     }
-                    const int c = ph / 3, kw = ph - c * 3;
+                    const int c = ph / a.kwn, kw = ph - c * a.kwn;
                     uint8_t* dst = slabs + static_cast<size_t>(buf) * a.slab_bytes;
                     mbar_expect_tx(&wfull_bar[buf], a.slab_bytes);
                     for (int kh = 0; kh < 3; ++kh)  // box (CC, NT, 1, 1, 3 kd) -> [kd][NT][CC] behind each kh
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(brick_threads(CC, XF), 1) conv_brick_kernel(co
             int c_loaded = -1;
             float sc[8], sh[8], sl[8];
             for (int ph = 0; ph < nloads; ++ph) {
-                const int c = KWF ? ph : ph / 3;
+                const int c = KWF ? ph : ph / a.kwn;
                 if (c != c_loaded) {  // (scale, shift, slope) of this thread's 8 channels for (batch item, K chunk)
                     const float4* row = table + (static_cast<size_t>(t.n) * a.in_norm_c + c * CC + col * 8);
 #pragma unroll

@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include "bsg_ptx.cuh"
 
 namespace bsg {
 
@@ -84,11 +85,21 @@ __device__ __forceinline__ void stats_transpose_reduce(float (&s1)[32], float (&
 // Norm statistics of one 32-column chunk when the rows of a warp span SEVERAL batch items (tile boxes with fewer than
 // 32 voxels per item: the <= 2^3 levels of a deep net run with batch > 4 per tile).  One masked transpose-reduce and
 // one flush per batch item of the warp; cold path (tiny layers only), kept out of line.
-static __device__ __noinline__ void stats_chunk_grouped(const uint32_t (&v)[32], const EpiParams& e, int co, bool valid, int lane,
-                                                 int vox_per_item, int n_first) {
+// It re-reads the chunk from TMEM itself (taddr): handing it the caller's register array by reference would force that
+// array into local memory for the whole (hot) epilogue.
+static __device__ __noinline__ void stats_chunk_grouped(uint32_t taddr, const float* sbias, bool has_bias, double* stats,
+                                                        int cout, int No, int co, bool valid, int lane, int vox_per_item,
+                                                        int n_first) {
+    EpiParams e;
+    e.stats = stats;
+    e.cout = cout;
+    e.No = No;
+    uint32_t v[32];
+    tmem_ld_32x32(taddr, v);
+    tmem_ld_wait();
     float f[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + (e.has_bias ? e.sbias[co + i] : 0.f);
+    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + (has_bias ? sbias[co + i] : 0.f);
     for (int g = 0; g * vox_per_item < 32; ++g) {
         const bool mine = valid && (lane / vox_per_item == g);
         float s1[32], s2[32];

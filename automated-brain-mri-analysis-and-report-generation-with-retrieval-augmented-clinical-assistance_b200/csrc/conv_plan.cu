@@ -90,21 +90,29 @@ int plan_brick(const bsg_conv_desc* d, bsg_conv_plan* p) {
     a.tb = d->D / P;
     a.tn = d->N;
     a.nchunks = d->cin / cc;
-    a.nphases = 3 * a.nchunks;
+    a.kwn = d->kw_taps == 1 ? 1 : 3;
+    a.nphases = a.kwn * a.nchunks;
     a.slab_bytes = 9u * cout_pad * cc * 2u;
     // leave ~8 KB of the SM's shared memory unclaimed: the HBM-bound elementwise kernels of the other stream lane
     // (norm apply, gather, head) need their 1 KB system reservation each to become co-resident with this CTA
     const uint32_t avail = 227 * 1024 - 1024 - 1280 - 8192;
     const uint32_t stage_kwf = round_up(10u * 18u * cc * 2u, 1024), stage_3x = round_up(8u * 18u * cc * 2u, 1024);
-    if (a.nphases <= 6 && static_cast<uint64_t>(a.nphases) * a.slab_bytes + 3ull * stage_kwf <= avail) {
+    if (a.kwn == 3 && a.nphases <= 6 && static_cast<uint64_t>(a.nphases) * a.slab_bytes + 3ull * stage_kwf <= avail) {
         a.nslabbuf = a.nphases;  // resident slabs -> kw-fused activation boxes
         a.kwf = 1;
+    } else if (a.kwn == 1 && a.nphases <= 6 && static_cast<uint64_t>(a.nphases) * a.slab_bytes + 3ull * stage_3x <= avail) {
+        a.nslabbuf = a.nphases;  // 3x3x1 kernel: resident slabs, plain 8-wide boxes (no w halo to share)
+        a.kwf = 0;
     } else if (2ull * a.slab_bytes + 2ull * stage_3x <= avail) {
         a.nslabbuf = 2;
         a.kwf = 0;
     } else {
         return 0;
     }
+    // the in-consumer norm transform rewrites every landed box once: with streamed slabs an element arrives in three
+    // kw-shifted boxes and the 128 B/clk shared-memory port, which MMA operand reads already fill, pays for it three
+    // times (measured: 64->64 @128^3 1.71 -> 2.73 ms, more than the 0.37 ms pass it replaces) -> kw-fused plans only
+    if (d->in_norm != nullptr && !a.kwf) return 0;
     const uint32_t box_w = a.kwf ? 10u : 8u;
     a.a_tx_bytes = box_w * 18u * cc * 2u;
     a.a_stage_bytes = a.kwf ? stage_kwf : stage_3x;
@@ -122,8 +130,9 @@ int plan_brick(const bsg_conv_desc* d, bsg_conv_plan* p) {
     // weights [27 taps (kd, kw, kh)][cout_pad][cin] seen as (cin, row, kh, kw, kd): a box of the 3 kd taps of one
     // (kh, kw) lands as [kd][cout_pad][cc] = the B operand of one N = 3*cout_pad MMA
     const uint64_t tap_bytes = static_cast<uint64_t>(d->cin) * 2 * cout_pad;
-    uint64_t wdims[5] = {static_cast<uint64_t>(d->cin), static_cast<uint64_t>(cout_pad), 3ull, 3ull, 3ull};
-    uint64_t wstr[4] = {static_cast<uint64_t>(d->cin) * 2, tap_bytes, tap_bytes * 3, tap_bytes * 9};
+    const uint64_t kwn = static_cast<uint64_t>(a.kwn);
+    uint64_t wdims[5] = {static_cast<uint64_t>(d->cin), static_cast<uint64_t>(cout_pad), 3ull, kwn, 3ull};
+    uint64_t wstr[4] = {static_cast<uint64_t>(d->cin) * 2, tap_bytes, tap_bytes * 3, tap_bytes * 3 * kwn};
     uint32_t wbox[5] = {static_cast<uint32_t>(cc), static_cast<uint32_t>(cout_pad), 1u, 1u, 3u};
     rc = encode_map(&a.mapW, d->weights, 5, wdims, wstr, wbox, cc);
     if (rc != BSG_OK) return rc;
@@ -153,7 +162,7 @@ int plan_brick(const bsg_conv_desc* d, bsg_conv_plan* p) {
     const int max_ctas = d->max_ctas > 0 ? d->max_ctas : sm_count_cached();
     p->grid = units < max_ctas ? units : max_ctas;
     p->smem_bytes = conv_brick_smem_bytes(a);
-    p->flops = 2.0 * 27 * static_cast<double>(d->cin) * d->cout * (static_cast<double>(d->W) * d->H * d->D * d->N);
+    p->flops = 2.0 * 9 * a.kwn * static_cast<double>(d->cin) * d->cout * (static_cast<double>(d->W) * d->H * d->D * d->N);
     return 1;
 }
 
@@ -215,6 +224,11 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
             *out_plan = p;
             return BSG_OK;
         }
+    }
+    if (d->kw_taps == 1) {
+        delete p;
+        return set_error(BSG_EINVAL, "kw_taps 1 (3x3x1 kernel) exists for the brick kernel only (stride-1, Cout <= 64, "
+                                     "W %% 8 == 0, H %% 16 == 0, D %% (256 / Cout_pad) == 0)");
     }
     if (d->in_norm != nullptr) {
         delete p;

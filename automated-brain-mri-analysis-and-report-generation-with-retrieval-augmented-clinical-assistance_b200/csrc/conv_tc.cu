@@ -332,8 +332,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         // >= 32 voxels per item (bn <= 4); smaller boxes take the grouped path (stats_chunk_grouped).
         const int vox_per_item = a.bw * a.bh * a.bd;
         const bool grouped = a.stats != nullptr && vox_per_item < 32;
-        EpiParams epi_plain = epi;  // the chunk body without statistics (grouped path)
-        epi_plain.stats = nullptr;
+        if (grouped) epi.stats = nullptr;  // the chunk body then skips the statistics; the grouped path gets a.stats
         StatAcc sacc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) sacc[j].s1 = sacc[j].s2 = 0.f;
@@ -403,10 +402,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 }
                 StatAcc chunk_stats;
                 chunk_stats.s1 = chunk_stats.s2 = 0.f;
-                epilogue_32cols<false>(v, grouped ? epi_plain : epi, co, valid, lane, chunk_stats, orow, unused1, unused2,
-                                       guard);
+                epilogue_32cols<false>(v, epi, co, valid, lane, chunk_stats, orow, unused1, unused2, guard);
                 if (grouped) {
-                    stats_chunk_grouped(v, epi, co, valid, lane, vox_per_item, t.n0 + (q * 32) / vox_per_item);
+                    stats_chunk_grouped(t_addr + cb, sbias, a.bias != nullptr, a.stats, a.cout, a.No, co, valid, lane, vox_per_item,
+                                        t.n0 + (q * 32) / vox_per_item);
                 } else if (a.stats != nullptr) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
@@ -420,7 +419,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
-        if (a.stats != nullptr && !grouped) {
+        if (epi.stats != nullptr) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) flush_stats(epi, sacc[j], stat_nt * a.ntile + j * 32, lane, stat_n);
         }

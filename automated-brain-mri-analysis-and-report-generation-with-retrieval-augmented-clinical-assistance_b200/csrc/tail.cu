@@ -22,6 +22,32 @@ struct MirrorSet {
     int code[kMaxMirrors];  // bit0: flip x (tensor dim 4), bit1: flip y (dim 3), bit2: flip z (dim 2)
 };
 
+// 16 packed channels (8 pairs) of a kw-packed voxel from its three w-neighbours' C channels: forward order
+// [x(w-1) | x(w) | x(w+1) | 0] and the order a copy flipped along x sees, [x(w+1) | x(w) | x(w-1) | 0].
+template <int C>
+__device__ __forceinline__ void kwpack_pairs(const float (&v)[3][5], int out_f16, uint32_t (&pkf)[8], uint32_t (&pkr)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float f[2], r[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int e = 2 * j + q;  // packed channel e: neighbour k = e / C, channel c = e % C (compile-time)
+            const int k = e / C, c = e % C;
+            f[q] = e < 3 * C ? v[k][c] : 0.f;
+            r[q] = e < 3 * C ? v[2 - k][c] : 0.f;
+        }
+        if (out_f16) {
+            __half2 p = __floats2half2_rn(f[0], f[1]), q2 = __floats2half2_rn(r[0], r[1]);
+            pkf[j] = *reinterpret_cast<uint32_t*>(&p);
+            pkr[j] = *reinterpret_cast<uint32_t*>(&q2);
+        } else {
+            __nv_bfloat162 p = __floats2bfloat162_rn(f[0], f[1]), q2 = __floats2bfloat162_rn(r[0], r[1]);
+            pkf[j] = *reinterpret_cast<uint32_t*>(&p);
+            pkr[j] = *reinterpret_cast<uint32_t*>(&q2);
+        }
+    }
+}
+
 // out[m][d][h][w][c] = vol[c][z0 + fz(d)][y0 + fy(h)][x0 + fx(w)], c < C; channels C..cpad-1 are zero.
 // grid (ceil(P1*P2 / 256), P0): one thread per SOURCE voxel of the tile — it is read and converted once and stored to
 // its position in each of the (up to 8) mirrored copies; a warp's 32 consecutive w land on 32 consecutive (or
@@ -30,13 +56,47 @@ struct MirrorSet {
 __global__ void __launch_bounds__(kThreads) gather_patch_kernel(const float* __restrict__ vol, int C, int Z, int Y,
                                                                 int X, int z0, int y0, int x0, int P0, int P1, int P2,
                                                                 const MirrorSet ms, __nv_bfloat16* __restrict__ out,
-                                                                int cpad, int out_f16) {
+                                                                int cpad, int out_f16, int kwpack) {
     const int hw = blockIdx.x * blockDim.x + threadIdx.x;
     if (hw >= P1 * P2) return;
     const int d = blockIdx.y;
     const int h = hw / P2, w = hw - h * P2;
     const size_t plane = static_cast<size_t>(Z) * Y * X;
     const float* src = vol + (static_cast<size_t>(z0 + d) * Y + (y0 + h)) * X + (x0 + w);
+    if (kwpack) {
+        // kw-packed layout for the network's first conv (3*C <= 16): channel k*C + c of a voxel holds channel c of its
+        // w-neighbour k-1 IN THE COPY's orientation (zero outside the tile = the conv's zero padding), so that the
+        // 3x3x3 conv over C channels becomes a 3x3x1 conv over 3*C: 9 taps of K = 16 instead of 27 (the 4 BraTS
+        // modalities are padded to K = 16 either way).  A copy flipped along x sees the neighbours swapped.
+        float v[3][5];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int ww = w + k - 1;
+            const bool inb = ww >= 0 && ww < P2;
+#pragma unroll
+            for (int c = 0; c < 5; ++c) v[k][c] = (inb && c < C) ? __ldg(src + (k - 1) + c * plane) : 0.f;
+        }
+        uint32_t pkf[8], pkr[8];
+        switch (C) {
+            case 1: kwpack_pairs<1>(v, out_f16, pkf, pkr); break;
+            case 2: kwpack_pairs<2>(v, out_f16, pkf, pkr); break;
+            case 3: kwpack_pairs<3>(v, out_f16, pkf, pkr); break;
+            case 4: kwpack_pairs<4>(v, out_f16, pkf, pkr); break;
+            default: kwpack_pairs<5>(v, out_f16, pkf, pkr); break;
+        }
+        for (int m = 0; m < ms.n; ++m) {
+            const int code = ms.code[m];
+            const int ow = (code & 1) ? P2 - 1 - w : w;
+            const int oh = (code & 2) ? P1 - 1 - h : h;
+            const int od = (code & 4) ? P0 - 1 - d : d;
+            __nv_bfloat16* dst = out + (((static_cast<size_t>(m) * P0 + od) * P1 + oh) * P2 + ow) * cpad;
+            const uint32_t* pk = (code & 1) ? pkr : pkf;
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(dst), "r"(pk[0]), "r"(pk[1]),
+                         "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                         : "memory");
+        }
+        return;
+    }
     for (int c0 = 0; c0 < cpad; c0 += 16) {
         uint32_t pk[8];
 #pragma unroll
@@ -402,9 +462,12 @@ using namespace bsg;
 extern "C" {
 
 int bsg_gather_patch_tta(const float* vol, int C, int Z, int Y, int X, int z0, int y0, int x0, int P0, int P1, int P2,
-                         const int* mirror_codes_host, int nmirrors, void* out_bf16, int cpad, int out_f16, void* stream) {
+                         const int* mirror_codes_host, int nmirrors, void* out_bf16, int cpad, int out_f16, int kwpack,
+                         void* stream) {
     BSG_REQUIRE(vol != nullptr && out_bf16 != nullptr, "null argument");
     BSG_REQUIRE(cpad % 8 == 0 && cpad >= C, "cpad %d must be a multiple of 8 and >= C=%d", cpad, C);
+    BSG_REQUIRE(!kwpack || (cpad == 16 && 3 * C <= 16 && (reinterpret_cast<uintptr_t>(out_bf16) & 31) == 0),
+                "kwpack needs 3 * C <= 16, cpad == 16 and a 32-byte aligned output");
     BSG_REQUIRE(z0 >= 0 && y0 >= 0 && x0 >= 0 && z0 + P0 <= Z && y0 + P1 <= Y && x0 + P2 <= X,
                 "tile exceeds the volume");
     MirrorSet ms;
@@ -412,7 +475,7 @@ int bsg_gather_patch_tta(const float* vol, int C, int Z, int Y, int X, int z0, i
     if (rc != BSG_OK) return rc;
     dim3 grid(static_cast<unsigned>(ceil_div(P1 * P2, kThreads)), static_cast<unsigned>(P0));
     gather_patch_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        vol, C, Z, Y, X, z0, y0, x0, P0, P1, P2, ms, static_cast<__nv_bfloat16*>(out_bf16), cpad, out_f16);
+        vol, C, Z, Y, X, z0, y0, x0, P0, P1, P2, ms, static_cast<__nv_bfloat16*>(out_bf16), cpad, out_f16, kwpack);
     BSG_CUDA_OK(cudaGetLastError());
     return BSG_OK;
 }

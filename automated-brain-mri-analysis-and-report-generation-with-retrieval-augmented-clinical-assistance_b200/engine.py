@@ -84,6 +84,8 @@ class UNetEngine:
         # that conv (applied in shared memory on the way to the tensor core) instead of a separate HBM pass
         self.fuse_norm = os.environ.get("BSG_FUSE_NORM", "1") != "0"
         self.fused_norms = 0
+        self.try_kwpack = os.environ.get("BSG_KWPACK", "1") != "0"
+        self.kwpack = False  # the first conv reads the kw-packed input layout (set by _add_block when its plan took it)
         self.flops_algo = 0.0    # algorithmic FLOPs on the real channel counts (the 4 input channels are padded to 16)
         self.act_dtype = torch.float16 if self.f16 else torch.bfloat16
         self.steps = []       # callables, in launch order
@@ -108,7 +110,7 @@ class UNetEngine:
         self.keep.append(t)
         return t
 
-    def _pack_block(self, blk, cin_pad):
+    def _pack_block(self, blk, cin_pad, kwpack=False):
         """Packed 16-bit weights + fp32 bias of one conv block (eval BatchNorm folded in), norm affine parameters."""
         conv, norm = blk.conv, blk.instnorm
         w = conv.weight.detach().to(self.device, torch.float32)
@@ -127,12 +129,13 @@ class UNetEngine:
             beta = norm.bias.detach().to(self.device).float().contiguous() if norm.bias is not None else None
         else:
             raise NotImplementedError(f"norm {type(norm).__name__}")
-        return (P.pack_conv3_weight(w, cin_pad, self.act_dtype), P.pad_bias(b, w.shape[0]).to(self.device), gamma, beta)
+        wp = P.pack_conv3_weight_kwpacked(w, self.act_dtype) if kwpack else P.pack_conv3_weight(w, cin_pad, self.act_dtype)
+        return (wp, P.pad_bias(b, w.shape[0]).to(self.device), gamma, beta)
 
     def _overflow_slot(self):
         return self._overflow.data_ptr() if self._overflow is not None else None
 
-    def _add_block(self, blk, src, dst, spatial_in, defer_apply=False, claim=None):
+    def _add_block(self, blk, src, dst, spatial_in, defer_apply=False, claim=None, first=False):
         """One ConvDropoutNormNonlin block.  `claim`: the norm state of the block that produced `src`, when this conv is
         its only consumer — if the planner can run this conv with the in-consumer transform (brick kernel), the
         producer's normalise + LeakyReLU pass is dropped and its statistics go to this conv's input table instead.
@@ -147,12 +150,15 @@ class UNetEngine:
         else:
             act = L.BSG_ACT_NONE
         cin_pad = src.c
-        wp, bp, gamma, beta = self._pack_block(blk, cin_pad)
+        d, h, wd = spatial_in
+        # the network's first conv: with 3 * C <= 16 input channels the gather kernel packs the three w neighbours of a
+        # voxel into its 16 channels and the conv runs as a 3x3x1 kernel — 9 taps of K = 16 instead of 27
+        kwpack = False
+        if first and self.try_kwpack and 3 * conv.in_channels <= 16 and cin_pad == 16 and stride == 1:
+            kwpack = True
+        wp, bp, gamma, beta = self._pack_block(blk, cin_pad, kwpack)
         if act == L.BSG_ACT_NONE:
             stats = self._carve_stats(cout)
-        self.keep += [wp, bp]
-        self._weight_slots.append(("block", blk, cin_pad, (wp, bp, gamma, beta)))
-        d, h, wd = spatial_in
         desc = dict(kind=L.BSG_CONV_K3, stride=stride, N=self.batch, D=d, H=h, W=wd, cin=cin_pad,
                     in_ptr=src.ptr(), in_ctot=src.ctot, cout=cout, out_ptr=dst.buf.data_ptr(),
                     out_ctot=dst.ctot, out_coff=dst.coff, weights=wp.data_ptr(), bias=bp.data_ptr(), act=act,
@@ -160,6 +166,16 @@ class UNetEngine:
                     out_f16=self.f16, in_f16=self.f16, use_khshift=-1,
                     max_ctas=0, overflow=self._overflow_slot())
         plan = None
+        if kwpack:
+            try:
+                plan = L.ConvPlan(kw_taps=1, **desc)
+                self.kwpack = True
+            except L.BsgError:  # shape does not suit the brick kernel: plain 27-tap first layer
+                kwpack = False
+                wp, bp, gamma, beta = self._pack_block(blk, cin_pad, False)
+                desc.update(weights=wp.data_ptr(), bias=bp.data_ptr())
+        self.keep += [wp, bp]
+        self._weight_slots.append(("block_kw" if kwpack else "block", blk, cin_pad, (wp, bp, gamma, beta)))
         if claim is not None and self.fuse_norm and src.coff == 0 and src.c == src.ctot:
             table = torch.zeros(self.batch, cin_pad, 4, dtype=torch.float32, device=self.device)
             try:
@@ -273,7 +289,7 @@ class UNetEngine:
                 else:
                     dst = _Act(self._alloc(out_spatial, cout), 0, cout)
                     is_skip = False
-                prev = self._add_block(blk, cur, dst, spatial, claim=prev if i > 0 else None)
+                prev = self._add_block(blk, cur, dst, spatial, claim=prev if i > 0 else None, first=(d == 0 and i == 0))
                 if is_skip:
                     prev = None  # a skip tensor also feeds the decoder: it must be materialised
                 cur, spatial = dst, out_spatial
@@ -313,8 +329,8 @@ class UNetEngine:
         maps point at fixed buffers, so they stay valid): what load_state_dict / load_checkpoint_ram need per fold,
         instead of rebuilding activation buffers, plans and tensor maps."""
         for kind, mod, cin_pad, tensors in self._weight_slots:
-            if kind == "block":
-                for dst, src in zip(tensors, self._pack_block(mod, cin_pad)):
+            if kind in ("block", "block_kw"):
+                for dst, src in zip(tensors, self._pack_block(mod, cin_pad, kind == "block_kw")):
                     if dst is not None:
                         dst.copy_(src)
             else:
@@ -369,7 +385,10 @@ class UNetEngine:
         if n > self.batch or tuple(x.shape[2:]) != self.patch:
             raise ValueError("input does not match the engine geometry")
         self.x.buf.zero_()
-        self.x.buf[:n, ..., :self.in_channels] = x.to(self.device).permute(0, 2, 3, 4, 1).to(self.act_dtype)
+        if self.kwpack:
+            self.x.buf[:n] = P.kwpack_input(x.to(self.device, torch.float32), self.cin_pad).to(self.act_dtype)
+        else:
+            self.x.buf[:n, ..., :self.in_channels] = x.to(self.device).permute(0, 2, 3, 4, 1).to(self.act_dtype)
         self.run()
         f = self.features.view()[:n].float()  # (n, d, h, w, c)
         if self.final_norm is not None:

@@ -16,6 +16,29 @@ def pack_conv3_weight(w, cin_pad=None, dtype=torch.bfloat16):
     return p.to(dtype).contiguous()
 
 
+def pack_conv3_weight_kwpacked(w, dtype=torch.bfloat16):
+    """First-layer nn.Conv3d weight (Cout, Cin, kd, kh, kw), 3 * Cin <= 16 -> 16-bit [9 taps (kd, kh)][cout_pad][16] with
+    K index kw * Cin + ci: the 3x3x1 kernel over the kw-packed input (bsg_gather_patch_tta kwpack = 1)."""
+    cout, cin = w.shape[0], w.shape[1]
+    assert 3 * cin <= 16
+    cout_pad = round_up(cout, 32)
+    p = torch.zeros(9, cout_pad, 16, dtype=torch.float32, device=w.device)
+    p[:, :cout, :3 * cin] = w.float().permute(2, 3, 0, 4, 1).reshape(9, cout, 3 * cin)  # (kd, kh, co, kw, ci)
+    return p.to(dtype).contiguous()
+
+
+def kwpack_input(x, cpad=16):
+    """(N, C, D, H, W) float -> (N, D, H, W, cpad) float with channel k*C + c = x[:, c] shifted by k-1 along w (zero
+    outside): the torch-side twin of the gather kernel's kwpack layout (forward_logits convenience path)."""
+    n, c, d, h, w = x.shape
+    out = torch.zeros(n, d, h, w, cpad, dtype=x.dtype, device=x.device)
+    xl = x.permute(0, 2, 3, 4, 1)
+    out[..., 1:, 0:c] = xl[..., :-1, :]
+    out[..., c:2 * c] = xl
+    out[..., :-1, 2 * c:3 * c] = xl[..., 1:, :]
+    return out
+
+
 def pack_conv1_weight(w, cin_pad=None, dtype=torch.bfloat16):
     """1x1x1 conv weight (Cout, Cin, 1, 1, 1) -> 16-bit [1][cout_pad][cin_pad]."""
     cout, cin = w.shape[0], w.shape[1]

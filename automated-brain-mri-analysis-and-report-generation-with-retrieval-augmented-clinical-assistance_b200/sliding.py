@@ -191,7 +191,7 @@ class SlidingWindowPredictor:
                         codes = (C.c_int * (b - a))(*[m for _, m in chunk[a:b]])
                         out = eng.x.buf.data_ptr() + 2 * a * pv * eng.x.ctot
                         L.check(lib.bsg_gather_patch_tta(_ptr(vol), Cn, Z, Y, X, z, y, x, p0, p1, p2, codes, b - a,
-                                                         C.c_void_p(out), eng.x.ctot, eng.f16, sp))
+                                                         C.c_void_p(out), eng.x.ctot, eng.f16, int(eng.kwpack), sp))
                     eng.run(None)
                     if multi and head_done is not None:
                         s.wait_event(head_done)

@@ -415,7 +415,7 @@ def hbm_rooflines(dev, peaks, f16):
     dt = torch.float16 if f16 else torch.bfloat16
     xin = torch.empty(8, p, p, p, 16, dtype=dt, device=dev)
     row("gather_patch_kernel (tile crop + 8 mirror copies, 4 -> 16 ch)",
-        timed(lambda: L.check(lib.bsg_gather_patch_tta(ptr(vol), 4, Z, Y, X, 27, 56, 56, p, p, p, codes, 8, ptr(xin), 16, f16,
+        timed(lambda: L.check(lib.bsg_gather_patch_tta(ptr(vol), 4, Z, Y, X, 27, 56, 56, p, p, p, codes, 8, ptr(xin), 16, f16, 0,
                                                        L.stream_ptr()))),
         4 * pv * 4 + 8 * pv * 32, "per tile voxel: 4 fp32 read + 8 mirrors x 16 ch x 2 B written")
     del xin

@@ -87,6 +87,9 @@ typedef struct bsg_conv_desc {
                             rows written by bsg_norm_finalize_table).  Brick kernel only: bsg_conv_plan_create returns
                             BSG_EINVAL when the layer does not qualify and the caller keeps the separate pass. */
     int in_norm_c;       /* channels per batch item of the in_norm table (>= cin) */
+    int kw_taps;         /* 0 / 3: 3x3x3 kernel.  1: 3x3x1 kernel (kd, kh taps only), weights [9 taps (kd, kh)][cout_pad][cin]:
+                            the network's first conv on an input whose w neighbours were packed into the channels by
+                            bsg_gather_patch_tta(kwpack = 1) — 9 taps of K = 16 instead of 27.  Brick kernel only. */
 } bsg_conv_desc;
 
 typedef struct bsg_conv_plan bsg_conv_plan;
@@ -247,8 +250,11 @@ int bsg_masked_threshold_count(const float* x1, const float* x2, const float* x3
 /* out[m][d][h][w][c] (bf16, or fp16 when out_f16 = 1; cpad channels, zero padded) =
  * vol[c][z0+fz(d)][y0+fy(h)][x0+fx(w)]: the tile crop data[None, :, lb_x:ub_x, ...] plus torch.flip(x, axes) for every
  * mirror m, written as one channels-last batch. */
+/* kwpack = 1 (needs 3 * C <= 16, cpad == 16): channel k*C + c of an output voxel = channel c of its w-neighbour k-1 in
+ * the copy's orientation, zero outside the tile — the input layout of a first conv planned with kw_taps = 1. */
 int bsg_gather_patch_tta(const float* vol, int C, int Z, int Y, int X, int z0, int y0, int x0, int P0, int P1, int P2,
-                         const int* mirror_codes_host, int nmirrors, void* out16, int cpad, int out_f16, void* stream);
+                         const int* mirror_codes_host, int nmirrors, void* out16, int cpad, int out_f16, int kwpack,
+                         void* stream);
 
 /* InstanceNorm3d / GroupNorm (generic_UNet.py:62-65,72) from the statistics the conv epilogue accumulated:
  * stats (fp64) [N][C][2] = (sum, sum of squares) over `count` voxels -> scale_shift (fp32) [N][C][2] with

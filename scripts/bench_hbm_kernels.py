@@ -86,7 +86,7 @@ def main():
     codes = (C.c_int * 8)(*range(8))
     xin = torch.empty(8, p, p, p, 16, dtype=torch.bfloat16, device=dev)
     report("gather_patch_tta (8 mirrors, 4->16 ch)",
-           timed(lambda: L.check(lib.bsg_gather_patch_tta(ptr(vol), 4, Z, Y, X, 27, 56, 56, p, p, p, codes, 8, ptr(xin), 16, 0,
+           timed(lambda: L.check(lib.bsg_gather_patch_tta(ptr(vol), 4, Z, Y, X, 27, 56, 56, p, p, p, codes, 8, ptr(xin), 16, 0, 0,
                                                           L.stream_ptr()))), 4 * pv * 4 + 8 * pv * 32)
     feat = torch.randn(8, p, p, p, 32, device=dev).to(torch.bfloat16)
     acc = torch.zeros(3, Z, Y, X, device=dev)

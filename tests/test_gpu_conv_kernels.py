@@ -107,3 +107,59 @@ def test_fp16_range_flag(cin, cout, shape):
     assert int(flag.item()) == 0 and torch.isfinite(got).all()
     _, _, got, _, _, _, flag = _conv_case(cin, cout, 1, D, H, W, False, seed=5, scale_in=300.0, scale_w=300.0, want_flag=True)
     assert int(flag.item()) == 1 and not torch.isfinite(got).all()
+
+
+@pytest.mark.parametrize("cout,stats,shape", [(32, False, (16, 16, 16)), (64, True, (8, 32, 24)), (64, False, (4, 16, 16))])
+def test_brick_conv_3x3x1_kernel(cout, stats, shape):
+    """kw_taps = 1: a (3, 3, 1) kernel over 16 input channels — the kw-packed first layer of the network — against
+    torch's conv3d with the same kernel."""
+    L, P, dev = _setup()
+    D, H, W = shape
+    N, cin = 2, 16
+    g = torch.Generator(device="cpu").manual_seed(cout + D)
+    x = torch.randn(N, cin, D, H, W, generator=g).to(torch.float16)
+    xb = x.permute(0, 2, 3, 4, 1).contiguous().to(dev)
+    w = torch.randn(cout, cin, 3, 3, 1, generator=g) / (9 * cin) ** 0.5
+    wp = torch.zeros(9, P.round_up(cout, 32), 16, dtype=torch.float16)
+    wp[:, :cout] = w[..., 0].permute(2, 3, 0, 1).reshape(9, cout, cin).to(torch.float16)  # taps (kd, kh)
+    wp = wp.to(dev)
+    b = torch.randn(cout, generator=g).to(dev)
+    bp = P.pad_bias(b, cout).to(dev)
+    out = torch.zeros(N, D, H, W, cout, dtype=torch.float16, device=dev)
+    st = torch.zeros(N, cout, 2, dtype=torch.float64, device=dev) if stats else None
+    plan = L.ConvPlan(kind=L.BSG_CONV_K3, stride=1, N=N, D=D, H=H, W=W, cin=cin, in_ptr=xb.data_ptr(), in_ctot=cin, cout=cout,
+                      out_ptr=out.data_ptr(), out_ctot=cout, out_coff=0, weights=wp.data_ptr(), bias=bp.data_ptr(),
+                      act=0 if stats else 1, slope=0.01, stats=st.data_ptr() if stats else None, use_khshift=-1, max_ctas=0,
+                      in_f16=1, out_f16=1, kw_taps=1)
+    plan.run()
+    torch.cuda.synchronize()
+    ref = F.conv3d(x.float().to(dev), w.to(torch.float16).float().to(dev), b, padding=(1, 1, 0))
+    pre = ref
+    if not stats:
+        ref = F.leaky_relu(ref, 0.01)
+    got = out.permute(0, 4, 1, 2, 3).float()
+    err = (got - ref).abs().max().item()
+    assert err <= 3e-3 * max(ref.abs().max().item(), 1.0)
+    if stats:
+        s_ref = torch.stack([pre.sum(dim=(2, 3, 4)), (pre * pre).sum(dim=(2, 3, 4))], dim=-1)
+        assert ((st.float() - s_ref).abs() / (s_ref.abs() + 1.0)).max().item() < 1e-3
+
+
+def test_gather_kwpack_matches_torch_layout():
+    """bsg_gather_patch_tta(kwpack = 1): every mirrored copy of the tile holds, per voxel, its three w neighbours' channels
+    in the COPY's orientation (zeros outside the tile) — the same tensor packing.kwpack_input builds from the flipped tile."""
+    import ctypes as C
+    L, P, dev = _setup()
+    vol = torch.randn(4, 20, 24, 40, generator=torch.Generator().manual_seed(3)).to(dev)
+    p0, p1, p2 = 16, 16, 32
+    z0, y0, x0 = 3, 5, 7
+    codes = (C.c_int * 8)(*range(8))
+    out = torch.zeros(8, p0, p1, p2, 16, dtype=torch.float16, device=dev)
+    L.check(L.lib().bsg_gather_patch_tta(C.c_void_p(vol.data_ptr()), 4, 20, 24, 40, z0, y0, x0, p0, p1, p2, codes, 8,
+                                         C.c_void_p(out.data_ptr()), 16, 1, 1, L.stream_ptr()))
+    tile = vol[:, z0:z0 + p0, y0:y0 + p1, x0:x0 + p2]
+    for m in range(8):
+        dims = [a for a, bit in ((3, 1), (2, 2), (1, 4)) if m & bit]
+        flipped = torch.flip(tile, dims) if dims else tile
+        ref = P.kwpack_input(flipped[None], 16)[0].to(torch.float16)
+        assert torch.equal(out[m], ref), f"mirror code {m}"
