@@ -29,6 +29,10 @@ struct PeerFinalizeParams {
     int order[kMaxClasses];
 };
 
+__device__ __forceinline__ bool exceeds_half(float a, float w) {  // fl32(a / w) > 0.5, exactly (see tail.cu)
+    return static_cast<double>(a) > static_cast<double>(w) * (0.5 + 0x1p-25);
+}
+
 __global__ void __launch_bounds__(kThreads) peer_finalize_kernel(const PeerFinalizeParams fp, const float* __restrict__ wsum,
                                                                  size_t nvox, size_t v0, size_t nv) {
     __shared__ const float* s_acc[kMaxPtrs];
@@ -38,6 +42,7 @@ __global__ void __launch_bounds__(kThreads) peer_finalize_kernel(const PeerFinal
     __syncthreads();
     const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
     const size_t ngroups = nv / 4;
+    const bool by_compare = fp.K == 1 && fp.mode == 1;
     for (size_t g = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
         const size_t i = v0 + g * 4;
         const float4 wv = __ldg(reinterpret_cast<const float4*>(wsum + i));
@@ -65,8 +70,11 @@ __global__ void __launch_bounds__(kThreads) peer_finalize_kernel(const PeerFinal
                                     a.x += b[r].x, a.y += b[r].y, a.z += b[r].z, a.w += b[r].w;
                             }
                     }
-                    const float q[4] = {__fdiv_rn(a.x, wv.x), __fdiv_rn(a.y, wv.y), __fdiv_rn(a.z, wv.z),
-                                        __fdiv_rn(a.w, wv.w)};
+                    // one fold + regions decision: fl(a / w) > 0.5 decided exactly without the division (tail.cu)
+                    const float q[4] = {by_compare ? (exceeds_half(a.x, wv.x) ? 1.f : 0.f) : __fdiv_rn(a.x, wv.x),
+                                        by_compare ? (exceeds_half(a.y, wv.y) ? 1.f : 0.f) : __fdiv_rn(a.y, wv.y),
+                                        by_compare ? (exceeds_half(a.z, wv.z) ? 1.f : 0.f) : __fdiv_rn(a.z, wv.z),
+                                        by_compare ? (exceeds_half(a.w, wv.w) ? 1.f : 0.f) : __fdiv_rn(a.w, wv.w)};
 #pragma unroll
                     for (int v = 0; v < 4; ++v) s[v] = j == 0 ? q[v] : s[v] + q[v];
                 }

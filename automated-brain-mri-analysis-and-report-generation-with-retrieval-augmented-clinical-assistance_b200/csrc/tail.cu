@@ -342,6 +342,13 @@ struct FinalizeParams {
     int order[kMaxClasses];  // regions_class_order
 };
 
+// fl32(a / w) > 0.5 for w > 0, without the division: round-to-nearest-even maps the quotient to a float above 0.5 iff it
+// lies above the midpoint of 0.5 and its successor, 0.5 * (1 + 2^-24) (the tie goes to 0.5, the even one); a and w have
+// 24-bit significands, so w * (0.5 + 2^-25) is exact in fp64 and the comparison is exact.
+__device__ __forceinline__ bool exceeds_half(float a, float w) {
+    return static_cast<double>(a) > static_cast<double>(w) * (0.5 + 0x1p-25);
+}
+
 // One voxel's decision from its class probabilities (argmax, or the ordered > 0.5 assignment of the region trainers).
 __device__ __forceinline__ int decide_label(const FinalizeParams& fp, const float (&p)[kMaxClasses]) {
     int lab = 0;
@@ -384,6 +391,9 @@ __global__ void __launch_bounds__(kThreads) finalize_kernel(const FinalizeParams
         }
         if constexpr (K1) {
             float a[kMaxClasses][VEC];
+            // regions decision without probabilities: fl(a / w) > 0.5 is decided EXACTLY by one fp64 product and compare
+            // (see exceeds_half) — the 12 IEEE divisions per thread made this pass ALU-bound at 18-22 % of HBM bandwidth
+            const bool by_compare = fp.mode == 1 && probs == nullptr;
 #pragma unroll
             for (int k = 0; k < kMaxClasses; ++k) {
                 if (k < fp.ncls) {
@@ -399,7 +409,8 @@ __global__ void __launch_bounds__(kThreads) finalize_kernel(const FinalizeParams
             for (int k = 0; k < kMaxClasses; ++k) {
                 if (k < fp.ncls) {
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) p[v][k] = __fdiv_rn(a[k][v], wv[v]);
+                    for (int v = 0; v < VEC; ++v)
+                        p[v][k] = by_compare ? (exceeds_half(a[k][v], wv[v]) ? 1.f : 0.f) : __fdiv_rn(a[k][v], wv[v]);
                 }
             }
         } else {
