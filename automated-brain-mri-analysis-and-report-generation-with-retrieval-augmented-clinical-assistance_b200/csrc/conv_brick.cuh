@@ -46,9 +46,14 @@ struct BrickArgs {
 };
 
 constexpr int kBrickThreads = 224;  // 4 epilogue warps + activation producer + weight producer + MMA issuer
-// CC == 16 instantiations run a second epilogue warp group (see conv_brick.cu)
-// ... and so do the XF instantiations (warps 7-10: in-consumer norm transform)
-constexpr int brick_threads(int cc, bool xf = false) { return (cc == 16 || xf) ? kBrickThreads + 128 : kBrickThreads; }
+// Epilogue warp groups: CC == 16 (the 4-channel network input: few MMAs per plane, the epilogue is the bottleneck) runs a
+// second group on warps 7..10 — except with norm statistics at NT = 64, where the 352-thread register budget (186) would
+// force the per-tile shuffle reduction (~4x the epilogue instructions): one group with per-thread sums is faster there.
+__host__ __device__ constexpr int brick_epi_groups(int cc, int nt, bool stats) { return (cc == 16 && !(stats && nt == 64)) ? 2 : 1; }
+// ... the XF instantiations use warps 7-10 for the in-consumer norm transform
+__host__ __device__ constexpr int brick_threads(int cc, int nt, bool stats, bool xf) {
+    return (brick_epi_groups(cc, nt, stats) == 2 || xf) ? kBrickThreads + 128 : kBrickThreads;
+}
 cudaError_t launch_conv_brick_xf(const BrickArgs& a, int cc, int nt, int grid, size_t smem_bytes, cudaStream_t stream);
 cudaError_t launch_conv_brick(const BrickArgs& a, int cc, int nt, int grid, size_t smem_bytes, cudaStream_t stream);
 size_t conv_brick_smem_bytes(const BrickArgs& a);

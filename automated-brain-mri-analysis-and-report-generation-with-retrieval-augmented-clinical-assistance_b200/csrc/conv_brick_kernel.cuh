@@ -73,10 +73,10 @@ __device__ __forceinline__ Unit decode_unit(const BrickArgs& a, int u, int P) {
 // Conv padding: the activation map of an XF plan is encoded with NaN out-of-bounds fill, so padding arrives as NaN
 // and is written back as 0 (zeros in y-space, as the reference pads AFTER the norm); no box geometry needed.
 template <int CC, int NT, bool STATS, bool KWF, bool XF>
-__global__ void __launch_bounds__(brick_threads(CC, XF), 1) conv_brick_kernel(const __grid_constant__ BrickArgs a) {
+__global__ void __launch_bounds__(brick_threads(CC, NT, STATS, XF), 1) conv_brick_kernel(const __grid_constant__ BrickArgs a) {
     static_assert(!(XF && CC == 16), "the in-consumer norm transform needs CC >= 32");
     constexpr int P = 256 / NT;
-    constexpr int kEpiGroups = (CC == 16) ? 2 : 1;
+    constexpr int kEpiGroups = brick_epi_groups(CC, NT, STATS);
     // 352-thread instantiations (second epilogue group, or the XF transform warps) have 186 registers per thread: the
     // NT = 64 statistics are then reduced per tile (shuffles) instead of kept as 128 per-thread sums
     constexpr bool kThreadAcc = !((kEpiGroups == 2 || XF) && NT == 64);
@@ -469,7 +469,7 @@ cudaError_t launch_variant(const BrickArgs& a, int grid, size_t smem_bytes, cuda
     static unsigned long long attr_done = 0;  // per device
     if (cudaError_t e = ensure_max_smem(conv_brick_kernel<CC, NT, STATS, KWF, XF>, &attr_done, 232448); e != cudaSuccess)
         return e;
-    conv_brick_kernel<CC, NT, STATS, KWF, XF><<<grid, brick_threads(CC, XF), smem_bytes, stream>>>(a);
+    conv_brick_kernel<CC, NT, STATS, KWF, XF><<<grid, brick_threads(CC, NT, STATS, XF), smem_bytes, stream>>>(a);
     return cudaGetLastError();
 }
 

@@ -759,17 +759,19 @@ def run_ours(args):
         post = None
         if out is not None and not sharded_only:
             post = {}
-            pend = pipe.submit(dev_vols[0], dev_gts[0])
-            pend["done"].synchronize()
-            t0 = time.perf_counter()
-            pipe.finish(pend)
-            post["inference_output_ms"] = (time.perf_counter() - t0) * 1e3
             bl = torch.from_numpy(np.ascontiguousarray(np.roll(gt_hosts[0].numpy(), 3, axis=0))).to(dev)
-            pend = pipe.submit(dev_vols[0], dev_gts[0])
-            pend["done"].synchronize()
-            t0 = time.perf_counter()
-            r = pipe.finish(pend, labels=bl)
-            post["blobby_labels_ms"] = (time.perf_counter() - t0) * 1e3
+
+            def post_ms(labels):  # second of two calls: the first re-warms the allocator after the passes above
+                for _ in range(2):
+                    pend = pipe.submit(dev_vols[0], dev_gts[0])
+                    pend["done"].synchronize()
+                    t0 = time.perf_counter()
+                    r = pipe.finish(pend, labels=labels)
+                    dt = (time.perf_counter() - t0) * 1e3
+                return dt, r
+
+            post["inference_output_ms"], _ = post_ms(None)
+            post["blobby_labels_ms"], r = post_ms(bl)
             post["blobby_components"] = r["components"]["num_components"] + r["components"].get("excluded_fragments", 0)
             post["note"] = ("the random-init nets' own output is one giant component + ~1e5 single-voxel enhancing foci; "
                             "blobby = SURVEY §8d config-4 label volumes (smoothed-noise thresholds)")
