@@ -104,6 +104,9 @@ _EXTRA_SIGS = {
     "bsg_finalize": [C.POINTER(_vp), _i, _vp, _i, _sz, _i, C.POINTER(_i), _vp, _vp, _vp],
     "bsg_finalize_peer": [_vp, _i, _i, _vp, _i, _sz, _sz, _sz, _i, C.POINTER(_i), _vp, _i, _vp],
     "bsg_enable_peer_access": [_i],
+    "bsg_ipc_export": [_vp, _vp, C.POINTER(_sz)],
+    "bsg_ipc_open": [_vp, C.POINTER(_vp)],
+    "bsg_ipc_close": [_vp],
     "bsg_nccl_unique_id": [_vp],
     "bsg_nccl_comm_create": [_vp, _i, _i, C.POINTER(_vp)],
     "bsg_nccl_reduce_accumulator": [_vp, _vp, _sz, _i, _vp],

@@ -11,6 +11,7 @@
 //                          rank ever holds or finalizes more than its 1/R slab.
 //   bsg_nccl_*             the plain-NCCL route (one ncclAllReduce / ncclReduce of the accumulator) over the library's
 //                          own communicator; libnccl is resolved at run time (dlopen), so the library loads without it.
+#include <cuda.h>
 #include <dlfcn.h>
 #include <nccl.h>
 #include "bsg_common.cuh"
@@ -176,6 +177,50 @@ int bsg_finalize_peer(const float* const* acc_table_dev, int K, int R, const flo
     peer_finalize_kernel<<<grid_for(nv / 4, kThreads, 8), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(fp, wsum, nvox,
                                                                                                           v0, nv);
     BSG_CUDA_OK(cudaGetLastError());
+    return BSG_OK;
+}
+
+// ---- CUDA IPC: peers map a rank's buffer into THEIR device's address space.  The handle is opened on the consuming
+// device (cudaIpcMemLazyEnablePeerAccess), which is what makes plain loads / stores from that device's kernels legal;
+// a mapping created under the producing device's context (what torch's tensor sharing does) is not reachable from
+// kernels running on another device.
+int bsg_ipc_export(const void* ptr, void* handle64_host, size_t* offset_out) {
+    BSG_REQUIRE(ptr != nullptr && handle64_host != nullptr && offset_out != nullptr, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+    // the handle names the whole allocation the pointer lies in (a caching allocator may have carved the buffer out of a
+    // larger cudaMalloc block): report the offset of ptr inside it
+    typedef CUresult (*GetRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+    static GetRangeFn get_range = nullptr;
+    if (get_range == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        BSG_CUDA_OK(cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || p == nullptr)
+            return set_error(BSG_ECUDA, "cuMemGetAddressRange entry point not available");
+        get_range = reinterpret_cast<GetRangeFn>(p);
+    }
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    if (get_range(&base, &size, reinterpret_cast<CUdeviceptr>(ptr)) != CUDA_SUCCESS)
+        return set_error(BSG_ECUDA, "cuMemGetAddressRange failed for %p", ptr);
+    cudaIpcMemHandle_t h;
+    BSG_CUDA_OK(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base)));
+    memcpy(handle64_host, &h, sizeof(h));
+    *offset_out = static_cast<size_t>(reinterpret_cast<CUdeviceptr>(ptr) - base);
+    return BSG_OK;
+}
+
+int bsg_ipc_open(const void* handle64_host, void** base_out) {
+    BSG_REQUIRE(handle64_host != nullptr && base_out != nullptr, "null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64_host, sizeof(h));
+    BSG_CUDA_OK(cudaIpcOpenMemHandle(base_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return BSG_OK;
+}
+
+int bsg_ipc_close(void* base) {
+    if (base == nullptr) return BSG_OK;
+    BSG_CUDA_OK(cudaIpcCloseMemHandle(base));
     return BSG_OK;
 }
 

@@ -5,8 +5,8 @@ per-fold predict calls), :128 (fold mean), :144-156 (regions decision).
 
 Two routes, same result up to the order of the fp32 additions:
 
-* peer (default on one NVSwitch box): every accumulator and label volume lives in memory the other ranks have mapped
-  (CUDA IPC through torch's shared-storage handles).  ONE kernel per model and rank — bsg_finalize_peer — reads the
+* peer (default on one NVSwitch box): every accumulator and label volume lives in a slab the other ranks have mapped
+  into their own device's address space (CUDA IPC: bsg_ipc_export / bsg_ipc_open).  ONE kernel per model and rank — bsg_finalize_peer — reads the
   rank's voxel slab of ALL ranks' accumulators over NVLink, sums in rank order, divides by the weight sum, averages
   the folds, decides, and stores the uint8 labels of the slab into EVERY rank's label volume.  Two tiny NCCL
   all-reduces order the ranks around it (all accumulators complete before / all slabs written after).
@@ -38,7 +38,9 @@ class ShardedExchange:
         if route not in ("peer", "nccl"):
             raise ValueError(f"route {route!r}: expected 'peer' or 'nccl'")
         self.route = route
-        self._bufs = {}     # key -> (local tensor, [per-rank tensors])
+        self._bufs = {}     # key -> (local tensor, [address of every rank's tensor, as mapped into this process])
+        self._slabs = []    # device allocations the buffers are carved from (one IPC handle each)
+        self._opened = {}   # IPC handle bytes -> base address of the mapping in this process
         self._tables = {}   # key tuple -> device pointer table
         self._token = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._comm = None
@@ -57,27 +59,53 @@ class ShardedExchange:
                     L.check(L.lib().bsg_enable_peer_access(d))
 
     # ------------------------------------------------------------------ shared buffers
+    SLAB_BYTES = 384 << 20  # two 107 MB accumulators + two 9 MB label volumes of a BraTS case, with room to spare
+
+    def _new_slab(self, min_bytes):
+        """One device allocation per rank, exported with CUDA IPC and mapped by every other rank.  Collective."""
+        nbytes = max(self.SLAB_BYTES, (int(min_bytes) + (1 << 21) - 1) >> 21 << 21)
+        local = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        bases = [local.data_ptr()] * self.world
+        if self.route == "peer" and self.world > 1:
+            lib = L.lib()
+            handle = C.create_string_buffer(64)
+            off = C.c_size_t(0)
+            L.check(lib.bsg_ipc_export(_ptr(local), handle, C.byref(off)))
+            gathered = [None] * self.world
+            self.dist.all_gather_object(gathered, (bytes(handle.raw), int(off.value)))
+            bases = []
+            for r, (hbytes, offset) in enumerate(gathered):
+                if r == self.rank:
+                    bases.append(local.data_ptr())
+                    continue
+                if hbytes not in self._opened:  # an allocation may be opened once per process
+                    base = C.c_void_p()
+                    L.check(lib.bsg_ipc_open(C.create_string_buffer(hbytes, 64), C.byref(base)))
+                    self._opened[hbytes] = base.value
+                bases.append(self._opened[hbytes] + offset)
+        self._slabs.append({"local": local, "bases": bases, "used": 0})
+        return self._slabs[-1]
+
     def shared(self, key, shape, dtype):
-        """A device tensor of this rank plus every other rank's tensor of the same key, mapped into this process.
-        Collective: all ranks call it with the same keys in the same order."""
+        """A device tensor of this rank plus the address of every rank's tensor of the same key as seen from THIS rank's
+        device.  Collective: all ranks call it with the same keys in the same order."""
         if key in self._bufs:
             return self._bufs[key]
-        local = torch.zeros(shape, dtype=dtype, device=self.device)
-        if self.route != "peer" or self.world == 1:
-            self._bufs[key] = (local, [local])
-            return self._bufs[key]
-        from torch.multiprocessing.reductions import reduce_tensor
-        fn, args = reduce_tensor(local)
-        gathered = [None] * self.world
-        self.dist.all_gather_object(gathered, (fn, args))
-        views = []
-        for r, (f, a) in enumerate(gathered):
-            views.append(local if r == self.rank else f(*a))
-        self._bufs[key] = (local, views)
+        numel = 1
+        for d in shape:
+            numel *= int(d)
+        nbytes = numel * torch.empty((), dtype=dtype).element_size()
+        slab = self._slabs[-1] if self._slabs else None
+        if slab is None or slab["used"] + nbytes > slab["local"].numel():
+            slab = self._new_slab(nbytes)
+        off = slab["used"]
+        slab["used"] = (off + nbytes + 255) // 256 * 256
+        local = slab["local"][off:off + nbytes].view(dtype).view(shape)
+        self._bufs[key] = (local, [b + off for b in slab["bases"]])
         return self._bufs[key]
 
-    def _table(self, tensors):
-        key = tuple(t.data_ptr() for t in tensors)
+    def _table(self, ptrs):
+        key = tuple(int(p) for p in ptrs)
         if key not in self._tables:
             self._tables[key] = torch.tensor(list(key), dtype=torch.int64, device=self.device)
         return self._tables[key]
@@ -100,11 +128,11 @@ class ShardedExchange:
         if regions_class_order is not None:
             mode = 1
             order = (C.c_int * ncls)(*[int(c) for c in regions_class_order])
-        seg_local, seg_views = self.shared(seg_key, (nvox,), torch.uint8)
+        seg_local, seg_ptrs = self.shared(seg_key, (nvox,), torch.uint8)
         if self.route == "peer" and nvox % 4 == 0:
-            accs = [self._bufs[k][1] for k in acc_keys]  # [K][R]
+            accs = [self._bufs[k][1] for k in acc_keys]  # [K][R] addresses
             table = self._table([accs[k][r] for k in range(K) for r in range(self.world)])
-            segs = self._table(seg_views)
+            segs = self._table(seg_ptrs)
             per = -(-(nvox // 4) // self.world) * 4
             v0 = min(self.rank * per, nvox)
             nv = min(per, nvox - v0)
@@ -148,8 +176,12 @@ class ShardedExchange:
             self.dist.barrier()
         self._tables.clear()
         self._bufs.clear()
-        import gc
-        gc.collect()  # the peers' mapped storages are released before the producers go away
+        for base in self._opened.values():
+            L.check(L.lib().bsg_ipc_close(C.c_void_p(base)))
+        self._opened.clear()
+        if self.dist.is_initialized():
+            self.dist.barrier()  # nobody frees a slab a peer still has mapped
+        self._slabs.clear()
         if self._comm is not None:
             L.lib().bsg_nccl_comm_destroy(self._comm)
             self._comm = None

@@ -314,6 +314,13 @@ int bsg_finalize_peer(const float* const* acc_table_dev, int K, int R, const flo
                       size_t nv, int mode, const int* order_host, uint8_t* const* seg_table_dev, int nseg, void* stream);
 /* cudaDeviceEnablePeerAccess(current -> peer_device), idempotent. */
 int bsg_enable_peer_access(int peer_device);
+/* CUDA IPC plumbing for the peer route (ranks are processes).  bsg_ipc_export: the 64-byte handle of the ALLOCATION that
+ * contains the device pointer `ptr` and ptr's offset inside it (a caching allocator may sub-allocate).  bsg_ipc_open: maps
+ * such an allocation into the CURRENT device's address space (lazy peer access) and returns its base — peer pointer =
+ * base + offset; open each handle once per process.  bsg_ipc_close unmaps it. */
+int bsg_ipc_export(const void* ptr, void* handle64_host, size_t* offset_out);
+int bsg_ipc_open(const void* handle64_host, void** base_out);
+int bsg_ipc_close(void* base);
 
 /* NCCL route — `ncclAllReduce(sum)` (root < 0) or `ncclReduce(sum)` to `root` of the fp32 accumulator in place, over
  * a communicator the library owns: rank 0 calls bsg_nccl_unique_id (128 bytes, host), ships the id to the other ranks
