@@ -47,9 +47,10 @@ struct BrickArgs {
 
 constexpr int kBrickThreads = 224;  // 4 epilogue warps + activation producer + weight producer + MMA issuer
 // Epilogue warp groups: CC == 16 (the 4-channel network input: few MMAs per plane, the epilogue is the bottleneck) runs a
-// second group on warps 7..10 — except with norm statistics at NT = 64, where the 352-thread register budget (186) would
-// force the per-tile shuffle reduction (~4x the epilogue instructions): one group with per-thread sums is faster there.
-__host__ __device__ constexpr int brick_epi_groups(int cc, int nt, bool stats) { return (cc == 16 && !(stats && nt == 64)) ? 2 : 1; }
+// second group on warps 7..10.  The groups take alternate planes — except with norm statistics at NT = 64, where they
+// take the two 32-column halves of every plane instead: a thread then keeps 64 statistic sums, not 128, which fits the
+// 352-thread register budget (186) without falling back to the per-tile shuffle reduction (~4x the instructions).
+__host__ __device__ constexpr int brick_epi_groups(int cc, int nt, bool stats) { return cc == 16 ? 2 : 1; }
 // ... the XF instantiations use warps 7-10 for the in-consumer norm transform
 __host__ __device__ constexpr int brick_threads(int cc, int nt, bool stats, bool xf) {
     return (brick_epi_groups(cc, nt, stats) == 2 || xf) ? kBrickThreads + 128 : kBrickThreads;

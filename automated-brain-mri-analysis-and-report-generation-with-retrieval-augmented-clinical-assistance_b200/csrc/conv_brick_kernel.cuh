@@ -79,7 +79,10 @@ __global__ void __launch_bounds__(brick_threads(CC, NT, STATS, XF), 1) conv_bric
     constexpr int kEpiGroups = brick_epi_groups(CC, NT, STATS);
     // 352-thread instantiations (second epilogue group, or the XF transform warps) have 186 registers per thread: the
     // NT = 64 statistics are then reduced per tile (shuffles) instead of kept as 128 per-thread sums
-    constexpr bool kThreadAcc = !((kEpiGroups == 2 || XF) && NT == 64);
+    // column split: the two epilogue groups share every plane (32 columns each) instead of alternating planes
+    constexpr bool kColSplit = kEpiGroups == 2 && NT == 64 && STATS;
+    constexpr int kChunks = kColSplit ? 1 : NT / 32;  // 32-column chunks one epilogue warp handles per plane
+    constexpr bool kThreadAcc = !(XF && NT == 64);
     constexpr uint32_t kRowBytes = CC * 2u;
     constexpr uint32_t kAtom = 8u * kRowBytes;              // 8 rows: one swizzle atom, one h step of the 8-wide box
     constexpr uint32_t kTapBytes = NT * kRowBytes;          // one tap of a weight slab
@@ -117,7 +120,7 @@ __global__ void __launch_bounds__(brick_threads(CC, NT, STATS, XF), 1) conv_bric
         }
         for (int i = 0; i < kMaxAcc; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+            mbar_init(&tempty_bar[i], kColSplit ? 8 : 4);  // one arrive per epilogue warp that reads the plane
         }
         fence_barrier_init();
     }
@@ -403,10 +406,11 @@ __global__ void __launch_bounds__(brick_threads(CC, NT, STATS, XF), 1) conv_bric
         epi.guard = (a.overflow != nullptr && a.out_f16) ? 1 : 0;
         EpiGuard guard;
         guard.init();
-        StatAcc sacc[NT / 32];
-        float t1[NT / 32][32], t2[NT / 32][32];  // per-thread sums over the planes of one brick (STATS only)
+        StatAcc sacc[kChunks];
+        float t1[kChunks][32], t2[kChunks][32];  // per-thread sums over the planes of one brick (STATS only)
+        const int cb0 = kColSplit ? group * 32 : 0;  // first column of this warp's chunk(s)
 #pragma unroll
-        for (int j = 0; j < NT / 32; ++j) {
+        for (int j = 0; j < kChunks; ++j) {
             sacc[j].s1 = sacc[j].s2 = 0.f;
 #pragma unroll
             for (int i = 0; i < 32; ++i) t1[j][i] = t2[j][i] = 0.f;
@@ -418,23 +422,24 @@ __global__ void __launch_bounds__(brick_threads(CC, NT, STATS, XF), 1) conv_bric
             const uint32_t bb = tcount & 1u, par = (tcount >> 1) & 1u;
             if (STATS && t.n != stat_n) {
 #pragma unroll
-                for (int j = 0; j < NT / 32; ++j) flush_stats(epi, sacc[j], j * 32, lane, stat_n);
+                for (int j = 0; j < kChunks; ++j) flush_stats(epi, sacc[j], cb0 + j * 32, lane, stat_n);
                 stat_n = t.n;
             }
             __nv_bfloat16* obase = a.out + t.n * a.os_n + static_cast<long long>(t.h0 + ih) * a.os_h +
                                    static_cast<long long>(t.w0 + iw) * a.os_w + a.out_c_off;
-            for (int q = group; q < P; q += kEpiGroups) {
+            for (int q = kColSplit ? 0 : group; q < P; q += kColSplit ? 1 : kEpiGroups) {
                 const uint32_t slot = bb * P + static_cast<uint32_t>(q);
                 mbar_wait(&tfull_bar[slot], par);
                 tc_fence_after();
                 __nv_bfloat16* orow = obase + static_cast<long long>(t.d0 + q) * a.os_d;
                 const uint32_t t_addr = tmem_base + (bb * P + static_cast<uint32_t>(P - 1 - q)) * NT + (static_cast<uint32_t>(q4 * 32) << 16);
 #pragma unroll
-                for (int cb = 0; cb < NT; cb += 32) {
+                for (int j = 0; j < kChunks; ++j) {
+                    const int cb = cb0 + j * 32;
                     uint32_t v[32];
                     tmem_ld_32x32(t_addr + cb, v);
                     tmem_ld_wait();
-                    epilogue_32cols<kThreadAcc>(v, epi, cb, true, lane, sacc[cb / 32], orow, t1[cb / 32], t2[cb / 32], guard);
+                    epilogue_32cols<kThreadAcc>(v, epi, cb, true, lane, sacc[j], orow, t1[j], t2[j], guard);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -442,7 +447,7 @@ __global__ void __launch_bounds__(brick_threads(CC, NT, STATS, XF), 1) conv_bric
             }
             if (STATS && kThreadAcc) {  // one warp reduction per brick instead of one per plane
 #pragma unroll
-                for (int j = 0; j < NT / 32; ++j) {
+                for (int j = 0; j < kChunks; ++j) {
                     stats_transpose_reduce(t1[j], t2[j], lane, sacc[j]);
 #pragma unroll
                     for (int i = 0; i < 32; ++i) t1[j][i] = t2[j][i] = 0.f;
@@ -451,7 +456,7 @@ __global__ void __launch_bounds__(brick_threads(CC, NT, STATS, XF), 1) conv_bric
         }
         if (STATS) {
 #pragma unroll
-            for (int j = 0; j < NT / 32; ++j) flush_stats(epi, sacc[j], j * 32, lane, stat_n);
+            for (int j = 0; j < kChunks; ++j) flush_stats(epi, sacc[j], cb0 + j * 32, lane, stat_n);
         }
         if (epi.guard) guard.flush(a.overflow);
     }
