@@ -5,6 +5,7 @@ Host logic only — step grid, Gaussian importance map, work-item packing, accum
 operation is a kernel of libbrainseg_b200.so.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -107,7 +108,11 @@ class SlidingWindowPredictor:
 
     def _lane_streams(self):
         if self._streams is None:
-            self._streams = [torch.cuda.Stream(self.device) for _ in self.engines] if len(self.engines) > 1 else [None]
+            # high-priority streams: when the post-processing of the previous case (second stream of the pipeline) and the
+            # forwards of this one both have blocks to place, the forwards go first
+            prio = int(os.environ.get("BSG_LANE_PRIORITY", "-1"))
+            self._streams = [torch.cuda.Stream(self.device, priority=prio) for _ in self.engines] \
+                if len(self.engines) > 1 else [None]
         return self._streams
 
     def geometry(self, shape):
