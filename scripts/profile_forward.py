@@ -9,17 +9,18 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
-import bench as B  # noqa: E402
+import synthetic_case as SY  # noqa: E402
 from brainseg_b200 import sliding  # noqa: E402
-from oracle import synthetic as SY  # noqa: E402
+
+PATCH = (128, 128, 128)
 
 
 def main():
     torch.cuda.set_device(0)
-    m1, m2 = B.build_models("large")
+    m1, m2 = SY.build_benchmark_models("large")
     vol = torch.from_numpy(SY.case_volume(0, (4, 128, 128, 136))).cuda()  # 2 tiles along x
     for net in (m1, m2):
-        pred = sliding.SlidingWindowPredictor(net.engines_for(B.PATCH, 8, 1), 0.5, True, sliding.ALL_MIRROR_CODES,
+        pred = sliding.SlidingWindowPredictor(net.engines_for(PATCH, 8, 1), 0.5, True, sliding.ALL_MIRROR_CODES,
                                               net._nonlin_name())
         for _ in range(2):  # second pass = warm
             acc = pred.accumulate(vol)
