@@ -82,7 +82,12 @@ int plan_brick(const bsg_conv_desc* d, bsg_conv_plan* p) {
     if (d->W % 8 != 0 || d->H % 16 != 0 || d->D % P != 0) return 0;
     BrickArgs& a = p->bargs;
     memset(&a, 0, sizeof(a));
-    const int cc = (d->cin % 64 == 0) ? 64 : (d->cin % 32 == 0 ? 32 : 16);
+    int cc = (d->cin % 64 == 0) ? 64 : (d->cin % 32 == 0 ? 32 : 16);
+    // in-consumer norm: every stage passes through one more pipeline step (TMA -> transform -> MMA) and the 64-channel
+    // kw-fused stage (23 KB) leaves room for only 4 of them next to the resident slabs — ncu: tensor pipe 49 % against
+    // 63 % without the transform, shared-memory banks at 38 %, i.e. latency, not bandwidth.  32-channel chunks halve the
+    // stage (twice as many in flight) at the same slab footprint.
+    if (d->in_norm != nullptr && cc == 64 && d->cin / 32 * 3 <= 6 && d->in_norm_cc != 64) cc = 32;
     a.P = P;
     a.D = d->D;
     a.tw = d->W / 8;

@@ -179,7 +179,8 @@ class UNetEngine:
         if claim is not None and self.fuse_norm and src.coff == 0 and src.c == src.ctot:
             table = torch.zeros(self.batch, cin_pad, 4, dtype=torch.float32, device=self.device)
             try:
-                plan = L.ConvPlan(in_norm=table.data_ptr(), in_norm_c=cin_pad, **desc)
+                plan = L.ConvPlan(in_norm=table.data_ptr(), in_norm_c=cin_pad,
+                                  in_norm_cc=int(os.environ.get("BSG_XF_CC", "0")), **desc)
             except L.BsgError:
                 plan = None  # layer does not suit the brick kernel: the producer keeps its separate pass
             if plan is not None:

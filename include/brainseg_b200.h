@@ -87,6 +87,8 @@ typedef struct bsg_conv_desc {
                             rows written by bsg_norm_finalize_table).  Brick kernel only: bsg_conv_plan_create returns
                             BSG_EINVAL when the layer does not qualify and the caller keeps the separate pass. */
     int in_norm_c;       /* channels per batch item of the in_norm table (>= cin) */
+    int in_norm_cc;      /* 0: planner's choice of K chunk for an in_norm plan (32 channels where that keeps the weight slabs
+                            resident); 64: force 64-channel chunks (measurement switch) */
     int kw_taps;         /* 0 / 3: 3x3x3 kernel.  1: 3x3x1 kernel (kd, kh taps only), weights [9 taps (kd, kh)][cout_pad][cin]:
                             the network's first conv on an input whose w neighbours were packed into the channels by
                             bsg_gather_patch_tta(kwpack = 1) — 9 taps of K = 16 instead of 27.  Brick kernel only. */
