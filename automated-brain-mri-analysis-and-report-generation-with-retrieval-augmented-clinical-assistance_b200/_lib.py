@@ -27,7 +27,7 @@ class ConvDesc(C.Structure):
         ("act", C.c_int), ("slope", C.c_float), ("stats", C.c_void_p), ("out_f16", C.c_int),
         ("use_khshift", C.c_int), ("max_ctas", C.c_int), ("in_f16", C.c_int), ("algo", C.c_int), ("pair", C.c_int),
         ("overflow", C.c_void_p), ("in_norm", C.c_void_p), ("in_norm_c", C.c_int), ("in_norm_cc", C.c_int),
-        ("kw_taps", C.c_int),
+        ("out_split_stride", C.c_int), ("kw_taps", C.c_int),
     ]
 
 
@@ -98,6 +98,9 @@ _EXTRA_SIGS = {
     "bsg_gather_patch_tta": [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(_i), _i, _vp, _i, _i, _i, _vp],
     "bsg_norm_finalize": [_vp, _i, _i, _i, _d, _f, _vp, _vp, _vp, _vp],
     "bsg_norm_finalize_table": [_vp, _i, _i, _i, _d, _f, _vp, _vp, _f, _vp, _i, _i, _vp],
+    "bsg_norm_apply_lrelu_split": [_vp, _sz, _i, _i, _i, _i, _vp, _f, _vp],
+    "bsg_head_tta_accumulate_split": [_vp, _i, _i, _i, _i, _i, C.POINTER(_i), _i, _f, C.POINTER(_f), C.POINTER(_f), _i, _i,
+                                      _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "bsg_norm_apply_lrelu": [_vp, _sz, _i, _i, _i, _i, _vp, _f, _i, _i, _vp],
     "bsg_head_tta_accumulate": [_vp, _i, _i, _i, _i, _i, _i, C.POINTER(_i), _i, _f, C.POINTER(_f), C.POINTER(_f), _i, _i,
                                 _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _f, _vp],

@@ -26,6 +26,7 @@ struct EpiParams {
     float slope;
     int out_f16;         // 1: store IEEE fp16 instead of bf16
     int guard;           // 1: track the largest stored magnitude (fp16 range guard, see EpiGuard)
+    int split_stride;    // SPLIT epilogues: channels between the three blocks [hi | hi | lo] of the fp16x3 output
 };
 
 // fp16 range guard: IEEE fp16 saturates at 65504 and nothing downstream would notice an inf (the reference's CUDA path
@@ -121,7 +122,12 @@ static __device__ __noinline__ void stats_chunk_grouped(uint32_t taddr, const fl
 // values over the warp right away into `acc`; THREAD_ACC = true only adds them to the caller's per-thread sums
 // t1 / t2 (32 + 32 registers per chunk), which the caller reduces once per brick with stats_transpose_reduce —
 // 64 FMAs per tile and chunk instead of 62 shuffles + ~190 selects/adds.
-template <bool THREAD_ACC>
+//
+// SPLIT (fp32-equivalent mode, engine dtype "fp32"): the fp32 result y is stored as TWO fp16 numbers, hi = fp16(y) and
+// lo = fp16(y - hi) (22 significant bits between them), laid out as three channel blocks [hi | hi | lo] `split_stride`
+// channels apart — exactly the K layout the next conv contracts against [w_hi | w_lo | w_hi]:
+// y*w ~= hi*w_hi + hi*w_lo + lo*w_hi, three fp16 MMAs with fp32 accumulation per fp32 multiply-add.
+template <bool THREAD_ACC, bool SPLIT = false>
 __device__ __forceinline__ void epilogue_32cols(const uint32_t (&v)[32], const EpiParams& e, int co, bool valid, int lane,
                                                 StatAcc& acc, __nv_bfloat16* orow, float (&t1)[32], float (&t2)[32],
                                                 EpiGuard& guard) {
@@ -174,6 +180,38 @@ __device__ __forceinline__ void epilogue_32cols(const uint32_t (&v)[32], const E
 #pragma unroll
         for (int i = 0; i < 16; ++i) m = fmaxf(m, fmaxf(fabsf(f[2 * i]), fabsf(f[2 * i + 1])));
         guard.amax = m;
+    }
+    if constexpr (SPLIT) {
+        __half* base = reinterpret_cast<__half*>(orow);
+        if (co + 32 <= e.cout) {
+            uint32_t ph[16], pl[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+                const float2 hf = __half22float2(h);
+                const __half2 l = __floats2half2_rn(f[2 * i] - hf.x, f[2 * i + 1] - hf.y);
+                ph[i] = *reinterpret_cast<const uint32_t*>(&h);
+                pl[i] = *reinterpret_cast<const uint32_t*>(&l);
+            }
+#pragma unroll
+            for (int blk = 0; blk < 3; ++blk) {
+                uint4* d4 = reinterpret_cast<uint4*>(base + co + blk * e.split_stride);
+                const uint32_t* p = blk == 2 ? pl : ph;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) d4[i] = make_uint4(p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (co + i < e.cout) {
+                    const __half h = __float2half_rn(f[i]);
+                    const __half l = __float2half_rn(f[i] - __half2float(h));
+                    base[co + i] = h;
+                    base[co + i + e.split_stride] = h;
+                    base[co + i + 2 * e.split_stride] = l;
+                }
+        }
+        return;
     }
     if (co + 32 <= e.cout) {
         // one uniform branch around the whole block: a per-element `out_f16 ? half : bf16` is if-converted into BOTH

@@ -74,7 +74,7 @@ namespace {
 // Brick kernel eligibility + geometry (see conv_brick.cuh).  Returns 1 when the plan was filled, 0 when the layer
 // does not suit the brick kernel, < 0 on error.
 int plan_brick(const bsg_conv_desc* d, bsg_conv_plan* p) {
-    if (d->kind != BSG_CONV_K3 || d->stride != 1 || d->algo == 0) return 0;
+    if (d->kind != BSG_CONV_K3 || d->stride != 1 || d->algo == 0 || d->out_split_stride != 0) return 0;
     const int cout_pad = static_cast<int>(round_up(d->cout, 32));
     if (cout_pad != 32 && cout_pad != 64) return 0;
     if (d->in_norm != nullptr && d->cin % 32 != 0) return 0;  // the in-consumer transform needs K chunks of >= 32 channels
@@ -83,11 +83,10 @@ int plan_brick(const bsg_conv_desc* d, bsg_conv_plan* p) {
     BrickArgs& a = p->bargs;
     memset(&a, 0, sizeof(a));
     int cc = (d->cin % 64 == 0) ? 64 : (d->cin % 32 == 0 ? 32 : 16);
-    // in-consumer norm: every stage passes through one more pipeline step (TMA -> transform -> MMA) and the 64-channel
-    // kw-fused stage (23 KB) leaves room for only 4 of them next to the resident slabs — ncu: tensor pipe 49 % against
-    // 63 % without the transform, shared-memory banks at 38 %, i.e. latency, not bandwidth.  32-channel chunks halve the
-    // stage (twice as many in flight) at the same slab footprint.
-    if (d->in_norm != nullptr && cc == 64 && d->cin / 32 * 3 <= 6 && d->in_norm_cc != 64) cc = 32;
+    // in-consumer norm: 32-channel chunks (half the stage, twice as many in flight next to the same slabs) were measured
+    // SLOWER than 64-channel ones (64->32 @128^3 x 4: 1.19 vs 0.97 ms) — twice the MMA instructions per byte; kept as a
+    // measurement switch only
+    if (d->in_norm != nullptr && cc == 64 && d->in_norm_cc == 32 && d->cin / 32 * 3 <= 6) cc = 32;
     a.P = P;
     a.D = d->D;
     a.tw = d->W / 8;
@@ -420,6 +419,11 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
     a.out_f16 = d->out_f16;
     a.in_f16 = d->in_f16;
     a.overflow = d->overflow;
+    a.split_stride = d->out_split_stride;
+    if (a.split_stride != 0 && !(d->out_f16 && d->in_f16 && a.split_stride % 8 == 0)) {
+        delete p;
+        return set_error(BSG_EINVAL, "out_split_stride needs fp16 operands and a block stride that is a multiple of 8");
+    }
 
     const int total_tiles = a.tn * a.td * a.th * a.tw * a.n_ntiles;
     int max_ctas = d->max_ctas > 0 ? d->max_ctas : sm_count_cached();

@@ -42,10 +42,12 @@ struct ConvArgs {
     double* stats;  // [No][cout][2] running (sum, sum of squares) of the pre-activation output, or null
     int out_f16;   // 1: store IEEE fp16 instead of bf16 (raw pre-norm outputs: 3 more mantissa bits, same bytes)
     int* overflow;  // device flag, set when a stored fp16 value left the fp16 range (null: no guard)
+    int split_stride;  // != 0: fp16x3 split output [hi | hi | lo], blocks this many channels apart (conv_epilogue.cuh)
     int in_f16;    // 1: activations and weights are IEEE fp16 instead of bf16
 };
 
 cudaError_t launch_conv_tc(const ConvArgs& a, int grid, size_t smem_bytes, cudaStream_t stream);  // pair: grid even
+cudaError_t launch_conv_tc_split(const ConvArgs& a, int grid, size_t smem_bytes, cudaStream_t stream);
 size_t conv_tc_smem_bytes(const ConvArgs& a);
 
 }  // namespace bsg

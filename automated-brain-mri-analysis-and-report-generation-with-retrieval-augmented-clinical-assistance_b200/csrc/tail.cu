@@ -63,6 +63,25 @@ __global__ void __launch_bounds__(kThreads) gather_patch_kernel(const float* __r
     const int h = hw / P2, w = hw - h * P2;
     const size_t plane = static_cast<size_t>(Z) * Y * X;
     const float* src = vol + (static_cast<size_t>(z0 + d) * Y + (y0 + h)) * X + (x0 + w);
+    if (kwpack == 2) {
+        // fp16x3 split of the fp32 input (engine dtype "fp32"): channels [hi (C) | hi (C) | lo (C) | 0...]
+        for (int m = 0; m < ms.n; ++m) {
+            const int code = ms.code[m];
+            const int ow = (code & 1) ? P2 - 1 - w : w;
+            const int oh = (code & 2) ? P1 - 1 - h : h;
+            const int od = (code & 4) ? P0 - 1 - d : d;
+            __half* dst = reinterpret_cast<__half*>(out) + (((static_cast<size_t>(m) * P0 + od) * P1 + oh) * P2 + ow) * cpad;
+            for (int c = 0; c < cpad; ++c) dst[c] = __float2half_rn(0.f);
+            for (int c = 0; c < C; ++c) {
+                const float v = __ldg(src + c * plane);
+                const __half hi = __float2half_rn(v);
+                dst[c] = hi;
+                dst[C + c] = hi;
+                dst[2 * C + c] = __float2half_rn(v - __half2float(hi));
+            }
+        }
+        return;
+    }
     if (kwpack) {
         // kw-packed layout for the network's first conv (3*C <= 16): channel k*C + c of a voxel holds channel c of its
         // w-neighbour k-1 IN THE COPY's orientation (zero outside the tile = the conv's zero padding), so that the
@@ -228,6 +247,52 @@ __global__ void __launch_bounds__(kThreads) norm_apply_kernel(__nv_bfloat16* __r
     }
 }
 
+// fp16x3 split layout (engine dtype "fp32"): x = hi + lo from blocks 0 and 2 of [hi | hi | lo], normalise + LeakyReLU in
+// fp32, write the three blocks back.  One 8-channel group per thread and step, same thread-constant channel mapping.
+__global__ void __launch_bounds__(kThreads) norm_apply_split_kernel(__half* __restrict__ x, size_t V, int C, int ctot,
+                                                                    int coff, const float* __restrict__ scale_shift,
+                                                                    float slope) {
+    const int c8n = C / 8;
+    const int n = blockIdx.y;
+    const size_t j0 = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;  // multiple of c8n (host guarantees it)
+    const int c8 = static_cast<int>(j0 % c8n);
+    const size_t vstep = stride / c8n;
+    float sc[8], sh[8];
+    {
+        const float2* ss = reinterpret_cast<const float2*>(scale_shift + (static_cast<size_t>(n) * C + c8 * 8) * 2);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float2 t = __ldg(ss + k);
+            sc[k] = t.x;
+            sh[k] = t.y;
+        }
+    }
+    for (size_t v = j0 / c8n; v < V; v += vstep) {
+        __half* p = x + (static_cast<size_t>(n) * V + v) * ctot + coff + c8 * 8;
+        const uint4 uh = *reinterpret_cast<const uint4*>(p), ul = *reinterpret_cast<const uint4*>(p + 2 * C);
+        const uint32_t wh[4] = {uh.x, uh.y, uh.z, uh.w}, wl[4] = {ul.x, ul.y, ul.z, ul.w};
+        uint32_t oh[4], ol[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&wh[k]));
+            const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&wl[k]));
+            float a = fmaf(fh.x + fl.x, sc[2 * k], sh[2 * k]), b = fmaf(fh.y + fl.y, sc[2 * k + 1], sh[2 * k + 1]);
+            a = a > 0.f ? a : a * slope;
+            b = b > 0.f ? b : b * slope;
+            const __half2 h = __floats2half2_rn(a, b);
+            const float2 hf = __half22float2(h);
+            const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+            oh[k] = *reinterpret_cast<const uint32_t*>(&h);
+            ol[k] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+        const uint4 vh = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+        *reinterpret_cast<uint4*>(p) = vh;
+        *reinterpret_cast<uint4*>(p + C) = vh;
+        *reinterpret_cast<uint4*>(p + 2 * C) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- head + TTA + accumulate
 constexpr int kMaxHeadCh = 64;
 struct HeadParams {
@@ -246,7 +311,7 @@ template <int NCLS, int CFEAT>
 __global__ void __launch_bounds__(kThreads) head_tta_accumulate_kernel(
     const __nv_bfloat16* __restrict__ feat, int ctot, int P0, int P1, int P2, const MirrorSet ms,
     const __grid_constant__ HeadParams hp, const int feat_f16, const float* __restrict__ gauss, float* __restrict__ acc, int Z, int Y, int X,
-    int z0, int y0, int x0, const float* __restrict__ norm_ss, const float norm_slope) {
+    int z0, int y0, int x0, const float* __restrict__ norm_ss, const float norm_slope, const int lo_off) {
     const int hw = blockIdx.x * blockDim.x + threadIdx.x;
     if (hw >= P1 * P2) return;
     const int d = blockIdx.y;
@@ -285,6 +350,17 @@ __global__ void __launch_bounds__(kThreads) head_tta_accumulate_kernel(
                     const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&ww[k]);
                     f[2 * k] = __bfloat162float(b2.x);
                     f[2 * k + 1] = __bfloat162float(b2.y);
+                }
+            }
+            if (lo_off != 0) {  // fp16x3 split features: f = hi + lo (blocks 0 and 2 of [hi | hi | lo])
+                const uint4 ul = (q * 8 < hp.cfeat) ? __ldg(reinterpret_cast<const uint4*>(feat + v * ctot + lo_off) + q)
+                                                    : make_uint4(0, 0, 0, 0);
+                const uint32_t wl[4] = {ul.x, ul.y, ul.z, ul.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 l2 = __half22float2(*reinterpret_cast<const __half2*>(&wl[k]));
+                    f[2 * k] += l2.x;
+                    f[2 * k + 1] += l2.y;
                 }
             }
             if (norm_ss != nullptr) {
@@ -477,8 +553,9 @@ int bsg_gather_patch_tta(const float* vol, int C, int Z, int Y, int X, int z0, i
                          void* stream) {
     BSG_REQUIRE(vol != nullptr && out_bf16 != nullptr, "null argument");
     BSG_REQUIRE(cpad % 8 == 0 && cpad >= C, "cpad %d must be a multiple of 8 and >= C=%d", cpad, C);
-    BSG_REQUIRE(!kwpack || (cpad == 16 && 3 * C <= 16 && (reinterpret_cast<uintptr_t>(out_bf16) & 31) == 0),
+    BSG_REQUIRE(kwpack != 1 || (cpad == 16 && 3 * C <= 16 && (reinterpret_cast<uintptr_t>(out_bf16) & 31) == 0),
                 "kwpack needs 3 * C <= 16, cpad == 16 and a 32-byte aligned output");
+    BSG_REQUIRE(kwpack != 2 || (3 * C <= cpad && out_f16), "the fp16x3 split layout needs 3 * C <= cpad and fp16 output");
     BSG_REQUIRE(z0 >= 0 && y0 >= 0 && x0 >= 0 && z0 + P0 <= Z && y0 + P1 <= Y && x0 + P2 <= X,
                 "tile exceeds the volume");
     MirrorSet ms;
@@ -545,11 +622,10 @@ int bsg_norm_apply_lrelu(void* x_bf16, size_t voxels_per_item, int N, int C, int
     return BSG_OK;
 }
 
-int bsg_head_tta_accumulate(const void* feat_bf16, int feat_f16, int cfeat, int ctot, int P0, int P1, int P2,
-                            const int* mirror_codes_host, int nmirrors, float mirror_weight,
-                            const float* head_w_host, const float* head_b_host, int ncls, int nonlin,
-                            const float* gauss, float* acc, int Z, int Y, int X, int z0, int y0, int x0,
-                            const float* norm_scale_shift, float norm_slope, void* stream) {
+static int head_launch(const void* feat_bf16, int feat_f16, int cfeat, int ctot, int P0, int P1, int P2,
+                       const int* mirror_codes_host, int nmirrors, float mirror_weight, const float* head_w_host,
+                       const float* head_b_host, int ncls, int nonlin, const float* gauss, float* acc, int Z, int Y, int X,
+                       int z0, int y0, int x0, const float* norm_scale_shift, float norm_slope, int lo_off, void* stream) {
     BSG_REQUIRE(feat_bf16 != nullptr && head_w_host != nullptr && acc != nullptr, "null argument");
     BSG_REQUIRE(cfeat % 8 == 0 && cfeat >= 8 && cfeat <= kMaxHeadCh, "head input channels %d (8..64, multiple of 8)",
                 cfeat);
@@ -576,7 +652,7 @@ int bsg_head_tta_accumulate(const void* feat_bf16, int feat_f16, int cfeat, int 
     const __nv_bfloat16* fp = static_cast<const __nv_bfloat16*>(feat_bf16);
 #define BSG_HEAD_LAUNCH(NC, CF)                                                                                     \
     head_tta_accumulate_kernel<NC, CF><<<grid, kThreads, 0, st>>>(fp, ctot, P0, P1, P2, ms, hp, feat_f16, gauss, acc, Z, \
-                                                                  Y, X, z0, y0, x0, norm_scale_shift, norm_slope)
+                                                                  Y, X, z0, y0, x0, norm_scale_shift, norm_slope, lo_off)
     if (ncls <= 4 && cfeat <= 32)
         BSG_HEAD_LAUNCH(4, 32);
     else if (ncls <= 4)
@@ -586,6 +662,48 @@ int bsg_head_tta_accumulate(const void* feat_bf16, int feat_f16, int cfeat, int 
     else
         BSG_HEAD_LAUNCH(8, 64);
 #undef BSG_HEAD_LAUNCH
+    BSG_CUDA_OK(cudaGetLastError());
+    return BSG_OK;
+}
+
+int bsg_head_tta_accumulate(const void* feat_bf16, int feat_f16, int cfeat, int ctot, int P0, int P1, int P2,
+                            const int* mirror_codes_host, int nmirrors, float mirror_weight,
+                            const float* head_w_host, const float* head_b_host, int ncls, int nonlin,
+                            const float* gauss, float* acc, int Z, int Y, int X, int z0, int y0, int x0,
+                            const float* norm_scale_shift, float norm_slope, void* stream) {
+    return head_launch(feat_bf16, feat_f16, cfeat, ctot, P0, P1, P2, mirror_codes_host, nmirrors, mirror_weight, head_w_host,
+                       head_b_host, ncls, nonlin, gauss, acc, Z, Y, X, z0, y0, x0, norm_scale_shift, norm_slope, 0, stream);
+}
+
+int bsg_head_tta_accumulate_split(const void* feat16, int cfeat, int ctot, int P0, int P1, int P2,
+                                  const int* mirror_codes_host, int nmirrors, float mirror_weight,
+                                  const float* head_w_host, const float* head_b_host, int ncls, int nonlin,
+                                  const float* gauss, float* acc, int Z, int Y, int X, int z0, int y0, int x0, void* stream) {
+    BSG_REQUIRE(ctot >= 3 * cfeat, "split features need ctot >= 3 * cfeat");
+    return head_launch(feat16, 1, cfeat, ctot, P0, P1, P2, mirror_codes_host, nmirrors, mirror_weight, head_w_host,
+                       head_b_host, ncls, nonlin, gauss, acc, Z, Y, X, z0, y0, x0, nullptr, 0.f, 2 * cfeat, stream);
+}
+
+int bsg_norm_apply_lrelu_split(void* x, size_t voxels_per_item, int N, int C, int ctot, int coff, const float* scale_shift,
+                               float slope, void* stream) {
+    BSG_REQUIRE(x != nullptr && scale_shift != nullptr, "null argument");
+    BSG_REQUIRE(C % 8 == 0 && ctot % 8 == 0 && coff % 8 == 0 && coff + 3 * C <= ctot, "bad split channel slice");
+    const int c8n = C / 8;
+    int g = c8n, r = kThreads;  // gcd(c8n, 256)
+    while (r != 0) {
+        const int t = g % r;
+        g = r;
+        r = t;
+    }
+    const int unit = c8n / g;
+    const size_t groups = voxels_per_item * static_cast<size_t>(c8n);
+    size_t blocks = (groups + kThreads - 1) / kThreads;
+    const size_t cap = static_cast<size_t>(sm_count_cached()) * 16 / (N > 0 ? N : 1) + 1;
+    if (blocks > cap) blocks = cap;
+    blocks = (blocks + unit - 1) / unit * unit;
+    dim3 grid(static_cast<unsigned>(blocks), static_cast<unsigned>(N));
+    norm_apply_split_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<__half*>(x), voxels_per_item, C, ctot, coff, scale_shift, slope);
     BSG_CUDA_OK(cudaGetLastError());
     return BSG_OK;
 }

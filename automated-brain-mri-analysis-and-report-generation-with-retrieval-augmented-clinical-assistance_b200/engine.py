@@ -25,10 +25,12 @@ def _ptr(t):
 
 
 class _Act:
-    """A channel slice [coff, coff+c) of a channels-last bf16 buffer (n, d, h, w, ctot)."""
+    """A channel slice [coff, coff+c) of a channels-last 16-bit buffer (n, d, h, w, ctot).  `parts` (engine dtype "fp32"
+    only): the slice holds fp16x3 split tensors — [(offset within the slice, logical channels)], each occupying the
+    three blocks [hi | hi | lo] of that many channels."""
 
-    def __init__(self, buf, coff, c):
-        self.buf, self.coff, self.c = buf, coff, c
+    def __init__(self, buf, coff, c, parts=None):
+        self.buf, self.coff, self.c, self.parts = buf, coff, c, parts
 
     @property
     def ctot(self):
@@ -70,11 +72,17 @@ class UNetEngine:
         # activation dtype: the network's own setting (SegmentationNetwork.engine_dtype — the fp16 range guard flips it
         # to "bf16" after an overflow) wins over the BSG_ACT_DTYPE environment default
         mode = (act_dtype or getattr(net, "engine_dtype", None) or os.environ.get("BSG_ACT_DTYPE", "auto")).lower()
-        if mode not in ("auto", "bf16", "fp16"):
-            raise ValueError(f"activation dtype {mode!r}: expected auto, bf16 or fp16")
+        if mode not in ("auto", "bf16", "fp16", "fp32"):
+            raise ValueError(f"activation dtype {mode!r}: expected auto, bf16, fp16 or fp32")
         # auto = fp16 for every stack.  (The InstanceNorm / GroupNorm stacks need it outright: bf16 activations miss the
         # 1e-2 probability bar there.)
         self.f16 = int(mode != "bf16")
+        # "fp32": the reference's CPU arithmetic (generic_UNet.py:68-72 outside autocast) on the 16-bit tensor pipe — every
+        # activation y is kept as the fp16 pair hi = fp16(y), lo = fp16(y - hi) in three channel blocks [hi | hi | lo],
+        # every weight as [w_hi | w_lo | w_hi] along K, so one fp32 multiply-add becomes three fp16 MMAs with fp32
+        # accumulation (hi*w_hi + hi*w_lo + lo*w_hi; the dropped lo*w_lo term is O(2^-22)).  3x the MMA work and bytes
+        # of the fp16 mode, tile kernel only; norms and the head work on hi + lo in fp32.
+        self.split = mode == "fp32"
         # fp16 range guard: one device flag (shared by all engines of the device), raised by a conv epilogue when a value
         # it stored left the fp16 range (bsg_conv_desc.overflow); the pipeline reads it back once per case
         self.guard = bool(self.f16) and os.environ.get("BSG_OVERFLOW_GUARD", "1") != "0"
@@ -82,9 +90,9 @@ class UNetEngine:
         self._weight_slots = []  # (kind, module, packed tensors): reload_weights() re-packs into them in place
         # InstanceNorm / GroupNorm blocks whose only consumer is a brick-kernel conv hand their normalise + LeakyReLU to
         # that conv (applied in shared memory on the way to the tensor core) instead of a separate HBM pass
-        self.fuse_norm = os.environ.get("BSG_FUSE_NORM", "1") != "0"
+        self.fuse_norm = os.environ.get("BSG_FUSE_NORM", "1") != "0" and not self.split
         self.fused_norms = 0
-        self.try_kwpack = os.environ.get("BSG_KWPACK", "1") != "0"
+        self.try_kwpack = os.environ.get("BSG_KWPACK", "1") != "0" and not self.split
         self.kwpack = False  # the first conv reads the kw-packed input layout (set by _add_block when its plan took it)
         self.flops_algo = 0.0    # algorithmic FLOPs on the real channel counts (the 4 input channels are padded to 16)
         self.act_dtype = torch.float16 if self.f16 else torch.bfloat16
@@ -110,7 +118,7 @@ class UNetEngine:
         self.keep.append(t)
         return t
 
-    def _pack_block(self, blk, cin_pad, kwpack=False):
+    def _pack_block(self, blk, cin_pad, kwpack=False, parts=None):
         """Packed 16-bit weights + fp32 bias of one conv block (eval BatchNorm folded in), norm affine parameters."""
         conv, norm = blk.conv, blk.instnorm
         w = conv.weight.detach().to(self.device, torch.float32)
@@ -129,7 +137,12 @@ class UNetEngine:
             beta = norm.bias.detach().to(self.device).float().contiguous() if norm.bias is not None else None
         else:
             raise NotImplementedError(f"norm {type(norm).__name__}")
-        wp = P.pack_conv3_weight_kwpacked(w, self.act_dtype) if kwpack else P.pack_conv3_weight(w, cin_pad, self.act_dtype)
+        if parts is not None:
+            wp = P.pack_conv3_weight(P.split_k_weight(w, parts, cin_pad, 1), cin_pad, self.act_dtype)
+        elif kwpack:
+            wp = P.pack_conv3_weight_kwpacked(w, self.act_dtype)
+        else:
+            wp = P.pack_conv3_weight(w, cin_pad, self.act_dtype)
         return (wp, P.pad_bias(b, w.shape[0]).to(self.device), gamma, beta)
 
     def _overflow_slot(self):
@@ -156,10 +169,11 @@ class UNetEngine:
         kwpack = False
         if first and self.try_kwpack and 3 * conv.in_channels <= 16 and cin_pad == 16 and stride == 1:
             kwpack = True
-        wp, bp, gamma, beta = self._pack_block(blk, cin_pad, kwpack)
+        wp, bp, gamma, beta = self._pack_block(blk, cin_pad, kwpack, src.parts)
         if act == L.BSG_ACT_NONE:
             stats = self._carve_stats(cout)
-        desc = dict(kind=L.BSG_CONV_K3, stride=stride, N=self.batch, D=d, H=h, W=wd, cin=cin_pad,
+        desc = dict(out_split_stride=cout if self.split else 0,
+                    kind=L.BSG_CONV_K3, stride=stride, N=self.batch, D=d, H=h, W=wd, cin=cin_pad,
                     in_ptr=src.ptr(), in_ctot=src.ctot, cout=cout, out_ptr=dst.buf.data_ptr(),
                     out_ctot=dst.ctot, out_coff=dst.coff, weights=wp.data_ptr(), bias=bp.data_ptr(), act=act,
                     slope=slope, stats=stats.data_ptr() if stats is not None else None,
@@ -175,7 +189,7 @@ class UNetEngine:
                 wp, bp, gamma, beta = self._pack_block(blk, cin_pad, False)
                 desc.update(weights=wp.data_ptr(), bias=bp.data_ptr())
         self.keep += [wp, bp]
-        self._weight_slots.append(("block_kw" if kwpack else "block", blk, cin_pad, (wp, bp, gamma, beta)))
+        self._weight_slots.append(("block_kw" if kwpack else "block", blk, (cin_pad, src.parts), (wp, bp, gamma, beta)))
         if claim is not None and self.fuse_norm and src.coff == 0 and src.c == src.ctot:
             table = torch.zeros(self.batch, cin_pad, 4, dtype=torch.float32, device=self.device)
             try:
@@ -229,7 +243,10 @@ class UNetEngine:
                                                     _ptr(state["table"]), cout, 0, sp))
                 return
             L.check(lib.bsg_norm_finalize(_ptr(stats), self.batch, cout, groups, float(vox), eps, gp, bp2, _ptr(ss), sp))
-            if state["apply"]:
+            if state["apply"] and self.split:
+                L.check(lib.bsg_norm_apply_lrelu_split(_ptr(dst.buf), vox, self.batch, cout, dst.ctot, dst.coff, _ptr(ss),
+                                                       slope, sp))
+            elif state["apply"]:
                 L.check(lib.bsg_norm_apply_lrelu(_ptr(dst.buf), vox, self.batch, cout, dst.ctot, dst.coff, _ptr(ss), slope,
                                                  self.f16, self.f16, sp))
 
@@ -241,21 +258,27 @@ class UNetEngine:
         return state
 
     def _add_tu(self, tu, src, dst, spatial_in):
-        w = tu.weight.detach().to(self.device, torch.float32)
-        wp = P.pack_convT2_weight(w, src.c, self.act_dtype)
+        wp = self._pack_tu(tu, src.c, src.parts)
+        w = tu.weight
         self.keep.append(wp)
-        self._weight_slots.append(("tu", tu, src.c, (wp,)))
+        self._weight_slots.append(("tu", tu, (src.c, src.parts), (wp,)))
         d, h, wd = spatial_in
         plan = L.ConvPlan(kind=L.BSG_CONVT_K2S2, stride=1, N=self.batch, D=d, H=h, W=wd, cin=src.c, in_ptr=src.ptr(),
                           in_ctot=src.ctot, cout=w.shape[1], out_ptr=dst.buf.data_ptr(), out_ctot=dst.ctot,
                           out_coff=dst.coff, weights=wp.data_ptr(), bias=None, act=L.BSG_ACT_NONE, slope=0.0,
                           stats=None, out_f16=self.f16, in_f16=self.f16, use_khshift=0, max_ctas=0,
-                          overflow=self._overflow_slot())
+                          overflow=self._overflow_slot(), out_split_stride=w.shape[1] if self.split else 0)
         self.flops += plan.info().flops
-        self.flops_algo += plan.info().flops
+        self.flops_algo += 2.0 * 8 * w.shape[0] * w.shape[1] * d * h * wd * self.batch
         self._note(f"convT2 {src.c}->{w.shape[1]} @{'x'.join(map(str, spatial_in))}", plan)
         self.steps.append(plan.run)
         self.launches_per_forward += 1
+
+    def _pack_tu(self, tu, cin_pad, parts):
+        w = tu.weight.detach().to(self.device, torch.float32)
+        if parts is not None:
+            w = P.split_k_weight(w, parts, cin_pad, 0)
+        return P.pack_convT2_weight(w, cin_pad, self.act_dtype)
 
     def _note(self, name, plan):
         i = plan.info()
@@ -269,8 +292,9 @@ class UNetEngine:
         num_pool = len(net.tu)
         in_ch = net.conv_blocks_context[0].blocks[0].conv.in_channels
         self.in_channels = in_ch
-        self.cin_pad = P.round_up(in_ch, 16)
-        self.x = _Act(self._alloc(self.patch, self.cin_pad), 0, self.cin_pad)
+        m = 3 if self.split else 1  # physical channels per logical channel
+        self.cin_pad = P.round_up(m * in_ch, 16)
+        self.x = _Act(self._alloc(self.patch, self.cin_pad), 0, self.cin_pad, [(0, in_ch)] if self.split else None)
         cur, spatial = self.x, self.patch
         cats = []
         for d in range(num_pool + 1):
@@ -282,13 +306,14 @@ class UNetEngine:
                 if cout % 16:
                     raise NotImplementedError(f"channel width {cout} is not a multiple of 16")
                 out_spatial = tuple(s // stride for s in spatial)
+                one = [(0, cout)] if self.split else None
                 if d < num_pool and i == len(blocks) - 1:
-                    cat = self._alloc(out_spatial, 2 * cout)  # [0,C): transposed-conv output, [C,2C): this skip
+                    cat = self._alloc(out_spatial, 2 * m * cout)  # [0,C): transposed-conv output, [C,2C): this skip
                     cats.append(cat)
-                    dst = _Act(cat, cout, cout)
+                    dst = _Act(cat, m * cout, m * cout, one)
                     is_skip = True
                 else:
-                    dst = _Act(self._alloc(out_spatial, cout), 0, cout)
+                    dst = _Act(self._alloc(out_spatial, m * cout), 0, m * cout, one)
                     is_skip = False
                 prev = self._add_block(blk, cur, dst, spatial, claim=prev if i > 0 else None, first=(d == 0 and i == 0))
                 if is_skip:
@@ -296,20 +321,21 @@ class UNetEngine:
                 cur, spatial = dst, out_spatial
         for u in range(num_pool):
             cat = cats[-(u + 1)]
-            cskip = cat.shape[-1] // 2
+            cskip = cat.shape[-1] // (2 * m)
             tu = net.tu[u]
             if tu.out_channels != cskip:
                 raise NotImplementedError("transposed conv width differs from the skip width")
-            self._add_tu(tu, cur, _Act(cat, 0, cskip), spatial)
+            self._add_tu(tu, cur, _Act(cat, 0, m * cskip, [(0, cskip)] if self.split else None), spatial)
             spatial = tuple(2 * s for s in spatial)
-            cur = _Act(cat, 0, 2 * cskip)
+            cur = _Act(cat, 0, 2 * m * cskip, [(0, cskip), (3 * cskip, cskip)] if self.split else None)
             loc = net.conv_blocks_localization[u]
             blks = list(loc[0].blocks) + list(loc[1].blocks)
             prev = None
             for j, blk in enumerate(blks):
-                dst = _Act(self._alloc(spatial, blk.conv.out_channels), 0, blk.conv.out_channels)
+                co = blk.conv.out_channels
+                dst = _Act(self._alloc(spatial, m * co), 0, m * co, [(0, co)] if self.split else None)
                 # the very last block's norm + LeakyReLU is applied by its only consumer, the head
-                last = (u == num_pool - 1) and (j == len(blks) - 1) and blk.conv.out_channels <= 64
+                last = (u == num_pool - 1) and (j == len(blks) - 1) and co <= 64 and not self.split
                 prev = self._add_block(blk, cur, dst, spatial, defer_apply=last, claim=prev if j > 0 else None)
                 cur = dst
         self.features = cur
@@ -329,14 +355,13 @@ class UNetEngine:
         """Re-packs the module tree's current parameters into the engine's EXISTING device tensors (plans and tensor
         maps point at fixed buffers, so they stay valid): what load_state_dict / load_checkpoint_ram need per fold,
         instead of rebuilding activation buffers, plans and tensor maps."""
-        for kind, mod, cin_pad, tensors in self._weight_slots:
+        for kind, mod, (cin_pad, parts), tensors in self._weight_slots:
             if kind in ("block", "block_kw"):
-                for dst, src in zip(tensors, self._pack_block(mod, cin_pad, kind == "block_kw")):
+                for dst, src in zip(tensors, self._pack_block(mod, cin_pad, kind == "block_kw", parts)):
                     if dst is not None:
                         dst.copy_(src)
             else:
-                tensors[0].copy_(P.pack_convT2_weight(mod.weight.detach().to(self.device, torch.float32), cin_pad,
-                                                      self.act_dtype))
+                tensors[0].copy_(self._pack_tu(mod, cin_pad, parts))
         self._load_head()
 
     def close(self):
@@ -386,12 +411,22 @@ class UNetEngine:
         if n > self.batch or tuple(x.shape[2:]) != self.patch:
             raise ValueError("input does not match the engine geometry")
         self.x.buf.zero_()
-        if self.kwpack:
+        if self.split:
+            xl = x.to(self.device, torch.float32).permute(0, 2, 3, 4, 1)
+            hi = xl.to(torch.float16)
+            c = self.in_channels
+            self.x.buf[:n, ..., 0:c] = hi
+            self.x.buf[:n, ..., c:2 * c] = hi
+            self.x.buf[:n, ..., 2 * c:3 * c] = (xl - hi.float()).to(torch.float16)
+        elif self.kwpack:
             self.x.buf[:n] = P.kwpack_input(x.to(self.device, torch.float32), self.cin_pad).to(self.act_dtype)
         else:
             self.x.buf[:n, ..., :self.in_channels] = x.to(self.device).permute(0, 2, 3, 4, 1).to(self.act_dtype)
         self.run()
         f = self.features.view()[:n].float()  # (n, d, h, w, c)
+        if self.split:
+            c = self.head_w.shape[1]
+            f = f[..., 0:c] + f[..., 2 * c:3 * c]
         if self.final_norm is not None:
             ss, slope = self.final_norm
             f = torch.nn.functional.leaky_relu(f * ss[:n, :, 0].view(n, 1, 1, 1, -1) + ss[:n, :, 1].view(n, 1, 1, 1, -1), slope)

@@ -19,27 +19,31 @@ class SegmentationNetwork(nn.Module):
         self._engines = {}
         self.engine_batch = 8  # (tile, mirror) forwards in flight, split evenly over `engine_lanes` CUDA streams
         self.engine_lanes = 2  # >1: HBM-bound passes of one lane overlap the tensor-bound convs of the other
-        self.engine_dtype = None  # None: BSG_ACT_DTYPE / auto (fp16); "bf16" after the fp16 range guard fired
+        # None: BSG_ACT_DTYPE / auto (fp16); "bf16" after the fp16 range guard fired; "fp32": fp32-equivalent arithmetic
+        # (fp16x3 split operands, engine.py) — what predict_3D(mixed_precision=False) selects, like upstream's no-autocast path
+        self.engine_dtype = None
 
     # ------------------------------------------------------------------ engine cache
-    def engine_for(self, patch_size, batch=None, slot=0):
-        """Cached UNetEngine for a patch size / batch; `slot` distinguishes the engines of concurrent stream lanes."""
+    def engine_for(self, patch_size, batch=None, slot=0, dtype=None):
+        """Cached UNetEngine for a patch size / batch; `slot` distinguishes the engines of concurrent stream lanes;
+        `dtype` overrides the network's engine_dtype for this engine."""
         from . import _lib as L
         from .engine import UNetEngine
         if not torch.cuda.is_available():
             raise L.BsgError("brainseg_b200 needs a CUDA device (sm_100); there is no CPU fallback")
         batch = int(batch or self.engine_batch)
-        key = (tuple(int(p) for p in patch_size), batch, torch.cuda.current_device(), int(slot), self.engine_dtype)
+        dtype = dtype or self.engine_dtype
+        key = (tuple(int(p) for p in patch_size), batch, torch.cuda.current_device(), int(slot), dtype)
         if key not in self._engines:
-            self._engines[key] = UNetEngine(self, key[0], batch)
+            self._engines[key] = UNetEngine(self, key[0], batch, act_dtype=dtype)
         return self._engines[key]
 
-    def engines_for(self, patch_size, batch=None, lanes=None):
+    def engines_for(self, patch_size, batch=None, lanes=None, dtype=None):
         """The lane engines of the sliding-window driver: `lanes` engines of batch/lanes forwards each."""
         batch = int(batch or self.engine_batch)
         lanes = max(1, min(int(lanes or self.engine_lanes), batch))
         per = -(-batch // lanes)
-        return [self.engine_for(patch_size, per, slot) for slot in range(lanes)]
+        return [self.engine_for(patch_size, per, slot, dtype) for slot in range(lanes)]
 
     def invalidate_engines(self):
         """Drops every cached engine (device buffers, plans, tensor maps) — after a change of ARCHITECTURE or of the
@@ -94,10 +98,12 @@ class SegmentationNetwork(nn.Module):
             raise ValueError("mirror axes. duh")
         x = np.asarray(x) if not torch.is_tensor(x) else x
         assert len(x.shape) == 4, "data must have shape (c,x,y,z)"
+        # upstream: mixed_precision=True runs the forwards under CUDA autocast (fp16), False in fp32
+        dtype = None if mixed_precision else "fp32"
         if use_sliding_window:
             assert patch_size is not None, "patch_size cannot be None for tiled prediction"
             seg, probs = self.predict_3D_device(x, do_mirroring, mirror_axes, step_size, patch_size,
-                                                regions_class_order, use_gaussian)
+                                                regions_class_order, use_gaussian, dtype=dtype)
         else:
             # upstream _internal_predict_3D_3Dconv: pad to >= patch_size (its `min_size`) and to a multiple of
             # input_shape_must_be_divisible_by, ONE mirrored forward over the whole volume (no Gaussian), crop back —
@@ -107,13 +113,13 @@ class SegmentationNetwork(nn.Module):
             whole = [max(s, f) for s, f in zip(x.shape[1:], floor)]
             whole = [w if w % d == 0 else w + d - w % d for w, d in zip(whole, div)]
             seg, probs = self.predict_3D_device(x, do_mirroring, mirror_axes, 1.0, whole, regions_class_order, False,
-                                                engine_batch=1)
+                                                engine_batch=1, dtype=dtype)
         seg = seg.cpu().numpy()
         seg = seg.astype(np.float32) if regions_class_order is not None else seg.astype(np.int64)
         return seg, probs.cpu().numpy()
 
     def predict_3D_device(self, x, do_mirroring=True, mirror_axes=(0, 1, 2), step_size=0.5, patch_size=None,
-                          regions_class_order=None, use_gaussian=True, want_probs=True, engine_batch=None):
+                          regions_class_order=None, use_gaussian=True, want_probs=True, engine_batch=None, dtype=None):
         """predict_3D without the final device->host copies: returns (uint8 seg, fp32 probs) cuda tensors."""
         dev = torch.device("cuda", torch.cuda.current_device())
         vol = (torch.from_numpy(np.ascontiguousarray(x)) if not torch.is_tensor(x) else x).to(dev, torch.float32)
@@ -129,7 +135,7 @@ class SegmentationNetwork(nn.Module):
             vol = torch.nn.functional.pad(vol, (pads[2][0], pads[2][1], pads[1][0], pads[1][1], pads[0][0], pads[0][1]))
         vol = vol.contiguous()
         codes = sliding.mirror_codes_for(mirror_axes, do_mirroring)
-        pred = sliding.SlidingWindowPredictor(self.engines_for(patch, engine_batch), step_size, use_gaussian, codes,
+        pred = sliding.SlidingWindowPredictor(self.engines_for(patch, engine_batch, dtype=dtype), step_size, use_gaussian, codes,
                                               self._nonlin_name())
         acc = pred.accumulate(vol)
         seg, probs = pred.finalize([acc], tuple(vol.shape[1:]), regions_class_order, want_probs)

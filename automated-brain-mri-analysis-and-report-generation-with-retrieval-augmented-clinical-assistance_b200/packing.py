@@ -59,6 +59,32 @@ def pack_convT2_weight(w, cin_pad=None, dtype=torch.bfloat16):
     return p.reshape(1, 8 * cout_pad, cin_pad).to(dtype).contiguous()
 
 
+def split_f16x3(x):
+    """fp32 tensor -> (hi, lo) fp16 pair with hi = fp16(x), lo = fp16(x - hi): x = hi + lo to ~22 significant bits."""
+    hi = x.float().to(torch.float16)
+    return hi, (x.float() - hi.float()).to(torch.float16)
+
+
+def split_k_weight(w, parts, cin_pad, dim):
+    """fp16x3 split of a weight along its input-channel dimension `dim` (engine dtype "fp32"): the source tensor holds
+    each part (offset, c) as the three channel blocks [hi | hi | lo], so the weight's K layout is [w_hi | w_lo | w_hi]
+    per part (zero elsewhere) and hi*w_hi + hi*w_lo + lo*w_hi = x*w - lo*w_lo.  Values are fp16-exact fp32."""
+    hi, lo = split_f16x3(w)
+    hi, lo = hi.float(), lo.float()
+    shape = list(w.shape)
+    shape[dim] = cin_pad
+    out = torch.zeros(shape, dtype=torch.float32, device=w.device)
+    start = 0
+    for off, c in parts:
+        h, l = hi.narrow(dim, start, c), lo.narrow(dim, start, c)
+        out.narrow(dim, off, c).copy_(h)
+        out.narrow(dim, off + c, c).copy_(l)
+        out.narrow(dim, off + 2 * c, c).copy_(h)
+        start += c
+    assert start == w.shape[dim], "parts do not cover the weight's input channels"
+    return out
+
+
 def pad_bias(b, cout):
     cout_pad = round_up(cout, 32)
     out = torch.zeros(cout_pad, dtype=torch.float32, device=b.device if b is not None else None)

@@ -196,7 +196,8 @@ class SlidingWindowPredictor:
                         codes = (C.c_int * (b - a))(*[m for _, m in chunk[a:b]])
                         out = eng.x.buf.data_ptr() + 2 * a * pv * eng.x.ctot
                         L.check(lib.bsg_gather_patch_tta(_ptr(vol), Cn, Z, Y, X, z, y, x, p0, p1, p2, codes, b - a,
-                                                         C.c_void_p(out), eng.x.ctot, eng.f16, int(eng.kwpack), sp))
+                                                         C.c_void_p(out), eng.x.ctot, eng.f16,
+                                                         2 if eng.split else int(eng.kwpack), sp))
                     eng.run(None)
                     if multi and head_done is not None:
                         s.wait_event(head_done)
@@ -204,6 +205,11 @@ class SlidingWindowPredictor:
                         z, y, x = tiles[chunk[a][0]]
                         codes = (C.c_int * (b - a))(*[m for _, m in chunk[a:b]])
                         fptr = feat.buf.data_ptr() + 2 * (a * pv * feat.ctot + feat.coff)
+                        if eng.split:  # fp16x3 split features: the head reads hi + lo
+                            L.check(lib.bsg_head_tta_accumulate_split(C.c_void_p(fptr), cfeat, feat.ctot, p0, p1, p2, codes,
+                                                                      b - a, weight, hw, hb, eng.num_classes, self.nonlin,
+                                                                      gptr, _ptr(acc), Z, Y, X, z, y, x, sp))
+                            continue
                         L.check(lib.bsg_head_tta_accumulate(C.c_void_p(fptr), eng.f16, cfeat, feat.ctot, p0, p1, p2, codes, b - a,
                                                             weight, hw, hb, eng.num_classes, self.nonlin, gptr,
                                                             _ptr(acc), Z, Y, X, z, y, x, nss(eng, a), nslope(eng), sp))

@@ -87,8 +87,12 @@ typedef struct bsg_conv_desc {
                             rows written by bsg_norm_finalize_table).  Brick kernel only: bsg_conv_plan_create returns
                             BSG_EINVAL when the layer does not qualify and the caller keeps the separate pass. */
     int in_norm_c;       /* channels per batch item of the in_norm table (>= cin) */
-    int in_norm_cc;      /* 0: planner's choice of K chunk for an in_norm plan (32 channels where that keeps the weight slabs
-                            resident); 64: force 64-channel chunks (measurement switch) */
+    int in_norm_cc;      /* 0: planner's choice of K chunk for an in_norm plan; 32: force 32-channel chunks where the weight
+                            slabs stay resident (measurement switch: slower) */
+    int out_split_stride; /* 0, or S: fp32-equivalent mode — the fp32 result y is stored as the fp16 pair hi = fp16(y),
+                            lo = fp16(y - hi) in THREE channel blocks [hi | hi | lo] at out_coff, out_coff + S,
+                            out_coff + 2S; the next conv contracts them against weights stacked [w_hi | w_lo | w_hi] on its
+                            input channels (y*w = hi*w_hi + hi*w_lo + lo*w_hi + O(2^-22)).  fp16 operands, tile kernel. */
     int kw_taps;         /* 0 / 3: 3x3x3 kernel.  1: 3x3x1 kernel (kd, kh taps only), weights [9 taps (kd, kh)][cout_pad][cin]:
                             the network's first conv on an input whose w neighbours were packed into the channels by
                             bsg_gather_patch_tta(kwpack = 1) — 9 taps of K = 16 instead of 27.  Brick kernel only. */
@@ -253,7 +257,8 @@ int bsg_masked_threshold_count(const float* x1, const float* x2, const float* x3
  * vol[c][z0+fz(d)][y0+fy(h)][x0+fx(w)]: the tile crop data[None, :, lb_x:ub_x, ...] plus torch.flip(x, axes) for every
  * mirror m, written as one channels-last batch. */
 /* kwpack = 1 (needs 3 * C <= 16, cpad == 16): channel k*C + c of an output voxel = channel c of its w-neighbour k-1 in
- * the copy's orientation, zero outside the tile — the input layout of a first conv planned with kw_taps = 1. */
+ * the copy's orientation, zero outside the tile — the input layout of a first conv planned with kw_taps = 1.
+ * kwpack = 2 (needs 3 * C <= cpad, fp16): the fp16x3 split of the fp32 input, channels [hi (C) | hi (C) | lo (C) | 0]. */
 int bsg_gather_patch_tta(const float* vol, int C, int Z, int Y, int X, int z0, int y0, int x0, int P0, int P1, int P2,
                          const int* mirror_codes_host, int nmirrors, void* out16, int cpad, int out_f16, int kwpack,
                          void* stream);
@@ -274,6 +279,11 @@ int bsg_norm_finalize_table(const double* stats, int N, int C, int groups, doubl
 int bsg_norm_apply_lrelu(void* x, size_t voxels_per_item, int N, int C, int ctot, int coff,
                          const float* scale_shift, float slope, int in_f16, int out_f16, void* stream);
 
+/* bsg_norm_apply_lrelu for the fp16x3 split layout (bsg_conv_desc.out_split_stride): reads hi (block 0) + lo (block 2) of
+ * the C-channel tensor at [coff, coff + 3C), normalises in fp32 and writes the three blocks [hi | hi | lo] back. */
+int bsg_norm_apply_lrelu_split(void* x, size_t voxels_per_item, int N, int C, int ctot, int coff, const float* scale_shift,
+                               float slope, void* stream);
+
 /* Fused tail of one tile: 1x1x1 segmentation head (generic_UNet.py:389-391, weights [ncls][cfeat] + optional bias,
  * HOST pointers), inference_apply_nonlin (0 sigmoid / 1 softmax / 2 identity), un-flip of each mirror's prediction,
  * result += mirror_weight * pred (mirror_weight = 1/num_results of the whole TTA), result *= gaussian,
@@ -288,6 +298,11 @@ int bsg_head_tta_accumulate(const void* feat16, int feat_f16, int cfeat, int cto
                             const float* head_w_host, const float* head_b_host, int ncls, int nonlin,
                             const float* gauss, float* acc, int Z, int Y, int X, int z0, int y0, int x0,
                             const float* norm_scale_shift, float norm_slope, void* stream);
+/* ... with the features in the fp16x3 split layout: head input = channels [0, cfeat) + channels [2*cfeat, 3*cfeat). */
+int bsg_head_tta_accumulate_split(const void* feat16, int cfeat, int ctot, int P0, int P1, int P2,
+                                  const int* mirror_codes_host, int nmirrors, float mirror_weight,
+                                  const float* head_w_host, const float* head_b_host, int ncls, int nonlin,
+                                  const float* gauss, float* acc, int Z, int Y, int X, int z0, int y0, int x0, void* stream);
 
 /* class_probabilities = aggregated_results / aggregated_nb_of_predictions; mean over K accumulators (np.mean over
  * folds, run_brats2021_inference_singlethread.py:128); decision: mode 0 argmax(0) (main_files/run_inference.py:150),

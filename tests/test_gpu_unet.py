@@ -227,3 +227,58 @@ def test_config1_full_case_brats_architecture():
     vol = torch.randn(4, 155, 240, 240, generator=torch.Generator().manual_seed(0)).numpy()
     perr, agree = _check_predict(net, vol, (128, 128, 128), (0, 1, 2), False, 0.5, (1, 2, 3), torch.sigmoid)
     assert agree >= 0.999, f"label agreement {agree * 100:.4f}% < 99.9%"
+
+
+# ---------------------------------------------------------------------------------------------- fp32-equivalent mode
+FP32_TOL = 1e-4  # BASELINE.json north_star: probabilities within 1e-4 of the reference's fp32 (CPU) arithmetic
+
+
+@pytest.mark.parametrize("variant", ["bn", "in", "gn"])
+def test_fp32_mode_forward_logits(variant):
+    """engine dtype "fp32" (fp16x3 split operands, three MMAs per fp32 product): logits of a single forward against the
+    fp32 oracle — every layer kind (first conv on the split input, stride 2, concat of two split tensors, transposed)."""
+    net = build_dropin_unet(variant, base=16, num_pool=3, groups=4, seed=3)
+    net.engine_dtype = "fp32"
+    fwd, _, _ = oracle_fns(net)
+    x = torch.randn(2, 4, 32, 32, 32, generator=torch.Generator().manual_seed(7))
+    ref = fwd(x)
+    got = net(x).cpu()
+    scale = max(ref.abs().max().item(), 1.0)
+    err = (got - ref).abs().max().item()
+    perr = (torch.sigmoid(got) - torch.sigmoid(ref)).abs().max().item()
+    print(f"fp32 mode {variant}: logits max err {err:.3g} (scale {scale:.3g}), sigmoid max err {perr:.3g}")
+    assert err < 1e-4 * scale
+    assert perr < FP32_TOL
+
+
+def test_fp32_mode_predict_3d_mixed_precision_false():
+    """predict_3D(mixed_precision=False) — upstream's no-autocast path — through the sliding window with all mirrors:
+    probabilities within 1e-4 of the fp32 oracle, labels equal wherever the oracle is not within 1e-4 of the threshold."""
+    net = build_dropin_unet("gn", base=16, num_pool=3, groups=4, seed=21)
+    fwd, _, _ = oracle_fns(net)
+    vol = torch.randn(4, 40, 56, 48, generator=torch.Generator().manual_seed(2)).numpy()
+    seg_ref, probs_ref = SW.predict_3d_tiled(fwd, torch.sigmoid, vol, net.num_classes, (32, 32, 32), True, (0, 1, 2), 0.5,
+                                             True, (1, 2, 3))
+    seg, probs = net.predict_3D(vol, True, (0, 1, 2), True, 0.5, (32, 32, 32), (1, 2, 3), True, "constant",
+                                {"constant_values": 0}, False, False, mixed_precision=False)
+    perr = np.abs(probs - probs_ref).max()
+    decisive = np.all(np.abs(probs_ref - 0.5) > FP32_TOL, axis=0)
+    agree = (seg == seg_ref).mean()
+    print(f"fp32 mode predict_3D: prob max err {perr:.3g}, label agreement {agree * 100:.4f}% "
+          f"({decisive.mean() * 100:.2f}% decisive)")
+    assert perr < FP32_TOL
+    assert np.array_equal(seg[decisive], seg_ref[decisive])
+    assert agree > 0.9999
+
+
+def test_fp32_mode_brats_architecture_full_patch():
+    """One 128^3 forward of model 1's architecture (5 pools, 320 features) in fp32-equivalent mode."""
+    net = build_dropin_unet("bn", base=32, num_pool=5, seed=1)
+    net.engine_dtype = "fp32"
+    fwd, _, _ = oracle_fns(net)
+    x = torch.randn(1, 4, 128, 128, 128, generator=torch.Generator().manual_seed(11))
+    ref = fwd(x)
+    got = net(x).cpu()
+    perr = (torch.sigmoid(got) - torch.sigmoid(ref)).abs().max().item()
+    print(f"fp32 mode bn_brats: sigmoid max err {perr:.3g}")
+    assert perr < FP32_TOL

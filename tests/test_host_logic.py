@@ -141,6 +141,34 @@ def test_weight_packing_layouts():
     assert torch.allclose(P.from_ndhwc(P.to_ndhwc_bf16(x), 4), x.to(torch.bfloat16).float())
 
 
+def test_fp16x3_split_arithmetic():
+    """Engine dtype "fp32": an activation tensor stored as [hi | hi | lo] contracted against weights stacked
+    [w_hi | w_lo | w_hi] reproduces the fp32 product to ~2^-20 relative, with every operand fp16-exact (what the 16-bit
+    tensor pipe multiplies exactly and accumulates in fp32)."""
+    from brainseg_b200 import packing as P
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(64, 24, generator=g, dtype=torch.float64) * 3.0   # (voxels, logical channels), two source parts
+    w = torch.randn(8, 24, generator=g, dtype=torch.float64) * 0.05  # (cout, logical channels)
+    parts = [(0, 16), (48, 8)]                                        # part 0: 16 ch at 0, part 1: 8 ch at 48
+    phys = torch.zeros(64, 80)
+    start = 0
+    for off, c in parts:
+        hi, lo = P.split_f16x3(x[:, start:start + c].float())
+        phys[:, off:off + c] = hi.float()
+        phys[:, off + c:off + 2 * c] = hi.float()
+        phys[:, off + 2 * c:off + 3 * c] = lo.float()
+        start += c
+    wk = P.split_k_weight(w.float(), parts, 80, 1)
+    assert torch.equal(wk, wk.to(torch.float16).float()) and torch.equal(phys, phys.to(torch.float16).float())
+    assert wk[:, 72:].abs().sum() == 0
+    got = phys.double() @ wk.double().t()
+    ref = x.float().double() @ w.float().double().t()
+    plain = x.float().to(torch.float16).double() @ w.float().to(torch.float16).double().t()
+    scale = (x.abs() @ w.abs().t()).max().item()
+    assert (got - ref).abs().max().item() < 4e-6 * scale
+    assert (plain - ref).abs().max().item() > 50 * (got - ref).abs().max().item()  # vs plain fp16 operands
+
+
 def test_remap_luts_and_dice_formulas_on_host():
     from brainseg_b200 import convert_labels_to_brats as CL
     from brainseg_b200 import evaluate_segmentation as EV
