@@ -48,6 +48,23 @@ def shard_work_items(num_tiles, mirror_codes, rank=0, world_size=1):
     return items[rank::world_size]
 
 
+def balanced_batch(items_per_rank, lanes=2, lo=4, hi=12):
+    """Forwards in flight (lanes x per-lane batch) for a rank that owns `items_per_rank` work items per model: an engine
+    always runs its whole batch, so a last chunk that is only partly filled is wasted work (18 items on two lanes of
+    8: 16 + a chunk of 2 run as 8 = 25 % more forwards than needed).  Picks the per-lane batch in [lo, hi] that wastes the
+    fewest forwards over the ceil(items / (lanes * b)) rounds, the larger batch on ties (the <= 8^3 levels amortise)."""
+    best = None
+    for b in range(lo, hi + 1):
+        rounds = -(-items_per_rank // (lanes * b))
+        # the last round fills lane after lane: only its last non-empty lane can be partly filled
+        rem = items_per_rank - (rounds - 1) * lanes * b
+        waste = -(-rem // b) * b - rem
+        key = (waste, rounds, -b)
+        if best is None or key < best[0]:
+            best = (key, b)
+    return lanes * best[1]
+
+
 _gauss_cache = {}
 
 

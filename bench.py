@@ -534,21 +534,24 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run_steps(p, k, vols, gts, owner_of=None, want_host_labels=False):
-        """k cases as a stream: the inference of case i+1 is submitted before the post-processing of case i is
-        collected, so host-side glue overlaps device work.  Every case is submitted AND finished inside the call.
-        owner_of(i): sharded mode — the rank that runs case i's post-processing."""
+    def run_steps(p, k, vols, gts, owner_of=None, want_host_labels=False, depth=1):
+        """k cases as a stream: the inference of the next `depth` cases is submitted before the post-processing of case
+        i is collected, so host-side glue overlaps device work.  Every case is submitted AND finished inside the call.
+        owner_of(i): sharded mode — the rank that runs case i's post-processing (depth 2 there: the owner's host thread
+        is busy with the post-processing for about as long as a sharded case takes, and every other rank would wait
+        for its share of the next case at the exchange)."""
         out = seg_host = None
-        pend = p.submit(vols[0], gts[0])
+        pend = [p.submit(vols[j % len(vols)], gts[j % len(gts)]) for j in range(min(depth, k))]
         for i in range(k):
-            nxt = p.submit(vols[(i + 1) % len(vols)], gts[(i + 1) % len(gts)]) if i + 1 < k else None
+            if i + depth < k:
+                j = i + depth
+                pend.append(p.submit(vols[j % len(vols)], gts[j % len(gts)]))
             mine = owner_of is None or owner_of(i) == rank
-            res = p.finish(pend, post=mine, labels=blobby[i % len(blobby)] if (blobby is not None and mine) else None)
+            res = p.finish(pend.pop(0), post=mine, labels=blobby[i % len(blobby)] if (blobby is not None and mine) else None)
             if mine:
                 out = res
                 if want_host_labels:
                     seg_host = res["segmentation"].cpu()  # D2H of the final label volume
-            pend = nxt
         return out, seg_host
 
     line_extra = {}
@@ -611,15 +614,19 @@ def run_ours(args):
         routes = [args.route] if args.route != "both" else ["peer", "nccl"]
         for route in routes:
             sh = SH.ShardedExchange(rank, world, dev, route=route)
+            # forwards in flight sized to the rank's share (an engine always runs its whole batch: 18 items per model on
+            # 8 GPUs = two lanes of 9, not 16 + a chunk of 2 that costs 8)
+            from brainseg_b200 import sliding as SL
+            lat_batch = SL.balanced_batch(-(-N_TILES * N_MIRRORS // world), lanes=2)
             lp = PL.BratsCasePipeline([m1, m2], PATCH, args.step_size, (0, 1, 2), True, True, (1, 2, 3), "brats2025",
-                                      batch=args.batch, rank=rank, world_size=world, shard=sh)
+                                      batch=lat_batch, rank=rank, world_size=world, shard=sh)
             owner = (lambda i: i % world)
-            run_steps(lp, max(2, min(args.warmup, 3)), [case0], [gt0], owner_of=owner)
+            run_steps(lp, max(2, min(args.warmup, 3)), [case0], [gt0], owner_of=owner, depth=2)
             barrier()
             ll0 = lp.kernel_launches()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            lout, _ = run_steps(lp, args.steps, [case0], [gt0], owner_of=owner, want_host_labels=True)
+            lout, _ = run_steps(lp, args.steps, [case0], [gt0], owner_of=owner, want_host_labels=True, depth=2)
             e1.record()
             barrier()
             t_lat = e0.elapsed_time(e1) / 1e3
@@ -646,7 +653,7 @@ def run_ours(args):
                 same = float((res["segmentation"] == ref_labels).float().mean().item())
             records[route] = {"ms_per_case": t_lat / args.steps * 1e3, "cases_per_s": args.steps / t_lat,
                               "single_case_ms": t_single_lat * 1e3, "single_case_ms_without_post": t_single_seg * 1e3,
-                              "gpu_launches": int(lat_launches),
+                              "gpu_launches": int(lat_launches), "forwards_in_flight": lat_batch,
                               "exchange_bytes_per_case": int((sh.peer_bytes + sh.nccl_bytes) / max(1, sh.launches) * 2),
                               "labels_equal_to_1gpu": same, "label_sha256_16": sha16(res["segmentation"])}
             log(f"latency mode [{route}]: {t_lat / args.steps * 1e3:.1f} ms per case pipelined, single case "
@@ -661,7 +668,7 @@ def run_ours(args):
         latency = dict(records[main_route])
         latency.update({"config": "configs[2]: the 288 (model, tile, mirror) forwards of ONE case dealt round-robin to the "
                                   f"{world} ranks; exchange = {main_route} route (see brainseg_b200/sharded.py); steps "
-                                  "pipelined as a case stream, post-processing of case i on rank i % N; host buffers "
+                                  "pipelined as a case stream (two cases submitted ahead), post-processing of case i on rank i % N; host buffers "
                                   "(H2D of the volume on every rank and D2H of the labels inside the timed region)",
                         "scaling": "strong", "route": main_route, "steps": args.steps,
                         "label_sha256_16_1gpu": sha16(ref_labels) if ref_labels is not None else None})

@@ -46,12 +46,14 @@ def test_forward_batch_one_and_engine_reuse():
 
 
 def _check_predict(net, vol, patch, mirror_axes, do_mirroring, step, regions, nonlin_fn, use_gaussian=True,
-                   tol=PROB_TOL):
-    fwd, _, _ = oracle_fns(net)
-    seg_ref, probs_ref = SW.predict_3d_tiled(fwd, nonlin_fn, vol, net.num_classes, patch, do_mirroring, mirror_axes,
-                                             step, use_gaussian, regions)
+                   tol=PROB_TOL, mixed_precision=True, ref=None):
+    if ref is None:
+        fwd, _, _ = oracle_fns(net)
+        ref = SW.predict_3d_tiled(fwd, nonlin_fn, vol, net.num_classes, patch, do_mirroring, mirror_axes, step,
+                                  use_gaussian, regions)
+    seg_ref, probs_ref = ref
     seg, probs = net.predict_3D(vol, do_mirroring, mirror_axes, True, step, patch, regions, use_gaussian, "constant",
-                                {"constant_values": 0}, False, False, True)
+                                {"constant_values": 0}, False, False, mixed_precision)
     assert probs.dtype == np.float32 and probs.shape == probs_ref.shape and seg.shape == seg_ref.shape
     assert seg.dtype == seg_ref.dtype
     perr = np.abs(probs - probs_ref).max()
@@ -65,7 +67,7 @@ def _check_predict(net, vol, patch, mirror_axes, do_mirroring, step, regions, no
           f"({decisive.mean() * 100:.1f}% decisive voxels)")
     assert perr < tol
     assert np.array_equal(seg[decisive], seg_ref[decisive])
-    return perr, agree
+    return perr, agree, ref
 
 
 def test_predict_3d_regions_sigmoid_all_mirrors():
@@ -222,11 +224,15 @@ def test_config1_full_case_brats_architecture():
     """BASELINE configs[0] in full: the synthetic 4x155x240x240 case, ONE model of the BraTS-2021 shape (31.2 M
     parameters), no mirroring, patch 128^3, step 0.5 (18 tiles), Gaussian weighting, regions export — against the fp32
     oracle running the same 18 forwards on the host (about a minute of CPU time on the GPU box).  north_star's bars:
-    probabilities within 1e-2 absolute, label volume agreement >= 99.9 %."""
+    probabilities within 1e-2 absolute, label volume agreement >= 99.9 %.  Then the same case with
+    mixed_precision=False (fp32-equivalent engine) against the same oracle result at north_star's fp32 bar: 1e-4."""
     net = build_dropin_unet("bn", base=32, num_pool=5, seed=1)
     vol = torch.randn(4, 155, 240, 240, generator=torch.Generator().manual_seed(0)).numpy()
-    perr, agree = _check_predict(net, vol, (128, 128, 128), (0, 1, 2), False, 0.5, (1, 2, 3), torch.sigmoid)
+    perr, agree, ref = _check_predict(net, vol, (128, 128, 128), (0, 1, 2), False, 0.5, (1, 2, 3), torch.sigmoid)
     assert agree >= 0.999, f"label agreement {agree * 100:.4f}% < 99.9%"
+    perr32, agree32, _ = _check_predict(net, vol, (128, 128, 128), (0, 1, 2), False, 0.5, (1, 2, 3), torch.sigmoid,
+                                        tol=1e-4, mixed_precision=False, ref=ref)
+    assert agree32 >= 0.99999, f"fp32 mode label agreement {agree32 * 100:.5f}%"
 
 
 # ---------------------------------------------------------------------------------------------- fp32-equivalent mode

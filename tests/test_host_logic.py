@@ -123,6 +123,21 @@ def test_work_item_sharding_partitions_the_case():
         assert max(map(len, shards)) - min(map(len, shards)) <= 1
 
 
+def test_balanced_batch_wastes_no_forwards():
+    """Sharded mode: the forwards in flight are sized to the rank's share of the 144 (tile, mirror) items per model."""
+    from brainseg_b200 import sliding as S
+    for world in (1, 2, 3, 4, 6, 8):
+        n = -(-144 // world)
+        total = S.balanced_batch(n, lanes=2)
+        b = total // 2
+        assert 4 <= b <= 12 and total == 2 * b
+        rounds = -(-n // total)
+        rem = n - (rounds - 1) * total
+        assert -(-rem // b) * b - rem == 0, (world, n, b)  # every BraTS share divides evenly
+    assert S.balanced_batch(18, lanes=2) == 18        # 8 GPUs: two lanes of 9, one round
+    assert S.balanced_batch(7, lanes=1, lo=4, hi=8) == 7
+
+
 def test_weight_packing_layouts():
     from brainseg_b200 import packing as P
     w = torch.arange(2 * 3 * 27, dtype=torch.float32).reshape(2, 3, 3, 3, 3)
