@@ -106,6 +106,7 @@ _EXTRA_SIGS = {
                                 _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _f, _vp],
     "bsg_finalize": [C.POINTER(_vp), _i, _vp, _i, _sz, _i, C.POINTER(_i), _vp, _vp, _vp],
     "bsg_finalize_peer": [_vp, _i, _i, _vp, _i, _sz, _sz, _sz, _i, C.POINTER(_i), _vp, _i, _vp],
+    "bsg_finalize_peer_signal": [_vp, _i, _i, _vp, _i, _sz, _sz, _sz, _i, C.POINTER(_i), _vp, _i, _vp, _i, _u32, _vp],
     "bsg_enable_peer_access": [_i],
     "bsg_ipc_export": [_vp, _vp, C.POINTER(_sz)],
     "bsg_ipc_open": [_vp, C.POINTER(_vp)],

@@ -28,7 +28,25 @@ struct PeerFinalizeParams {
     uint8_t* const* seg_table;      // device [nseg]: label volumes to write (every rank's, or just the local one)
     int K, R, nseg, ncls, mode;
     int order[kMaxClasses];
+    // in-kernel rank ordering (bsg_finalize_peer_signal); null flag_table: the caller orders the ranks around the launch
+    uint32_t* const* flag_table;    // device [R]: every rank's flag block {arrive[R], done[R], blocks_done} as mapped here
+    int rank;
+    uint32_t epoch;
 };
+
+// Flag block of one rank (uint32): [0, R) arrive[src] = last epoch for which rank `src` announced "my accumulators are
+// complete", [R, 2R) done[src] = last epoch for which rank `src` finished reading this rank's accumulators and writing
+// its slab into this rank's label volumes, [2R] = local count of finished blocks.
+__device__ __forceinline__ uint32_t ld_flag(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_flag(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// epochs are compared modulo 2^32 (a flag can only lag or equal the epoch being waited for, never lead it by 2^31)
+__device__ __forceinline__ bool reached(uint32_t flag, uint32_t epoch) { return static_cast<int32_t>(flag - epoch) >= 0; }
 
 __device__ __forceinline__ bool exceeds_half(float a, float w) {  // fl32(a / w) > 0.5, exactly (see tail.cu)
     return static_cast<double>(a) > static_cast<double>(w) * (0.5 + 0x1p-25);
@@ -40,6 +58,17 @@ __global__ void __launch_bounds__(kThreads) peer_finalize_kernel(const PeerFinal
     __shared__ uint8_t* s_seg[16];
     for (int i = threadIdx.x; i < fp.K * fp.R; i += blockDim.x) s_acc[i] = fp.acc_table[i];
     for (int i = threadIdx.x; i < fp.nseg; i += blockDim.x) s_seg[i] = fp.seg_table[i];
+    if (fp.flag_table != nullptr) {
+        // (1) announce: this launch is stream-ordered behind this rank's accumulation, so its accumulators are complete —
+        //     block 0 tells every rank; (2) every block waits until all ranks have announced the same epoch before it
+        //     touches their accumulators.  The ranks are independent processes: a waiting block only ever waits for
+        //     kernels that depend on nothing of this rank's, so the wait is bounded by the peers' own queues.
+        if (blockIdx.x == 0 && threadIdx.x < fp.R) st_flag(fp.flag_table[threadIdx.x] + fp.rank, fp.epoch);
+        if (threadIdx.x < fp.R) {
+            const uint32_t* mine = fp.flag_table[fp.rank] + threadIdx.x;
+            while (!reached(ld_flag(mine), fp.epoch)) __nanosleep(200);
+        }
+    }
     __syncthreads();
     const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
     const size_t ngroups = nv / 4;
@@ -104,6 +133,27 @@ __global__ void __launch_bounds__(kThreads) peer_finalize_kernel(const PeerFinal
         }
         for (int t = 0; t < fp.nseg; ++t) *reinterpret_cast<uint32_t*>(s_seg[t] + i) = packed;
     }
+    if (fp.flag_table != nullptr) {
+        // (3) the last block of this rank to finish tells every rank "my slab has landed in your label volumes and I am
+        //     done with your accumulators", then (4) waits for the same word from all ranks: when this kernel completes,
+        //     the local label volumes are whole and the local accumulators may be overwritten.
+        __threadfence_system();  // this thread's peer stores are performed before the block's count below
+        __syncthreads();
+        __shared__ int s_last;
+        uint32_t* local = fp.flag_table[fp.rank];
+        if (threadIdx.x == 0) {
+            const uint32_t n = atomicAdd(local + 2 * fp.R, 1u) + 1u;
+            s_last = (n == gridDim.x) ? 1 : 0;
+            if (s_last) local[2 * fp.R] = 0u;  // ready for the next launch (same stream: ordered)
+        }
+        __syncthreads();
+        if (s_last && threadIdx.x < fp.R) {
+            __threadfence_system();
+            st_flag(fp.flag_table[threadIdx.x] + fp.R + fp.rank, fp.epoch);
+            const uint32_t* mine = local + fp.R + threadIdx.x;
+            while (!reached(ld_flag(mine), fp.epoch)) __nanosleep(200);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------- NCCL (dlopen)
@@ -153,8 +203,9 @@ using namespace bsg;
 
 extern "C" {
 
-int bsg_finalize_peer(const float* const* acc_table_dev, int K, int R, const float* wsum, int ncls, size_t nvox, size_t v0,
-                      size_t nv, int mode, const int* order_host, uint8_t* const* seg_table_dev, int nseg, void* stream) {
+static int finalize_peer_launch(const float* const* acc_table_dev, int K, int R, const float* wsum, int ncls, size_t nvox,
+                                size_t v0, size_t nv, int mode, const int* order_host, uint8_t* const* seg_table_dev, int nseg,
+                                uint32_t* const* flag_table_dev, int rank, uint32_t epoch, void* stream) {
     BSG_REQUIRE(acc_table_dev != nullptr && wsum != nullptr && seg_table_dev != nullptr, "null argument");
     BSG_REQUIRE(K >= 1 && R >= 1 && K * R <= kMaxPtrs, "K %d x R %d accumulators (<= %d)", K, R, kMaxPtrs);
     BSG_REQUIRE(nseg >= 1 && nseg <= 16, "nseg %d (1..16)", nseg);
@@ -163,6 +214,8 @@ int bsg_finalize_peer(const float* const* acc_table_dev, int K, int R, const flo
     BSG_REQUIRE(nvox % 4 == 0 && v0 % 4 == 0 && nv % 4 == 0 && v0 + nv <= nvox,
                 "voxel range [%zu, %zu) of %zu must be 4-aligned", v0, v0 + nv, nvox);
     BSG_REQUIRE((reinterpret_cast<uintptr_t>(wsum) & 15) == 0, "wsum must be 16-byte aligned");
+    BSG_REQUIRE(flag_table_dev == nullptr || (rank >= 0 && rank < R && nv > 0 && R <= kThreads),
+                "in-kernel ordering needs 0 <= rank < R and a non-empty voxel range on every rank");
     if (nv == 0) return BSG_OK;
     PeerFinalizeParams fp;
     memset(&fp, 0, sizeof(fp));
@@ -174,10 +227,30 @@ int bsg_finalize_peer(const float* const* acc_table_dev, int K, int R, const flo
     fp.ncls = ncls;
     fp.mode = mode;
     for (int k = 0; k < ncls; ++k) fp.order[k] = order_host ? order_host[k] : k;
-    peer_finalize_kernel<<<grid_for(nv / 4, kThreads, 8), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(fp, wsum, nvox,
-                                                                                                          v0, nv);
+    fp.flag_table = flag_table_dev;
+    fp.rank = rank;
+    fp.epoch = epoch;
+    int grid = grid_for(nv / 4, kThreads, 8);
+    // in-kernel ordering: blocks may sit waiting for the peers' announcements — one block per SM is plenty for a 1/R slab
+    // and keeps the waiting footprint next to the other stream's conv kernels small
+    if (flag_table_dev != nullptr && grid > sm_count_cached()) grid = sm_count_cached();
+    peer_finalize_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(fp, wsum, nvox, v0, nv);
     BSG_CUDA_OK(cudaGetLastError());
     return BSG_OK;
+}
+
+int bsg_finalize_peer(const float* const* acc_table_dev, int K, int R, const float* wsum, int ncls, size_t nvox, size_t v0,
+                      size_t nv, int mode, const int* order_host, uint8_t* const* seg_table_dev, int nseg, void* stream) {
+    return finalize_peer_launch(acc_table_dev, K, R, wsum, ncls, nvox, v0, nv, mode, order_host, seg_table_dev, nseg, nullptr,
+                                0, 0u, stream);
+}
+
+int bsg_finalize_peer_signal(const float* const* acc_table_dev, int K, int R, const float* wsum, int ncls, size_t nvox,
+                             size_t v0, size_t nv, int mode, const int* order_host, uint8_t* const* seg_table_dev, int nseg,
+                             uint32_t* const* flag_table_dev, int rank, uint32_t epoch, void* stream) {
+    BSG_REQUIRE(flag_table_dev != nullptr, "null flag table");
+    return finalize_peer_launch(acc_table_dev, K, R, wsum, ncls, nvox, v0, nv, mode, order_host, seg_table_dev, nseg,
+                                flag_table_dev, rank, epoch, stream);
 }
 
 // ---- CUDA IPC: peers map a rank's buffer into THEIR device's address space.  The handle is opened on the consuming

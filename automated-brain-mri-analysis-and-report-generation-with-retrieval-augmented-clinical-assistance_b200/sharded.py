@@ -8,8 +8,10 @@ Two routes, same result up to the order of the fp32 additions:
 * peer (default on one NVSwitch box): every accumulator and label volume lives in a slab the other ranks have mapped
   into their own device's address space (CUDA IPC: bsg_ipc_export / bsg_ipc_open).  ONE kernel per model and rank — bsg_finalize_peer — reads the
   rank's voxel slab of ALL ranks' accumulators over NVLink, sums in rank order, divides by the weight sum, averages
-  the folds, decides, and stores the uint8 labels of the slab into EVERY rank's label volume.  Two tiny NCCL
-  all-reduces order the ranks around it (all accumulators complete before / all slabs written after).
+  the folds, decides, and stores the uint8 labels of the slab into EVERY rank's label volume.  The ranks are ordered
+  INSIDE that kernel (bsg_finalize_peer_signal: release / acquire flags in peer memory — "my accumulators are complete"
+  before the reads, "my slab has landed" after the writes), so the exchange is one launch per model and rank with no
+  collective around it; BSG_PEER_SYNC=nccl brings back the two 4-byte NCCL all-reduces around bsg_finalize_peer.
 * nccl: one ncclAllReduce of each accumulator (bsg_nccl_reduce_accumulator, the library's own communicator), then the
   single-GPU bsg_finalize on every rank.
 
@@ -45,6 +47,10 @@ class ShardedExchange:
         self._token = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._comm = None
         self._side = torch.cuda.Stream(self.device)
+        self.peer_sync = os.environ.get("BSG_PEER_SYNC", "kernel").lower()  # kernel: flags inside the exchange kernel
+        if self.peer_sync not in ("kernel", "nccl"):
+            raise ValueError(f"BSG_PEER_SYNC {self.peer_sync!r}: expected 'kernel' or 'nccl'")
+        self._epoch = 0  # exchange calls so far: the same on every rank (they call in lockstep)
         self.nccl_bytes = 0   # bytes handed to NCCL collectives (accumulator route) per call of reduce()
         self.peer_bytes = 0   # bytes read from / written to peer memory by bsg_finalize_peer
         self.launches = 0
@@ -57,6 +63,10 @@ class ShardedExchange:
             for d in sorted(set(devs)):
                 if d != mine:
                     L.check(L.lib().bsg_enable_peer_access(d))
+            if len(set(devs)) < self.world:
+                # ranks sharing a device are time-sliced, not concurrent: a kernel waiting for a peer's flag would spin
+                # through its whole time slice — those set-ups keep the stream-ordered barriers around the kernel
+                self.peer_sync = "nccl"
 
     # ------------------------------------------------------------------ shared buffers
     SLAB_BYTES = 384 << 20  # two 107 MB accumulators + two 9 MB label volumes of a BraTS case, with room to spare
@@ -136,10 +146,18 @@ class ShardedExchange:
             per = -(-(nvox // 4) // self.world) * 4
             v0 = min(self.rank * per, nvox)
             nv = min(per, nvox - v0)
-            self.barrier()  # every rank's accumulators are complete
-            L.check(lib.bsg_finalize_peer(_ptr(table), K, self.world, _ptr(wsum), ncls, nvox, v0, nv, mode, order,
-                                          _ptr(segs), self.world, L.stream_ptr()))
-            self.barrier()  # every slab has landed in every label volume; accumulators may be reused
+            if self.peer_sync == "kernel" and self.world > 1 and nv > 0 and per * (self.world - 1) < nvox:
+                # flag block of every rank: arrive[R], done[R], finished-block count (zero-initialised slab memory)
+                _, flag_ptrs = self.shared(("flags",), (2 * self.world + 2,), torch.int32)
+                self._epoch += 1
+                L.check(lib.bsg_finalize_peer_signal(_ptr(table), K, self.world, _ptr(wsum), ncls, nvox, v0, nv, mode, order,
+                                                     _ptr(segs), self.world, _ptr(self._table(flag_ptrs)), self.rank,
+                                                     self._epoch, L.stream_ptr()))
+            else:
+                self.barrier()  # every rank's accumulators are complete
+                L.check(lib.bsg_finalize_peer(_ptr(table), K, self.world, _ptr(wsum), ncls, nvox, v0, nv, mode, order,
+                                              _ptr(segs), self.world, L.stream_ptr()))
+                self.barrier()  # every slab has landed in every label volume; accumulators may be reused
             self.launches += 1
             self.peer_bytes += K * ncls * nv * 4 * (self.world - 1) + nv * (self.world - 1)
             return seg_local

@@ -329,6 +329,16 @@ int bsg_finalize(const float* const* acc_list_host, int K, const float* wsum, in
  * slabs written) — e.g. two tiny NCCL all-reduces. */
 int bsg_finalize_peer(const float* const* acc_table_dev, int K, int R, const float* wsum, int ncls, size_t nvox, size_t v0,
                       size_t nv, int mode, const int* order_host, uint8_t* const* seg_table_dev, int nseg, void* stream);
+/* bsg_finalize_peer with the rank ordering INSIDE the kernel (no collective around the launch): flag_table_dev is a DEVICE
+ * array [R] of pointers to every rank's flag block (2R + 1 uint32, zero-initialised once, in peer-mapped memory) as mapped
+ * into this rank's address space; `epoch` is the number of this call (1, 2, ... — the same on every rank, which call in
+ * lockstep).  The kernel announces "rank's accumulators complete" to every rank (release store at system scope), waits
+ * until all ranks announced the epoch, reduces + finalizes + stores its slab into every label volume, announces "slab
+ * landed, done with your accumulators" and waits for the same word from all ranks: once the launch has completed on the
+ * stream, the local label volumes are whole and the local accumulators may be reused.  Every rank needs nv > 0. */
+int bsg_finalize_peer_signal(const float* const* acc_table_dev, int K, int R, const float* wsum, int ncls, size_t nvox,
+                             size_t v0, size_t nv, int mode, const int* order_host, uint8_t* const* seg_table_dev, int nseg,
+                             uint32_t* const* flag_table_dev, int rank, uint32_t epoch, void* stream);
 /* cudaDeviceEnablePeerAccess(current -> peer_device), idempotent. */
 int bsg_enable_peer_access(int peer_device);
 /* CUDA IPC plumbing for the peer route (ranks are processes).  bsg_ipc_export: the 64-byte handle of the ALLOCATION that

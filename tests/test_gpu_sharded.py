@@ -60,6 +60,51 @@ def test_finalize_peer_matches_rank_ordered_sum(K, R, mode):
     assert torch.equal(segs[0], ref) and torch.equal(segs[1], ref)
 
 
+@pytest.mark.timeout(120)
+def test_finalize_peer_signal_orders_the_ranks_in_the_kernel():
+    """bsg_finalize_peer_signal: R = 3 "ranks" played by three streams of this process.  Each rank's kernel announces its
+    accumulators, waits for the others' announcements inside the kernel, writes its slab into every rank's label volume
+    and returns only when all slabs have landed — no collective around the launches.  Three epochs reuse the flags;
+    rank 2's accumulator is filled by a kernel on ITS stream right before its exchange launch, so a rank that read
+    before the announcement would see the stale values."""
+    from brainseg_b200 import _lib as L
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    R, ncls, nvox = 3, 3, 4 * 256 * 6
+    g = torch.Generator(device="cpu").manual_seed(5)
+    accs = [torch.zeros(ncls, nvox, device=dev) for _ in range(R)]
+    wsum = torch.full((nvox,), float(R), device=dev)
+    segs = [torch.full((nvox,), 255, dtype=torch.uint8, device=dev) for _ in range(R)]
+    flags = [torch.zeros(2 * R + 2, dtype=torch.int32, device=dev) for _ in range(R)]
+    table = torch.tensor([a.data_ptr() for a in accs], dtype=torch.int64, device=dev)
+    seg_table = torch.tensor([s.data_ptr() for s in segs], dtype=torch.int64, device=dev)
+    flag_table = torch.tensor([f.data_ptr() for f in flags], dtype=torch.int64, device=dev)
+    order = (C.c_int * ncls)(1, 2, 3)
+    streams = [torch.cuda.Stream(dev) for _ in range(R)]
+    per = nvox // R
+    torch.cuda.synchronize()
+    for epoch in (1, 2, 3):
+        fresh = [torch.rand(ncls, nvox, generator=g).to(dev) * 2.0 for _ in range(R)]
+        torch.cuda.synchronize()
+        for r in (0, 1, 2):
+            with torch.cuda.stream(streams[r]):
+                if r == 2:
+                    torch.cuda._sleep(20_000_000)  # ~10 ms: ranks 0 and 1 are already waiting in their kernels
+                accs[r].copy_(fresh[r])
+                L.check(L.lib().bsg_finalize_peer_signal(_ptr(table), 1, R, _ptr(wsum), ncls, nvox, r * per, per, 1, order,
+                                                         _ptr(seg_table), R, _ptr(flag_table), r, epoch, L.stream_ptr()))
+        # each stream alone is enough to know the whole volume has landed in that rank's label volume
+        streams[0].synchronize()
+        probs = (fresh[0] + fresh[1] + fresh[2]) / wsum
+        ref = torch.zeros(nvox, dtype=torch.uint8, device=dev)
+        for i, c in enumerate((1, 2, 3)):
+            ref[probs[i] > 0.5] = c
+        assert torch.equal(segs[0], ref), f"epoch {epoch}: rank 0's label volume is not whole after its own launch"
+        torch.cuda.synchronize()
+        assert all(torch.equal(s, ref) for s in segs)
+        assert all(int(f[2 * R]) == 0 for f in flags)  # finished-block counts reset for the next launch
+
+
 def test_nccl_route_single_rank_communicator():
     """bsg_nccl_unique_id / comm_create / reduce_accumulator / comm_destroy on a one-rank communicator: the library
     resolves libnccl at run time and the all-reduce of one rank leaves the accumulator unchanged."""
