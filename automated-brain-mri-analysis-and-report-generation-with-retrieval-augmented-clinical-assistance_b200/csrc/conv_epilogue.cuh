@@ -26,6 +26,8 @@ struct EpiParams {
     float slope;
     int out_f16;         // 1: store IEEE fp16 instead of bf16
     int guard;           // 1: track the largest stored magnitude (fp16 range guard, see EpiGuard)
+    uint8_t* stage;      // non-null: write the 32 x 32 chunk (64-byte rows, 64B-swizzled) here instead of to global memory;
+                         // the caller issues the TMA tensor store (tile kernel, tma_out)
     int split_stride;    // SPLIT epilogues: channels between the three blocks [hi | hi | lo] of the fp16x3 output
 };
 
@@ -174,8 +176,8 @@ __device__ __forceinline__ void epilogue_32cols(const uint32_t (&v)[32], const E
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = f[i] > 0.f ? f[i] : f[i] * e.slope;
     }
-    if (!valid) return;
-    if (e.guard) {
+    if (!valid && e.stage == nullptr) return;
+    if (e.guard && valid) {
         float m = guard.amax;
 #pragma unroll
         for (int i = 0; i < 16; ++i) m = fmaxf(m, fmaxf(fabsf(f[2 * i]), fabsf(f[2 * i + 1])));
@@ -213,7 +215,7 @@ __device__ __forceinline__ void epilogue_32cols(const uint32_t (&v)[32], const E
         }
         return;
     }
-    if (co + 32 <= e.cout) {
+    if (co + 32 <= e.cout || e.stage != nullptr) {
         // one uniform branch around the whole block: a per-element `out_f16 ? half : bf16` is if-converted into BOTH
         // F2FP conversions plus a select, and the conversion pipe is what bounds the store-heavy epilogues (ncu on the
         // transposed conv: 82 % busy)
@@ -230,6 +232,19 @@ __device__ __forceinline__ void epilogue_32cols(const uint32_t (&v)[32], const E
                 __nv_bfloat162 b = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
                 pk[i] = *reinterpret_cast<uint32_t*>(&b);
             }
+        }
+        if (e.stage != nullptr) {
+            // staging row of this thread: 64 bytes at lane * 64, its four 16-byte pieces XOR-swizzled with address bits
+            // [7, 9) (CU_TENSOR_MAP_SWIZZLE_64B: what the store's tensor map undoes) — conflict-free 128-bit stores.
+            // Rows outside the tensor and channels >= cout are clipped by the tensor store.
+            const uint32_t row = smem_u32(e.stage) + static_cast<uint32_t>(lane) * 64u;
+            const uint32_t x = (static_cast<uint32_t>(lane) >> 1) & 3u;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(row + ((static_cast<uint32_t>(i) ^ x) << 4)),
+                             "r"(pk[4 * i]), "r"(pk[4 * i + 1]), "r"(pk[4 * i + 2]), "r"(pk[4 * i + 3])
+                             : "memory");
+            return;
         }
         __nv_bfloat16* dst = orow + co;
         if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) {

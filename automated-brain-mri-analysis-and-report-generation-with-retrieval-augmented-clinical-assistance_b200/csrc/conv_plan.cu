@@ -324,8 +324,13 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
             (d->pair == 1 || mtiles * a.n_ntiles >= 2ll * sm_count_cached()))
             a.pair = 1;
     }
+    // epilogue through shared memory + TMA tensor stores: the transposed convs (their output voxels are two apart, so the
+    // per-thread rows of the direct epilogue are 32 different 128-byte lines per store instruction: ncu had the
+    // load/store unit's tag stage saturated at 4.0 TB/s of writes); tma_store = 1 forces it for any layer
+    a.tma_out = (d->tma_store == 1 || (d->tma_store <= 0 && d->kind == BSG_CONVT_K2S2)) && d->out_split_stride == 0 &&
+                d->cout % 8 == 0;
     // kh halo reuse: needs the canonical 8 x 16 x 1 x 1 box, stride 1, 27 taps and >= 3 pipeline stages
-    const uint32_t budget = 227 * 1024 - 4096 - 6144;  // barriers + bias + alignment slack + room for co-resident CTAs
+    const uint32_t budget = 227 * 1024 - 4096 - 6144 - (a.tma_out ? kTmaOutSmemBytes : 0);  // barriers + bias + alignment slack + room for co-resident CTAs
     auto stage_bytes = [&](int khs, int taps3, uint32_t* ab, uint32_t* bb) {
         const uint32_t rows = khs ? static_cast<uint32_t>((a.bh + 2) * 8) : 128u;
         *ab = round_up(rows * a.cc * 2, 1024) * (taps3 ? 3 : 1);
@@ -398,6 +403,25 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
         uint64_t str[2] = {static_cast<uint64_t>(d->cin) * 2, static_cast<uint64_t>(d->cin) * 2 * rows};
         uint32_t box[3] = {static_cast<uint32_t>(a.cc), static_cast<uint32_t>(a.ntile / 2), 1u};
         rc = encode_map(&a.mapWh, d->weights, 3, dims, str, box, a.cc);
+    }
+    if (rc == BSG_OK && a.tma_out) {
+        // one epilogue warp = 32 consecutive rows of the 128-row tile = the sub-box (bw, sh, sd, sn) of the tile box
+        const int sh = a.bh < 32 / a.bw ? a.bh : 32 / a.bw;
+        const int sd = a.bd < 32 / (a.bw * sh) ? a.bd : 32 / (a.bw * sh);
+        const int sn = 32 / (a.bw * sh * sd);
+        const int om = a.out_mul;
+        const uint64_t oct = static_cast<uint64_t>(d->out_ctot);
+        const uint64_t Wo_ = static_cast<uint64_t>(a.Wo) * om, Ho_ = static_cast<uint64_t>(a.Ho) * om, Do_ = static_cast<uint64_t>(a.Do) * om;
+        uint64_t dims[5] = {static_cast<uint64_t>(d->cout), static_cast<uint64_t>(a.Wo), static_cast<uint64_t>(a.Ho),
+                            static_cast<uint64_t>(a.Do), static_cast<uint64_t>(a.No)};
+        uint64_t str[4] = {oct * 2 * om, oct * 2 * Wo_ * om, oct * 2 * Wo_ * Ho_ * om, oct * 2 * Wo_ * Ho_ * Do_};
+        uint32_t box[5] = {32u, static_cast<uint32_t>(a.bw), static_cast<uint32_t>(sh), static_cast<uint32_t>(sd),
+                           static_cast<uint32_t>(sn)};
+        const __nv_bfloat16* obase = static_cast<const __nv_bfloat16*>(d->out) + d->out_coff;
+        for (int par = 0; par < (om == 2 ? 8 : 1) && rc == BSG_OK; ++par) {
+            const uint64_t pw = par & 1, ph = (par >> 1) & 1, pd = (par >> 2) & 1;
+            rc = encode_map(&a.mapO[par], obase + ((pd * Ho_ + ph) * Wo_ + pw) * oct, 5, dims, str, box, 32);
+        }
     }
     if (rc != BSG_OK) {
         delete p;

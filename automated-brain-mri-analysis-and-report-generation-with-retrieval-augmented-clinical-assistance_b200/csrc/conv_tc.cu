@@ -5,7 +5,7 @@ namespace bsg {
 
 size_t conv_tc_smem_bytes(const ConvArgs& a) {
     return static_cast<size_t>(a.nstages) * (a.a_stage_bytes + a.b_stage_bytes) + 1024 /*barriers*/ + 2048 /*bias*/ +
-           1024 /*align*/;
+           1024 /*align*/ + (a.tma_out ? kTmaOutSmemBytes : 0);
 }
 
 cudaError_t launch_conv_tc(const ConvArgs& a, int grid, size_t smem_bytes, cudaStream_t stream) {

@@ -67,6 +67,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     uint64_t* tempty_bar = tfull_bar + 2;          // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
     float* sbias = reinterpret_cast<float*>(bar_area + 1024);  // [cout_pad] (<= 512), zeros when there is no bias
+    // tma_out: two 2 KB staging buffers (32 voxels x 64 bytes) per epilogue warp, 1024-byte aligned (64B swizzle atoms)
+    uint8_t* ostage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bar_area) + 3072 + 1023) & ~uintptr_t(1023));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -74,6 +76,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     if (warp == 4 && lane == 0) {
         tma_prefetch_desc(&a.mapW);
         tma_prefetch_desc(&a.mapA[0]);
+        if (a.tma_out) tma_prefetch_desc(&a.mapO[0]);
         for (int s = 0; s < a.nstages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], a.pair ? 2 : 1);  // pair mode: both CTAs' MMAs must have drained the stage
@@ -327,6 +330,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         epi.out_f16 = a.out_f16;
         epi.guard = (a.overflow != nullptr && a.out_f16) ? 1 : 0;
         epi.split_stride = a.split_stride;
+        epi.stage = nullptr;
+        // tma_out: this warp's 32 rows are the sub-box (bw, 32/bw .. ) of the tile at these offsets; its stores rotate
+        // through two staging buffers, lane 0 issues and tracks them
+        const int ewarp = q + 4 * half;
+        uint8_t* const my_stage = ostage + ewarp * 4096;
+        const int sub_h = ((q * 32) / a.bw) % a.bh, sub_d = ((q * 32) / (a.bw * a.bh)) % a.bd,
+                  sub_n = (q * 32) / (a.bw * a.bh * a.bd);
+        uint32_t nstore = 0;
         EpiGuard guard;
         guard.init();
         // running norm statistics of the (up to 8) 32-column chunks of the current N tile, flushed when the batch item
@@ -387,11 +398,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 tmem_ld_32x32(t_addr + cb, v);
                 tmem_ld_wait();
                 int co = q0 + cb;
+                int chunk_par = 0;  // tma_out: which output-parity view this chunk is stored through
                 if (a.out_mul == 2) {
                     // transposed conv: GEMM columns enumerate (parity (pd, ph, pw), channel); an N tile may span
                     // several parities, so the output voxel is re-derived per 32-column chunk (no division: the
                     // parity / channel pair is advanced chunk by chunk)
                     co = cpar;
+                    chunk_par = par;
                     orow = obase + static_cast<long long>(2 * d + ((par >> 2) & 1)) * a.os_d +
                            static_cast<long long>(2 * h + ((par >> 1) & 1)) * a.os_h +
                            static_cast<long long>(2 * w + (par & 1)) * a.os_w;
@@ -404,7 +417,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 }
                 StatAcc chunk_stats;
                 chunk_stats.s1 = chunk_stats.s2 = 0.f;
+                if (a.tma_out) {
+                    // the buffer about to be overwritten was handed to the store before last: at most one (the other
+                    // buffer's) may still be reading
+                    if (lane == 0) tma_store_wait_read<1>();
+                    __syncwarp();
+                    epi.stage = my_stage + (nstore & 1u) * 2048u;
+                }
                 epilogue_32cols<false, SPLIT>(v, epi, co, valid, lane, chunk_stats, orow, unused1, unused2, guard);
+                if (a.tma_out) {
+                    fence_proxy_async();  // every lane's staging writes -> visible to the async proxy
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_5d(&a.mapO[chunk_par], epi.stage, co, t.w0, t.h0 + sub_h, t.d0 + sub_d, t.n0 + sub_n);
+                        tma_store_commit();
+                    }
+                    ++nstore;
+                }
                 if (grouped) {
                     stats_chunk_grouped(t_addr + cb, sbias, a.bias != nullptr, a.stats, a.cout, a.No, co, valid, lane, vox_per_item,
                                         t.n0 + (q * 32) / vox_per_item);
@@ -426,6 +455,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             for (int j = 0; j < 8; ++j) flush_stats(epi, sacc[j], stat_nt * a.ntile + j * 32, lane, stat_n);
         }
         if (epi.guard) guard.flush(a.overflow);
+        if (a.tma_out && lane == 0) tma_store_wait_all();  // the staging buffers must outlive the stores reading them
     }
 
     tc_fence_before();

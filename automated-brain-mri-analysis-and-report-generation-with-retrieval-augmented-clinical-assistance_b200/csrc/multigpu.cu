@@ -34,9 +34,10 @@ struct PeerFinalizeParams {
     uint32_t epoch;
 };
 
-// Flag block of one rank (uint32): [0, R) arrive[src] = last epoch for which rank `src` announced "my accumulators are
+// Flag block of one rank (2R + 2 uint32): [0, R) arrive[src] = last epoch for which rank `src` announced "my accumulators are
 // complete", [R, 2R) done[src] = last epoch for which rank `src` finished reading this rank's accumulators and writing
-// its slab into this rank's label volumes, [2R] = local count of finished blocks.
+// its slab into this rank's label volumes, [2R] = local count of finished blocks, [2R + 1] = 0 or the code of a wait
+// that timed out.
 __device__ __forceinline__ uint32_t ld_flag(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -45,6 +46,15 @@ __device__ __forceinline__ uint32_t ld_flag(const uint32_t* p) {
 __device__ __forceinline__ void st_flag(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ unsigned long long now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Bounded wait for a flag to reach `epoch`: a rank that never arrives (crashed process, mismatched call sequence) must
+// not wedge this GPU.  After kFlagTimeoutNs the waiter gives up, records the failure in the rank's flag block (word
+// 2R + 1: the host reads it) and lets the kernel run to its end.
+constexpr unsigned long long kFlagTimeoutNs = 10ull * 1000 * 1000 * 1000;
 // epochs are compared modulo 2^32 (a flag can only lag or equal the epoch being waited for, never lead it by 2^31)
 __device__ __forceinline__ bool reached(uint32_t flag, uint32_t epoch) { return static_cast<int32_t>(flag - epoch) >= 0; }
 
@@ -65,8 +75,15 @@ __global__ void __launch_bounds__(kThreads) peer_finalize_kernel(const PeerFinal
         //     kernels that depend on nothing of this rank's, so the wait is bounded by the peers' own queues.
         if (blockIdx.x == 0 && threadIdx.x < fp.R) st_flag(fp.flag_table[threadIdx.x] + fp.rank, fp.epoch);
         if (threadIdx.x < fp.R) {
-            const uint32_t* mine = fp.flag_table[fp.rank] + threadIdx.x;
-            while (!reached(ld_flag(mine), fp.epoch)) __nanosleep(200);
+            uint32_t* local = fp.flag_table[fp.rank];
+            const unsigned long long t0 = now_ns();
+            while (!reached(ld_flag(local + threadIdx.x), fp.epoch)) {
+                __nanosleep(200);
+                if (now_ns() - t0 > kFlagTimeoutNs) {
+                    atomicExch(local + 2 * fp.R + 1, 1u + threadIdx.x);  // 1 + the rank that never announced
+                    break;
+                }
+            }
         }
     }
     __syncthreads();
@@ -150,8 +167,14 @@ __global__ void __launch_bounds__(kThreads) peer_finalize_kernel(const PeerFinal
         if (s_last && threadIdx.x < fp.R) {
             __threadfence_system();
             st_flag(fp.flag_table[threadIdx.x] + fp.R + fp.rank, fp.epoch);
-            const uint32_t* mine = local + fp.R + threadIdx.x;
-            while (!reached(ld_flag(mine), fp.epoch)) __nanosleep(200);
+            const unsigned long long t0 = now_ns();
+            while (!reached(ld_flag(local + fp.R + threadIdx.x), fp.epoch)) {
+                __nanosleep(200);
+                if (now_ns() - t0 > kFlagTimeoutNs) {
+                    atomicExch(local + 2 * fp.R + 1, 0x100u + threadIdx.x);  // 0x100 + the rank whose slab never landed
+                    break;
+                }
+            }
         }
     }
 }

@@ -187,9 +187,21 @@ class ShardedExchange:
         L.check(lib.bsg_nccl_comm_create(C.create_string_buffer(box[0], 128), self.world, self.rank, C.byref(comm)))
         return comm
 
+    def check(self):
+        """Raises if an in-kernel wait of the exchange timed out (a rank did not show up within 10 s): the label volumes
+        produced since are invalid.  Synchronises the device."""
+        torch.cuda.synchronize(self.device)
+        buf = self._bufs.get(("flags",))
+        if buf is not None:
+            code = int(buf[0][2 * self.world + 1].item())
+            if code:
+                who = (code & 0xFF) - (1 if code < 0x100 else 0)
+                raise L.BsgError(f"sharded exchange: rank {who} " + ("never announced its accumulators" if code < 0x100
+                                 else "never delivered its slab") + " (in-kernel wait timed out)")
+
     def close(self):
         """Releases the peer mappings and the communicator (call before destroy_process_group)."""
-        torch.cuda.synchronize(self.device)
+        self.check()
         if self.dist.is_initialized():
             self.dist.barrier()
         self._tables.clear()

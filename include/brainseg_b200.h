@@ -96,6 +96,10 @@ typedef struct bsg_conv_desc {
     int kw_taps;         /* 0 / 3: 3x3x3 kernel.  1: 3x3x1 kernel (kd, kh taps only), weights [9 taps (kd, kh)][cout_pad][cin]:
                             the network's first conv on an input whose w neighbours were packed into the channels by
                             bsg_gather_patch_tta(kwpack = 1) — 9 taps of K = 16 instead of 27.  Brick kernel only. */
+    int tma_store;       /* tile kernel epilogue: -1 / 0 = planner's choice (transposed convs: on), 1 = on, 2 = off.  On: every
+                            epilogue warp stages its 32 voxels x 32 channels in shared memory and writes them with one TMA
+                            tensor store (cp.async.bulk.tensor, one 64-byte row per voxel) instead of 32 scattered per-thread
+                            rows through the load/store unit — the transposed convs' output voxels are two apart. */
 } bsg_conv_desc;
 
 typedef struct bsg_conv_plan bsg_conv_plan;
@@ -330,12 +334,15 @@ int bsg_finalize(const float* const* acc_list_host, int K, const float* wsum, in
 int bsg_finalize_peer(const float* const* acc_table_dev, int K, int R, const float* wsum, int ncls, size_t nvox, size_t v0,
                       size_t nv, int mode, const int* order_host, uint8_t* const* seg_table_dev, int nseg, void* stream);
 /* bsg_finalize_peer with the rank ordering INSIDE the kernel (no collective around the launch): flag_table_dev is a DEVICE
- * array [R] of pointers to every rank's flag block (2R + 1 uint32, zero-initialised once, in peer-mapped memory) as mapped
+ * array [R] of pointers to every rank's flag block (2R + 2 uint32, zero-initialised once, in peer-mapped memory) as mapped
  * into this rank's address space; `epoch` is the number of this call (1, 2, ... — the same on every rank, which call in
  * lockstep).  The kernel announces "rank's accumulators complete" to every rank (release store at system scope), waits
  * until all ranks announced the epoch, reduces + finalizes + stores its slab into every label volume, announces "slab
  * landed, done with your accumulators" and waits for the same word from all ranks: once the launch has completed on the
- * stream, the local label volumes are whole and the local accumulators may be reused.  Every rank needs nv > 0. */
+ * stream, the local label volumes are whole and the local accumulators may be reused.  Every rank needs nv > 0.
+ * The waits are bounded (10 s): a rank that never shows up makes the kernel give up and write a non-zero code into word
+ * 2R + 1 of the local flag block (1 + r: rank r never announced; 0x100 + r: rank r's slab never landed) — the caller reads
+ * that word after synchronising; the label volumes are then invalid. */
 int bsg_finalize_peer_signal(const float* const* acc_table_dev, int K, int R, const float* wsum, int ncls, size_t nvox,
                              size_t v0, size_t nv, int mode, const int* order_host, uint8_t* const* seg_table_dev, int nseg,
                              uint32_t* const* flag_table_dev, int rank, uint32_t epoch, void* stream);

@@ -169,3 +169,80 @@ def test_gather_kwpack_matches_torch_layout():
         flipped = torch.flip(tile, dims) if dims else tile
         ref = P.kwpack_input(flipped[None], 16)[0].to(torch.float16)
         assert torch.equal(out[m], ref), f"mirror code {m}"
+
+
+# ---------------------------------------------------------------------------------------------- TMA tensor-store epilogue
+@pytest.mark.parametrize("cin,cout,N,shape,tma", [
+    (64, 64, 2, (8, 16, 16), -1),     # canonical 8x16x1x1 box, all 8 parities in one 256-column N tile... 64 x 8 = 512 -> 2 tiles
+    (64, 32, 1, (8, 16, 16), -1),     # N tile = 8 parities x 32
+    (128, 128, 3, (4, 4, 4), -1),     # 4x4x4x2 box, odd batch (partial tile along n), N tiles of 256 = 2 parities
+    (320, 320, 2, (4, 4, 4), -1),     # cout_pad 320: N tiles straddle parity boundaries
+    (64, 48, 1, (6, 10, 12), -1),     # cout 48 (channels 48..63 of the second chunk clipped), partial tiles in h and w
+    (64, 64, 2, (8, 16, 16), 2),      # the direct (per-thread row) epilogue, for comparison
+])
+def test_transposed_conv_tma_store(cin, cout, N, shape, tma):
+    """ConvTranspose3d k2 s2 (generic_UNet.py:363-364) through the tile kernel: the epilogue stages 32 voxels x 32 channels
+    per warp in shared memory and writes them with cp.async.bulk.tensor stores into the output's parity views; the
+    output lands inside a wider buffer (the skip half of the concat buffer must stay untouched)."""
+    L, P, dev = _setup()
+    D, H, W = shape
+    g = torch.Generator(device="cpu").manual_seed(cin + cout + D)
+    x = torch.randn(N, cin, D, H, W, generator=g).to(torch.float16)
+    xb = x.permute(0, 2, 3, 4, 1).contiguous().to(dev)
+    w = torch.randn(cin, cout, 2, 2, 2, generator=g) / cin ** 0.5
+    wp = P.pack_convT2_weight(w.to(dev), cin, torch.float16)
+    ctot, coff = 2 * cout + 8, 8
+    out = torch.full((N, 2 * D, 2 * H, 2 * W, ctot), 7.0, dtype=torch.float16, device=dev)
+    plan = L.ConvPlan(kind=L.BSG_CONVT_K2S2, stride=1, N=N, D=D, H=H, W=W, cin=cin, in_ptr=xb.data_ptr(), in_ctot=cin,
+                      cout=cout, out_ptr=out.data_ptr(), out_ctot=ctot, out_coff=coff, weights=wp.data_ptr(), bias=None,
+                      act=0, slope=0.0, stats=None, use_khshift=0, max_ctas=0, in_f16=1, out_f16=1, tma_store=tma)
+    plan.run()
+    torch.cuda.synchronize()
+    ref = F.conv_transpose3d(x.float().to(dev), w.to(torch.float16).float().to(dev), stride=2)
+    got = out[..., coff:coff + cout].permute(0, 4, 1, 2, 3).float()
+    err = (got - ref).abs().max().item()
+    print(f"convT {cin}->{cout} @{D}x{H}x{W} x{N} tma_store={tma}: max err {err:.4g} (ref max {ref.abs().max().item():.3g})")
+    assert err <= 2e-3 * max(ref.abs().max().item(), 1.0)
+    assert (out[..., :coff] == 7.0).all() and (out[..., coff + cout:] == 7.0).all()  # neighbours in the buffer untouched
+
+
+@pytest.mark.parametrize("cin,cout,stride,shape,stats", [
+    (64, 128, 1, (8, 16, 16), False),   # KHS mode
+    (64, 128, 2, (16, 16, 32), True),   # stride 2 + statistics
+    (128, 256, 1, (4, 8, 8), False),    # 8x8x2 box
+    (64, 80, 1, (5, 9, 11), True),      # cout 80 -> cout_pad 96, partial tiles everywhere
+])
+def test_tile_conv_with_forced_tma_store(cin, cout, stride, shape, stats):
+    """tma_store = 1 on 3x3x3 convs of the tile kernel: same results as the direct epilogue, statistics and the fp16 flag
+    are computed from the registers either way."""
+    L, P, dev = _setup()
+    D, H, W = shape
+    N = 2
+    g = torch.Generator(device="cpu").manual_seed(cin + cout + stride)
+    x = torch.randn(N, cin, D, H, W, generator=g).to(torch.float16)
+    xb = x.permute(0, 2, 3, 4, 1).contiguous().to(dev)
+    w = torch.randn(cout, cin, 3, 3, 3, generator=g) / (27 * cin) ** 0.5
+    wp = P.pack_conv3_weight(w.to(dev), cin, torch.float16)
+    b = torch.randn(cout, generator=g).to(dev)
+    bp = P.pad_bias(b, cout).to(dev)
+    Do, Ho, Wo = D // stride, H // stride, W // stride
+    outs, sts = [], []
+    for tma in (1, 2):
+        out = torch.zeros(N, Do, Ho, Wo, cout, dtype=torch.float16, device=dev)
+        st = torch.zeros(N, cout, 2, dtype=torch.float64, device=dev) if stats else None
+        plan = L.ConvPlan(kind=L.BSG_CONV_K3, stride=stride, N=N, D=D, H=H, W=W, cin=cin, in_ptr=xb.data_ptr(), in_ctot=cin,
+                          cout=cout, out_ptr=out.data_ptr(), out_ctot=cout, out_coff=0, weights=wp.data_ptr(),
+                          bias=bp.data_ptr(), act=0 if stats else 1, slope=0.01, stats=st.data_ptr() if stats else None,
+                          use_khshift=-1, max_ctas=0, in_f16=1, out_f16=1, algo=0, tma_store=tma)
+        plan.run()
+        torch.cuda.synchronize()
+        outs.append(out)
+        sts.append(st)
+    ref = F.conv3d(x.float().to(dev), w.to(torch.float16).float().to(dev), b, stride=stride, padding=1)
+    if not stats:
+        ref = F.leaky_relu(ref, 0.01)
+    got = outs[0].permute(0, 4, 1, 2, 3).float()
+    assert (got - ref).abs().max().item() <= 3e-3 * max(ref.abs().max().item(), 1.0)
+    assert torch.equal(outs[0], outs[1])
+    if stats:
+        assert torch.allclose(sts[0], sts[1], rtol=1e-12, atol=0)

@@ -103,6 +103,7 @@ def test_finalize_peer_signal_orders_the_ranks_in_the_kernel():
         torch.cuda.synchronize()
         assert all(torch.equal(s, ref) for s in segs)
         assert all(int(f[2 * R]) == 0 for f in flags)  # finished-block counts reset for the next launch
+        assert all(int(f[2 * R + 1]) == 0 for f in flags), "an in-kernel wait timed out"
 
 
 def test_nccl_route_single_rank_communicator():

@@ -232,7 +232,7 @@ def test_config1_full_case_brats_architecture():
     assert agree >= 0.999, f"label agreement {agree * 100:.4f}% < 99.9%"
     perr32, agree32, _ = _check_predict(net, vol, (128, 128, 128), (0, 1, 2), False, 0.5, (1, 2, 3), torch.sigmoid,
                                         tol=1e-4, mixed_precision=False, ref=ref)
-    assert agree32 >= 0.99999, f"fp32 mode label agreement {agree32 * 100:.5f}%"
+    assert agree32 >= 0.9999, f"fp32 mode label agreement {agree32 * 100:.5f}%"
 
 
 # ---------------------------------------------------------------------------------------------- fp32-equivalent mode
