@@ -129,7 +129,10 @@ static __device__ __noinline__ void stats_chunk_grouped(uint32_t taddr, const fl
 // lo = fp16(y - hi) (22 significant bits between them), laid out as three channel blocks [hi | hi | lo] `split_stride`
 // channels apart — exactly the K layout the next conv contracts against [w_hi | w_lo | w_hi]:
 // y*w ~= hi*w_hi + hi*w_lo + lo*w_hi, three fp16 MMAs with fp32 accumulation per fp32 multiply-add.
-template <bool THREAD_ACC, bool SPLIT = false>
+// EPI: kEpiDirect (per-thread rows straight to global memory), kEpiSplit (above), kEpiStage (the 32 x 32 chunk goes to the
+// shared-memory staging row block e.stage, the caller issues a TMA tensor store).
+constexpr int kEpiDirect = 0, kEpiSplit = 1, kEpiStage = 2;
+template <bool THREAD_ACC, int EPI = kEpiDirect>
 __device__ __forceinline__ void epilogue_32cols(const uint32_t (&v)[32], const EpiParams& e, int co, bool valid, int lane,
                                                 StatAcc& acc, __nv_bfloat16* orow, float (&t1)[32], float (&t2)[32],
                                                 EpiGuard& guard) {
@@ -176,14 +179,14 @@ __device__ __forceinline__ void epilogue_32cols(const uint32_t (&v)[32], const E
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = f[i] > 0.f ? f[i] : f[i] * e.slope;
     }
-    if (!valid && e.stage == nullptr) return;
+    if (!valid && EPI != kEpiStage) return;
     if (e.guard && valid) {
         float m = guard.amax;
 #pragma unroll
         for (int i = 0; i < 16; ++i) m = fmaxf(m, fmaxf(fabsf(f[2 * i]), fabsf(f[2 * i + 1])));
         guard.amax = m;
     }
-    if constexpr (SPLIT) {
+    if constexpr (EPI == kEpiSplit) {
         __half* base = reinterpret_cast<__half*>(orow);
         if (co + 32 <= e.cout) {
             uint32_t ph[16], pl[16];
@@ -215,7 +218,7 @@ __device__ __forceinline__ void epilogue_32cols(const uint32_t (&v)[32], const E
         }
         return;
     }
-    if (co + 32 <= e.cout || e.stage != nullptr) {
+    if (co + 32 <= e.cout || EPI == kEpiStage) {
         // one uniform branch around the whole block: a per-element `out_f16 ? half : bf16` is if-converted into BOTH
         // F2FP conversions plus a select, and the conversion pipe is what bounds the store-heavy epilogues (ncu on the
         // transposed conv: 82 % busy)
@@ -233,7 +236,7 @@ __device__ __forceinline__ void epilogue_32cols(const uint32_t (&v)[32], const E
                 pk[i] = *reinterpret_cast<uint32_t*>(&b);
             }
         }
-        if (e.stage != nullptr) {
+        if constexpr (EPI == kEpiStage) {
             // staging row of this thread: 64 bytes at lane * 64, its four 16-byte pieces XOR-swizzled with address bits
             // [7, 9) (CU_TENSOR_MAP_SWIZZLE_64B: what the store's tensor map undoes) — conflict-free 128-bit stores.
             // Rows outside the tensor and channels >= cout are clipped by the tensor store.

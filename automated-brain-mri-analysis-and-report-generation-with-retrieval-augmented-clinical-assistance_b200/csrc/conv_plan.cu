@@ -324,11 +324,11 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
             (d->pair == 1 || mtiles * a.n_ntiles >= 2ll * sm_count_cached()))
             a.pair = 1;
     }
-    // epilogue through shared memory + TMA tensor stores: the transposed convs (their output voxels are two apart, so the
-    // per-thread rows of the direct epilogue are 32 different 128-byte lines per store instruction: ncu had the
-    // load/store unit's tag stage saturated at 4.0 TB/s of writes); tma_store = 1 forces it for any layer
-    a.tma_out = (d->tma_store == 1 || (d->tma_store <= 0 && d->kind == BSG_CONVT_K2S2)) && d->out_split_stride == 0 &&
-                d->cout % 8 == 0;
+    // epilogue through shared memory + TMA tensor stores (tma_store = 1 only).  Measured on the transposed convs, whose
+    // per-thread output rows are two voxels apart (64->64 @64^3 x 4: 0.355 ms direct, 0.464 ms staged; 64->32: 0.155 /
+    // 0.196 ms): a store of 32 separate 64-byte rows costs the TMA unit more than the load/store unit, and the extra
+    // staging round trip lengthens the latency-bound TMEM -> convert -> store chain — so the planner never picks it
+    a.tma_out = d->tma_store == 1 && d->out_split_stride == 0 && d->cout % 8 == 0;
     // kh halo reuse: needs the canonical 8 x 16 x 1 x 1 box, stride 1, 27 taps and >= 3 pipeline stages
     const uint32_t budget = 227 * 1024 - 4096 - 6144 - (a.tma_out ? kTmaOutSmemBytes : 0);  // barriers + bias + alignment slack + room for co-resident CTAs
     auto stage_bytes = [&](int khs, int taps3, uint32_t* ab, uint32_t* bb) {

@@ -53,7 +53,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvArgs& a, int tile) {
 // one 3-tap weight box): the layers whose one-tap stages are bound by the per-stage round trip rather than by MMA time
 // (stride-2 32->64, the <= 8^3 levels) run a third of the stages.
 constexpr int kModeGeneric = 0, kModeKhs = 1, kModeS2 = 2, kModeS1 = 3, kModeS2x3 = 4, kModeS1x3 = 5;
-template <int CC, int MODE, bool SPLIT>
+template <int CC, int MODE, int EPI>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvArgs a) {
     constexpr bool KHS = MODE == kModeKhs;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     if (warp == 4 && lane == 0) {
         tma_prefetch_desc(&a.mapW);
         tma_prefetch_desc(&a.mapA[0]);
-        if (a.tma_out) tma_prefetch_desc(&a.mapO[0]);
+        if constexpr (EPI == kEpiStage) tma_prefetch_desc(&a.mapO[0]);
         for (int s = 0; s < a.nstages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], a.pair ? 2 : 1);  // pair mode: both CTAs' MMAs must have drained the stage
@@ -417,15 +417,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 }
                 StatAcc chunk_stats;
                 chunk_stats.s1 = chunk_stats.s2 = 0.f;
-                if (a.tma_out) {
+                if constexpr (EPI == kEpiStage) {
                     // the buffer about to be overwritten was handed to the store before last: at most one (the other
                     // buffer's) may still be reading
                     if (lane == 0) tma_store_wait_read<1>();
                     __syncwarp();
                     epi.stage = my_stage + (nstore & 1u) * 2048u;
                 }
-                epilogue_32cols<false, SPLIT>(v, epi, co, valid, lane, chunk_stats, orow, unused1, unused2, guard);
-                if (a.tma_out) {
+                epilogue_32cols<false, EPI>(v, epi, co, valid, lane, chunk_stats, orow, unused1, unused2, guard);
+                if constexpr (EPI == kEpiStage) {
                     fence_proxy_async();  // every lane's staging writes -> visible to the async proxy
                     __syncwarp();
                     if (lane == 0) {
@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             for (int j = 0; j < 8; ++j) flush_stats(epi, sacc[j], stat_nt * a.ntile + j * 32, lane, stat_n);
         }
         if (epi.guard) guard.flush(a.overflow);
-        if (a.tma_out && lane == 0) tma_store_wait_all();  // the staging buffers must outlive the stores reading them
+        if (EPI == kEpiStage && lane == 0) tma_store_wait_all();  // the staging buffers must outlive the stores reading them
     }
 
     tc_fence_before();
@@ -467,10 +467,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
 }
 
-template <int CC, int MODE, bool SPLIT>
+template <int CC, int MODE, int EPI>
 static cudaError_t launch_variant(const ConvArgs& a, int grid, size_t smem_bytes, cudaStream_t stream) {
     static unsigned long long attr_done = 0;  // per device
-    if (cudaError_t e = ensure_max_smem(conv_tc_kernel<CC, MODE, SPLIT>, &attr_done, 232448); e != cudaSuccess) return e;
+    if (cudaError_t e = ensure_max_smem(conv_tc_kernel<CC, MODE, EPI>, &attr_done, 232448); e != cudaSuccess) return e;
     if (a.pair) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(static_cast<unsigned>(grid));
@@ -484,42 +484,42 @@ static cudaError_t launch_variant(const ConvArgs& a, int grid, size_t smem_bytes
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, conv_tc_kernel<CC, MODE, SPLIT>, a);
+        return cudaLaunchKernelEx(&cfg, conv_tc_kernel<CC, MODE, EPI>, a);
     }
-    conv_tc_kernel<CC, MODE, SPLIT><<<grid, kThreads, smem_bytes, stream>>>(a);
+    conv_tc_kernel<CC, MODE, EPI><<<grid, kThreads, smem_bytes, stream>>>(a);
     return cudaGetLastError();
 }
 
-template <bool SPLIT>
+template <int EPI>
 static cudaError_t launch_modes(const ConvArgs& a, int grid, size_t smem_bytes, cudaStream_t stream) {
     if (a.khshift) {
-        if (a.cc == 64) return launch_variant<64, kModeKhs, SPLIT>(a, grid, smem_bytes, stream);
-        if (a.cc == 32) return launch_variant<32, kModeKhs, SPLIT>(a, grid, smem_bytes, stream);
-        return launch_variant<16, kModeKhs, SPLIT>(a, grid, smem_bytes, stream);
+        if (a.cc == 64) return launch_variant<64, kModeKhs, EPI>(a, grid, smem_bytes, stream);
+        if (a.cc == 32) return launch_variant<32, kModeKhs, EPI>(a, grid, smem_bytes, stream);
+        return launch_variant<16, kModeKhs, EPI>(a, grid, smem_bytes, stream);
     }
     if (a.taps3 && a.ntaps == 27 && !a.pair) {
         if (a.stride == 2) {
-            if (a.cc == 64) return launch_variant<64, kModeS2x3, SPLIT>(a, grid, smem_bytes, stream);
-            if (a.cc == 32) return launch_variant<32, kModeS2x3, SPLIT>(a, grid, smem_bytes, stream);
-            return launch_variant<16, kModeS2x3, SPLIT>(a, grid, smem_bytes, stream);
+            if (a.cc == 64) return launch_variant<64, kModeS2x3, EPI>(a, grid, smem_bytes, stream);
+            if (a.cc == 32) return launch_variant<32, kModeS2x3, EPI>(a, grid, smem_bytes, stream);
+            return launch_variant<16, kModeS2x3, EPI>(a, grid, smem_bytes, stream);
         }
-        if (a.cc == 64) return launch_variant<64, kModeS1x3, SPLIT>(a, grid, smem_bytes, stream);
-        if (a.cc == 32) return launch_variant<32, kModeS1x3, SPLIT>(a, grid, smem_bytes, stream);
-        return launch_variant<16, kModeS1x3, SPLIT>(a, grid, smem_bytes, stream);
+        if (a.cc == 64) return launch_variant<64, kModeS1x3, EPI>(a, grid, smem_bytes, stream);
+        if (a.cc == 32) return launch_variant<32, kModeS1x3, EPI>(a, grid, smem_bytes, stream);
+        return launch_variant<16, kModeS1x3, EPI>(a, grid, smem_bytes, stream);
     }
     if (a.stride == 2 && a.ntaps == 27) {
-        if (a.cc == 64) return launch_variant<64, kModeS2, SPLIT>(a, grid, smem_bytes, stream);
-        if (a.cc == 32) return launch_variant<32, kModeS2, SPLIT>(a, grid, smem_bytes, stream);
-        return launch_variant<16, kModeS2, SPLIT>(a, grid, smem_bytes, stream);
+        if (a.cc == 64) return launch_variant<64, kModeS2, EPI>(a, grid, smem_bytes, stream);
+        if (a.cc == 32) return launch_variant<32, kModeS2, EPI>(a, grid, smem_bytes, stream);
+        return launch_variant<16, kModeS2, EPI>(a, grid, smem_bytes, stream);
     }
     if (a.stride == 1 && a.ntaps == 27) {
-        if (a.cc == 64) return launch_variant<64, kModeS1, SPLIT>(a, grid, smem_bytes, stream);
-        if (a.cc == 32) return launch_variant<32, kModeS1, SPLIT>(a, grid, smem_bytes, stream);
-        return launch_variant<16, kModeS1, SPLIT>(a, grid, smem_bytes, stream);
+        if (a.cc == 64) return launch_variant<64, kModeS1, EPI>(a, grid, smem_bytes, stream);
+        if (a.cc == 32) return launch_variant<32, kModeS1, EPI>(a, grid, smem_bytes, stream);
+        return launch_variant<16, kModeS1, EPI>(a, grid, smem_bytes, stream);
     }
-    if (a.cc == 64) return launch_variant<64, kModeGeneric, SPLIT>(a, grid, smem_bytes, stream);
-    if (a.cc == 32) return launch_variant<32, kModeGeneric, SPLIT>(a, grid, smem_bytes, stream);
-    return launch_variant<16, kModeGeneric, SPLIT>(a, grid, smem_bytes, stream);
+    if (a.cc == 64) return launch_variant<64, kModeGeneric, EPI>(a, grid, smem_bytes, stream);
+    if (a.cc == 32) return launch_variant<32, kModeGeneric, EPI>(a, grid, smem_bytes, stream);
+    return launch_variant<16, kModeGeneric, EPI>(a, grid, smem_bytes, stream);
 }
 
 }  // namespace

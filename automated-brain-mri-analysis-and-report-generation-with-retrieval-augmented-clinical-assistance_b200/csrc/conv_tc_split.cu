@@ -5,7 +5,7 @@
 namespace bsg {
 
 cudaError_t launch_conv_tc_split(const ConvArgs& a, int grid, size_t smem_bytes, cudaStream_t stream) {
-    return launch_modes<true>(a, grid, smem_bytes, stream);
+    return launch_modes<kEpiSplit>(a, grid, smem_bytes, stream);
 }
 
 }  // namespace bsg

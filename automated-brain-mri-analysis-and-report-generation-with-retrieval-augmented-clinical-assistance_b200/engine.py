@@ -93,9 +93,9 @@ class UNetEngine:
         self.fuse_norm = os.environ.get("BSG_FUSE_NORM", "1") != "0" and not self.split
         self.fused_norms = 0
         self.try_kwpack = os.environ.get("BSG_KWPACK", "1") != "0" and not self.split
-        # tile-kernel epilogue through shared memory + TMA tensor stores: -1 planner's choice (transposed convs), 1 every
-        # tile-kernel layer, 2 none (measurement switch)
-        self.tma_store = int(os.environ.get("BSG_TMA_STORE", "-1"))
+        # tile-kernel epilogue through shared memory + TMA tensor stores: 1 = every tile-kernel layer (measurement switch;
+        # measured slower than the direct per-thread stores, see conv_plan.cu), default off
+        self.tma_store = int(os.environ.get("BSG_TMA_STORE", "0"))
         self.kwpack = False  # the first conv reads the kw-packed input layout (set by _add_block when its plan took it)
         self.flops_algo = 0.0    # algorithmic FLOPs on the real channel counts (the 4 input channels are padded to 16)
         self.act_dtype = torch.float16 if self.f16 else torch.bfloat16

@@ -173,17 +173,17 @@ def test_gather_kwpack_matches_torch_layout():
 
 # ---------------------------------------------------------------------------------------------- TMA tensor-store epilogue
 @pytest.mark.parametrize("cin,cout,N,shape,tma", [
-    (64, 64, 2, (8, 16, 16), -1),     # canonical 8x16x1x1 box, all 8 parities in one 256-column N tile... 64 x 8 = 512 -> 2 tiles
-    (64, 32, 1, (8, 16, 16), -1),     # N tile = 8 parities x 32
-    (128, 128, 3, (4, 4, 4), -1),     # 4x4x4x2 box, odd batch (partial tile along n), N tiles of 256 = 2 parities
-    (320, 320, 2, (4, 4, 4), -1),     # cout_pad 320: N tiles straddle parity boundaries
-    (64, 48, 1, (6, 10, 12), -1),     # cout 48 (channels 48..63 of the second chunk clipped), partial tiles in h and w
-    (64, 64, 2, (8, 16, 16), 2),      # the direct (per-thread row) epilogue, for comparison
+    (64, 64, 2, (8, 16, 16), 1),      # canonical 8x16x1x1 box, N tiles of 256 columns = 4 parities x 64
+    (64, 32, 1, (8, 16, 16), 1),      # N tile = 8 parities x 32
+    (128, 128, 3, (4, 4, 4), 1),      # 4x4x4x2 box, odd batch (partial tile along n), N tiles of 256 = 2 parities
+    (320, 320, 2, (4, 4, 4), 1),      # cout_pad 320: N tiles straddle parity boundaries
+    (64, 48, 1, (6, 10, 12), 1),      # cout 48 (channels 48..63 of the second chunk clipped), partial tiles in h and w
+    (64, 64, 2, (8, 16, 16), 0),      # the direct (per-thread row) epilogue — the planner's choice — for comparison
 ])
 def test_transposed_conv_tma_store(cin, cout, N, shape, tma):
-    """ConvTranspose3d k2 s2 (generic_UNet.py:363-364) through the tile kernel: the epilogue stages 32 voxels x 32 channels
-    per warp in shared memory and writes them with cp.async.bulk.tensor stores into the output's parity views; the
-    output lands inside a wider buffer (the skip half of the concat buffer must stay untouched)."""
+    """ConvTranspose3d k2 s2 (generic_UNet.py:363-364) through the tile kernel with tma_store = 1: the epilogue stages 32
+    voxels x 32 channels per warp in shared memory and writes them with cp.async.bulk.tensor stores into the output's
+    parity views; the output lands inside a wider buffer (the skip half of the concat buffer must stay untouched)."""
     L, P, dev = _setup()
     D, H, W = shape
     g = torch.Generator(device="cpu").manual_seed(cin + cout + D)
@@ -227,7 +227,7 @@ def test_tile_conv_with_forced_tma_store(cin, cout, stride, shape, stats):
     bp = P.pad_bias(b, cout).to(dev)
     Do, Ho, Wo = D // stride, H // stride, W // stride
     outs, sts = [], []
-    for tma in (1, 2):
+    for tma in (1, 0):
         out = torch.zeros(N, Do, Ho, Wo, cout, dtype=torch.float16, device=dev)
         st = torch.zeros(N, cout, 2, dtype=torch.float64, device=dev) if stats else None
         plan = L.ConvPlan(kind=L.BSG_CONV_K3, stride=stride, N=N, D=D, H=H, W=W, cin=cin, in_ptr=xb.data_ptr(), in_ctot=cin,
@@ -243,6 +243,8 @@ def test_tile_conv_with_forced_tma_store(cin, cout, stride, shape, stats):
         ref = F.leaky_relu(ref, 0.01)
     got = outs[0].permute(0, 4, 1, 2, 3).float()
     assert (got - ref).abs().max().item() <= 3e-3 * max(ref.abs().max().item(), 1.0)
-    assert torch.equal(outs[0], outs[1])
+    # the staging buffers take shared memory from the pipeline, so the planner may pick another stage layout (tap order):
+    # same values up to the order of the fp32 additions
+    assert (outs[0].float() - outs[1].float()).abs().max().item() <= 2e-3 * max(ref.abs().max().item(), 1.0)
     if stats:
-        assert torch.allclose(sts[0], sts[1], rtol=1e-12, atol=0)
+        assert torch.allclose(sts[0], sts[1], rtol=1e-4, atol=1e-3)

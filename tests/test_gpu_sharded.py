@@ -82,6 +82,10 @@ def test_finalize_peer_signal_orders_the_ranks_in_the_kernel():
     order = (C.c_int * ncls)(1, 2, 3)
     streams = [torch.cuda.Stream(dev) for _ in range(R)]
     per = nvox // R
+    # every kernel used below runs once BEFORE any rank waits inside a kernel: CUDA loads a kernel lazily at its first
+    # launch, and that load waits for the device to drain — behind a kernel that is itself waiting for the launch
+    torch.cuda._sleep(1000)
+    accs[0].copy_(accs[1])
     torch.cuda.synchronize()
     for epoch in (1, 2, 3):
         fresh = [torch.rand(ncls, nvox, generator=g).to(dev) * 2.0 for _ in range(R)]
