@@ -509,7 +509,8 @@ def run_ours(args):
     log(f"rank {rank}/{world}: building models ({torch.get_num_threads()} host threads)")
     m1, m2 = SY.build_benchmark_models(args.model2)
     sharded_only = args.mode == "latency" and world > 1
-    pipe = PL.BratsCasePipeline([m1, m2], PATCH, args.step_size, (0, 1, 2), True, True, (1, 2, 3), "brats2025", batch=args.batch)
+    pipe = PL.BratsCasePipeline([m1, m2], PATCH, args.step_size, (0, 1, 2), True, True, (1, 2, 3), "brats2025", batch=args.batch,
+                                lanes=args.lanes)
     eng1, eng2 = pipe.predictors[0].engine, pipe.predictors[1].engine
     kinds = sorted({"fp16" if e.f16 else "bf16" for e in (eng1, eng2)})
     act_dtype = kinds[0] if len(kinds) == 1 else "+".join(kinds)  # 16-bit operands, fp32 accumulation in TMEM
@@ -827,6 +828,7 @@ def main():
                          "blobby synthetic labels (configs[3] as written)")
     ap.add_argument("--distinct", type=int, default=8, help="distinct seeded cases per rank (N > 1)")
     ap.add_argument("--batch", type=int, default=16, help="(tile, mirror) forwards in flight per model (2 stream lanes)")
+    ap.add_argument("--lanes", type=int, default=2, help="stream lanes the forwards in flight are dealt to")
     ap.add_argument("--patch", type=int, default=128, help="cubic patch size (configs[4] sweep: 128 / 160)")
     ap.add_argument("--step-size", type=float, default=0.5, help="sliding-window step (configs[4] sweep: 0.5 / 0.25)")
     ap.add_argument("--volume", type=int, nargs=3, default=None, metavar=("Z", "Y", "X"),
