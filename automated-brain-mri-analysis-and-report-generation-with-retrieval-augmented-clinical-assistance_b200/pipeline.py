@@ -103,6 +103,15 @@ class BratsCasePipeline:
         sh = self.shard
         main = torch.cuda.current_stream(self.device)
         side = sh.side_stream()
+        trace = getattr(self, "trace", None)  # bench: list collecting (label, event) pairs of one case
+
+        def mark(label, stream):
+            if trace is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(stream)
+                trace.append((label, ev))
+
+        mark("start", main)
         members = [[p for row in self.fold_predictors for p in row]] if self.ensemble == "prob_mean" else \
             [list(row) for row in self.fold_predictors]
         segs = []
@@ -114,12 +123,14 @@ class BratsCasePipeline:
                 acc.zero_()
                 pred.accumulate(vol, acc)
                 keys.append(key)
+            mark(f"forwards_{mi}", main)
             ready = torch.cuda.Event()
             ready.record(main)
             side.wait_event(ready)
             _, _, wsum = row[0].geometry(shape)
             with torch.cuda.stream(side):
                 seg = sh.finalize(keys, wsum, row[0].engine.num_classes, self.regions, ("seg", mi, shape))
+            mark(f"exchange_{mi}", side)
             segs.append(seg.view(shape))
         done = torch.cuda.Event()
         done.record(side)

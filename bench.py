@@ -645,6 +645,17 @@ def run_ours(args):
                 torch.cuda.synchronize()
                 singles.append(time.perf_counter() - t0)
                 singles_nopost.append(t_seg)
+            # one more single case with phase events: this rank's forwards of each model and the exchange behind them
+            barrier()
+            lp.trace = []
+            pend = lp.submit(case0, gt0)
+            pend["done"].synchronize()
+            tr, lp.trace = dict(lp.trace), None
+            phases = torch.tensor([tr["start"].elapsed_time(tr["forwards_0"]), tr["forwards_0"].elapsed_time(tr["exchange_0"]),
+                                   tr["forwards_0"].elapsed_time(tr["forwards_1"]), tr["forwards_1"].elapsed_time(tr["exchange_1"])],
+                                  dtype=torch.float64, device=dev)
+            dist.all_reduce(phases, op=dist.ReduceOp.MAX)
+            lp.finish(pend, post=False)
             tt = torch.tensor([t_lat, statistics.median(singles), statistics.median(singles_nopost)], dtype=torch.float64, device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             t_lat, t_single_lat, t_single_seg = tt.tolist()
@@ -655,6 +666,12 @@ def run_ours(args):
             records[route] = {"ms_per_case": t_lat / args.steps * 1e3, "cases_per_s": args.steps / t_lat,
                               "single_case_ms": t_single_lat * 1e3, "single_case_ms_without_post": t_single_seg * 1e3,
                               "gpu_launches": int(lat_launches), "forwards_in_flight": lat_batch,
+                              "single_case_phases_ms_max_over_ranks": {
+                                  "model1_forwards": phases[0].item(), "model1_exchange_after_forwards": phases[1].item(),
+                                  "model2_forwards": phases[2].item(), "model2_exchange_after_forwards": phases[3].item(),
+                                  "note": "CUDA events on one unpipelined case; an exchange is timed from the end of the "
+                                          "rank's own forwards to its label volume being whole (includes waiting for "
+                                          "the slowest rank); model 1's exchange overlaps model 2's forwards"},
                               "exchange_bytes_per_case": int((sh.peer_bytes + sh.nccl_bytes) / max(1, sh.launches) * 2),
                               "labels_equal_to_1gpu": same, "label_sha256_16": sha16(res["segmentation"])}
             log(f"latency mode [{route}]: {t_lat / args.steps * 1e3:.1f} ms per case pipelined, single case "
