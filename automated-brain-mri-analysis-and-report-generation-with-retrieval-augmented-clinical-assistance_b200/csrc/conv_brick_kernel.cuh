@@ -409,7 +409,11 @@ __global__ void __launch_bounds__(brick_threads(CC, NT, STATS, XF), 1) conv_bric
         EpiGuard guard;
         guard.init();
         StatAcc sacc[kChunks];
-        float t1[kChunks][32], t2[kChunks][32];  // per-thread sums over the planes of one brick (STATS only)
+        // per-thread sums over ALL planes this warp sees of one batch item (STATS only): fp32 sums of a few hundred values;
+        // the warp transpose-reduce (62 shuffles + ~190 selects / adds per chunk) runs once per batch item, not per brick —
+        // ncu source view of the 16 -> 64 first layer: the reduce was 62 of the 414 warp instructions an epilogue warp
+        // issues per plane and chunk, in an epilogue that is issue-bound
+        float t1[kChunks][32], t2[kChunks][32];
         const int cb0 = kColSplit ? group * 32 : 0;  // first column of this warp's chunk(s)
 #pragma unroll
         for (int j = 0; j < kChunks; ++j) {
@@ -424,7 +428,14 @@ __global__ void __launch_bounds__(brick_threads(CC, NT, STATS, XF), 1) conv_bric
             const uint32_t bb = tcount & 1u, par = (tcount >> 1) & 1u;
             if (STATS && t.n != stat_n) {
 #pragma unroll
-                for (int j = 0; j < kChunks; ++j) flush_stats(epi, sacc[j], cb0 + j * 32, lane, stat_n);
+                for (int j = 0; j < kChunks; ++j) {
+                    if (kThreadAcc && stat_n >= 0) {
+                        stats_transpose_reduce(t1[j], t2[j], lane, sacc[j]);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) t1[j][i] = t2[j][i] = 0.f;
+                    }
+                    flush_stats(epi, sacc[j], cb0 + j * 32, lane, stat_n);
+                }
                 stat_n = t.n;
             }
             __nv_bfloat16* obase = a.out + t.n * a.os_n + static_cast<long long>(t.h0 + ih) * a.os_h +
@@ -447,18 +458,13 @@ __global__ void __launch_bounds__(brick_threads(CC, NT, STATS, XF), 1) conv_bric
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[slot]);
             }
-            if (STATS && kThreadAcc) {  // one warp reduction per brick instead of one per plane
-#pragma unroll
-                for (int j = 0; j < kChunks; ++j) {
-                    stats_transpose_reduce(t1[j], t2[j], lane, sacc[j]);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) t1[j][i] = t2[j][i] = 0.f;
-                }
-            }
         }
         if (STATS) {
 #pragma unroll
-            for (int j = 0; j < kChunks; ++j) flush_stats(epi, sacc[j], cb0 + j * 32, lane, stat_n);
+            for (int j = 0; j < kChunks; ++j) {
+                if (kThreadAcc && stat_n >= 0) stats_transpose_reduce(t1[j], t2[j], lane, sacc[j]);
+                flush_stats(epi, sacc[j], cb0 + j * 32, lane, stat_n);
+            }
         }
         if (epi.guard) guard.flush(a.overflow);
     }

@@ -65,6 +65,21 @@ __device__ __forceinline__ void flush_stats(const EpiParams& e, StatAcc& acc, in
     acc.s2 = 0.f;
 }
 
+// Packed fp32 pairs (sm_100 FADD2 / FFMA2: two fp32 operations per issue slot) for the epilogue's bias add and
+// per-thread statistic sums — the first layers' epilogues are bound by instruction issue, not by the tensor pipe.
+__device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1, float b0, float b1) {  // d = a + b
+    asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 ra, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, ra;\n\t}\n"
+        : "=f"(d0), "=f"(d1)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void fma2(float& c0, float& c1, float a0, float a1, float b0, float b1) {  // c += a * b
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%0, %1};\n\t"
+        "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0, %1}, rc;\n\t}\n"
+        : "+f"(c0), "+f"(c1)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
 // Per-channel sum / sum of squares over the warp's 32 lanes by transpose-reduce (31 shuffles per array): afterwards
 // lane l owns channel l of the chunk, added into its running statistics.
 __device__ __forceinline__ void stats_transpose_reduce(float (&s1)[32], float (&s2)[32], int lane, StatAcc& acc) {
@@ -147,10 +162,8 @@ __device__ __forceinline__ void epilogue_32cols(const uint32_t (&v)[32], const E
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n"
                          : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3)
                          : "r"(baddr + 16u * i));
-            f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b0;
-            f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b1;
-            f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b2;
-            f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b3;
+            add2(f[4 * i + 0], f[4 * i + 1], __uint_as_float(v[4 * i + 0]), __uint_as_float(v[4 * i + 1]), b0, b1);
+            add2(f[4 * i + 2], f[4 * i + 3], __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]), b2, b3);
         }
     } else {
 #pragma unroll
@@ -158,11 +171,12 @@ __device__ __forceinline__ void epilogue_32cols(const uint32_t (&v)[32], const E
     }
     if (e.stats != nullptr) {
         if (THREAD_ACC) {
+            if (valid) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float x = valid ? f[i] : 0.f;
-                t1[i] += x;
-                t2[i] = fmaf(x, x, t2[i]);
+                for (int i = 0; i < 16; ++i) {
+                    add2(t1[2 * i], t1[2 * i + 1], t1[2 * i], t1[2 * i + 1], f[2 * i], f[2 * i + 1]);
+                    fma2(t2[2 * i], t2[2 * i + 1], f[2 * i], f[2 * i + 1], f[2 * i], f[2 * i + 1]);
+                }
             }
         } else {
             float s1[32], s2[32];
