@@ -406,6 +406,7 @@ __global__ void __launch_bounds__(brick_threads(CC, NT, STATS, XF), 1) conv_bric
         epi.guard = (a.overflow != nullptr && a.out_f16) ? 1 : 0;
         epi.split_stride = 0;
         epi.stage = nullptr;
+        epi.stage_wide = epi.stage_sub = 0;
         EpiGuard guard;
         guard.init();
         StatAcc sacc[kChunks];

@@ -26,8 +26,10 @@ struct EpiParams {
     float slope;
     int out_f16;         // 1: store IEEE fp16 instead of bf16
     int guard;           // 1: track the largest stored magnitude (fp16 range guard, see EpiGuard)
-    uint8_t* stage;      // non-null: write the 32 x 32 chunk (64-byte rows, 64B-swizzled) here instead of to global memory;
-                         // the caller issues the TMA tensor store (tile kernel, tma_out)
+    uint8_t* stage;      // kEpiStage: the 32 x 32 chunk goes here instead of to global memory; the caller issues the TMA tensor
+                         // store (tile kernel, tma_out).  stage_wide = 0: rows of 64 bytes (64B swizzle); 1: rows of 128 bytes
+                         // (128B swizzle), this chunk being their half `stage_sub`
+    int stage_wide, stage_sub;
     int split_stride;    // SPLIT epilogues: channels between the three blocks [hi | hi | lo] of the fp16x3 output
 };
 
@@ -251,14 +253,17 @@ __device__ __forceinline__ void epilogue_32cols(const uint32_t (&v)[32], const E
             }
         }
         if constexpr (EPI == kEpiStage) {
-            // staging row of this thread: 64 bytes at lane * 64, its four 16-byte pieces XOR-swizzled with address bits
-            // [7, 9) (CU_TENSOR_MAP_SWIZZLE_64B: what the store's tensor map undoes) — conflict-free 128-bit stores.
-            // Rows outside the tensor and channels >= cout are clipped by the tensor store.
-            const uint32_t row = smem_u32(e.stage) + static_cast<uint32_t>(lane) * 64u;
-            const uint32_t x = (static_cast<uint32_t>(lane) >> 1) & 3u;
+            // staging row of this thread: 64 bytes at lane * 64 (or its half of the 128 bytes at lane * 128), the 16-byte
+            // pieces XOR-swizzled the way the store's tensor map undoes (CU_TENSOR_MAP_SWIZZLE_64B: address bits [4, 6)
+            // ^ [7, 9); _128B: bits [4, 7) ^ [7, 10)) — conflict-free 128-bit shared-memory stores.  Rows outside the
+            // tensor and channels >= cout are clipped by the tensor store.
+            const uint32_t ulane = static_cast<uint32_t>(lane);
+            const uint32_t row = smem_u32(e.stage) + (e.stage_wide ? ulane * 128u : ulane * 64u);
+            const uint32_t x = e.stage_wide ? (ulane & 7u) : ((ulane >> 1) & 3u);
+            const uint32_t p0 = e.stage_wide ? static_cast<uint32_t>(e.stage_sub) * 4u : 0u;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(row + ((static_cast<uint32_t>(i) ^ x) << 4)),
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(row + (((p0 + static_cast<uint32_t>(i)) ^ x) << 4)),
                              "r"(pk[4 * i]), "r"(pk[4 * i + 1]), "r"(pk[4 * i + 2]), "r"(pk[4 * i + 3])
                              : "memory");
             return;

@@ -415,12 +415,13 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
         uint64_t dims[5] = {static_cast<uint64_t>(d->cout), static_cast<uint64_t>(a.Wo), static_cast<uint64_t>(a.Ho),
                             static_cast<uint64_t>(a.Do), static_cast<uint64_t>(a.No)};
         uint64_t str[4] = {oct * 2 * om, oct * 2 * Wo_ * om, oct * 2 * Wo_ * Ho_ * om, oct * 2 * Wo_ * Ho_ * Do_};
-        uint32_t box[5] = {32u, static_cast<uint32_t>(a.bw), static_cast<uint32_t>(sh), static_cast<uint32_t>(sd),
-                           static_cast<uint32_t>(sn)};
+        a.store_cols = (a.cout_pad % 64 == 0 && a.ntile % 64 == 0) ? 64 : 32;
+        uint32_t box[5] = {static_cast<uint32_t>(a.store_cols), static_cast<uint32_t>(a.bw), static_cast<uint32_t>(sh),
+                           static_cast<uint32_t>(sd), static_cast<uint32_t>(sn)};
         const __nv_bfloat16* obase = static_cast<const __nv_bfloat16*>(d->out) + d->out_coff;
         for (int par = 0; par < (om == 2 ? 8 : 1) && rc == BSG_OK; ++par) {
             const uint64_t pw = par & 1, ph = (par >> 1) & 1, pd = (par >> 2) & 1;
-            rc = encode_map(&a.mapO[par], obase + ((pd * Ho_ + ph) * Wo_ + pw) * oct, 5, dims, str, box, 32);
+            rc = encode_map(&a.mapO[par], obase + ((pd * Ho_ + ph) * Wo_ + pw) * oct, 5, dims, str, box, a.store_cols);
         }
     }
     if (rc != BSG_OK) {

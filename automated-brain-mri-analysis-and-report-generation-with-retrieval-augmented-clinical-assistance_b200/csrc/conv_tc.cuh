@@ -16,6 +16,8 @@ struct ConvArgs {
     CUtensorMap mapO[8];  // tma_out: the output tensor (cout, Wo, Ho, Do, No) in TILE coordinates, box = one epilogue warp's
                           // 32 voxels x 32 channels; transposed conv: one double-strided view per output parity (pd,ph,pw)
     int tma_out;          // 1: epilogue stores through shared memory + TMA tensor stores
+    int store_cols;       // tma_out: channels per store row, 64 (128-byte rows = whole lines) when cout_pad and the N tile
+                          // are multiples of 64, else 32
     int pair;             // 1: launched as 2-CTA clusters; the two CTAs work on neighbouring M tiles of the same N tile
                           //    in lock-step, each fetches half of every weight stage and multicasts it to both
     int bw, bh, bd, bn;   // output tile box, bw*bh*bd*bn == 128
@@ -49,7 +51,7 @@ struct ConvArgs {
     int in_f16;    // 1: activations and weights are IEEE fp16 instead of bf16
 };
 
-constexpr unsigned kTmaOutSmemBytes = 8 * 2 * 2048 + 1024;  // two staging buffers per epilogue warp + alignment
+constexpr unsigned kTmaOutSmemBytes = 8 * 2 * 4096 + 1024;  // two staging buffers per epilogue warp + alignment
 cudaError_t launch_conv_tc(const ConvArgs& a, int grid, size_t smem_bytes, cudaStream_t stream);  // pair: grid even
 cudaError_t launch_conv_tc_tma(const ConvArgs& a, int grid, size_t smem_bytes, cudaStream_t stream);
 cudaError_t launch_conv_tc_split(const ConvArgs& a, int grid, size_t smem_bytes, cudaStream_t stream);

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     uint64_t* tempty_bar = tfull_bar + 2;          // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
     float* sbias = reinterpret_cast<float*>(bar_area + 1024);  // [cout_pad] (<= 512), zeros when there is no bias
-    // tma_out: two 2 KB staging buffers (32 voxels x 64 bytes) per epilogue warp, 1024-byte aligned (64B swizzle atoms)
+    // tma_out: two 4 KB staging buffers (32 voxels x 64 or 128 bytes) per epilogue warp, 1024-byte aligned (swizzle atoms)
     uint8_t* ostage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bar_area) + 3072 + 1023) & ~uintptr_t(1023));
 
     const int warp = threadIdx.x >> 5;
@@ -331,10 +331,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         epi.guard = (a.overflow != nullptr && a.out_f16) ? 1 : 0;
         epi.split_stride = a.split_stride;
         epi.stage = nullptr;
+        epi.stage_wide = epi.stage_sub = 0;
         // tma_out: this warp's 32 rows are the sub-box (bw, 32/bw .. ) of the tile at these offsets; its stores rotate
         // through two staging buffers, lane 0 issues and tracks them
         const int ewarp = q + 4 * half;
-        uint8_t* const my_stage = ostage + ewarp * 4096;
+        uint8_t* const my_stage = ostage + ewarp * 8192;
         const int sub_h = ((q * 32) / a.bw) % a.bh, sub_d = ((q * 32) / (a.bw * a.bh)) % a.bd,
                   sub_n = (q * 32) / (a.bw * a.bh * a.bd);
         uint32_t nstore = 0;
@@ -391,6 +392,57 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     ++par;
                 }
             }
+            if constexpr (EPI == kEpiStage) {
+                // Staged route: the warp's unit is one store row block — 32 voxels x `store_cols` (32 or 64) channels of ONE
+                // output parity = rows of 64 or 128 bytes (whole lines when the layer has >= 64 output channels), written
+                // by one TMA tensor store.  The two warps of a quadrant take alternate units.
+                const int wide = a.store_cols >> 5;  // 32-column chunks per unit
+                const int nunits = nchunk / wide;
+#pragma unroll 1
+                for (int u = half; u < nunits; u += 2) {
+                    const int col0 = q0 + u * a.store_cols;  // first GEMM column of the unit
+                    int upar = 0, co0 = col0;
+                    if (a.out_mul == 2) {
+                        upar = col0 / a.cout_pad;
+                        co0 = col0 - upar * a.cout_pad;
+                    }
+                    // the buffer about to be overwritten was handed to the store before last: at most one (the other
+                    // buffer's) may still be reading
+                    if (lane == 0) tma_store_wait_read<1>();
+                    __syncwarp();
+                    epi.stage = my_stage + (nstore & 1u) * 4096u;
+                    epi.stage_wide = wide - 1;
+#pragma unroll 1
+                    for (int sub = 0; sub < wide; ++sub) {
+                        const int j = u * wide + sub;
+                        uint32_t v[32];
+                        tmem_ld_32x32(t_addr + j * 32, v);
+                        tmem_ld_wait();
+                        StatAcc chunk_stats;
+                        chunk_stats.s1 = chunk_stats.s2 = 0.f;
+                        epi.stage_sub = sub;
+                        epilogue_32cols<false, EPI>(v, epi, co0 + sub * 32, valid, lane, chunk_stats, orow, unused1, unused2, guard);
+                        if (grouped) {
+                            stats_chunk_grouped(t_addr + j * 32, sbias, a.bias != nullptr, a.stats, a.cout, a.No, co0 + sub * 32,
+                                                valid, lane, vox_per_item, t.n0 + (q * 32) / vox_per_item);
+                        } else if (a.stats != nullptr) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k)
+                                if (k == j) {
+                                    sacc[k].s1 += chunk_stats.s1;
+                                    sacc[k].s2 += chunk_stats.s2;
+                                }
+                        }
+                    }
+                    fence_proxy_async();  // every lane's staging writes -> visible to the async proxy
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_5d(&a.mapO[upar], epi.stage, co0, t.w0, t.h0 + sub_h, t.d0 + sub_d, t.n0 + sub_n);
+                        tma_store_commit();
+                    }
+                    ++nstore;
+                }
+            } else
 #pragma unroll 1
             for (int j = half; j < nchunk; j += 2) {
                 const int cb = j * 32;
@@ -398,13 +450,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 tmem_ld_32x32(t_addr + cb, v);
                 tmem_ld_wait();
                 int co = q0 + cb;
-                int chunk_par = 0;  // tma_out: which output-parity view this chunk is stored through
                 if (a.out_mul == 2) {
                     // transposed conv: GEMM columns enumerate (parity (pd, ph, pw), channel); an N tile may span
                     // several parities, so the output voxel is re-derived per 32-column chunk (no division: the
                     // parity / channel pair is advanced chunk by chunk)
                     co = cpar;
-                    chunk_par = par;
                     orow = obase + static_cast<long long>(2 * d + ((par >> 2) & 1)) * a.os_d +
                            static_cast<long long>(2 * h + ((par >> 1) & 1)) * a.os_h +
                            static_cast<long long>(2 * w + (par & 1)) * a.os_w;
@@ -417,23 +467,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 }
                 StatAcc chunk_stats;
                 chunk_stats.s1 = chunk_stats.s2 = 0.f;
-                if constexpr (EPI == kEpiStage) {
-                    // the buffer about to be overwritten was handed to the store before last: at most one (the other
-                    // buffer's) may still be reading
-                    if (lane == 0) tma_store_wait_read<1>();
-                    __syncwarp();
-                    epi.stage = my_stage + (nstore & 1u) * 2048u;
-                }
                 epilogue_32cols<false, EPI>(v, epi, co, valid, lane, chunk_stats, orow, unused1, unused2, guard);
-                if constexpr (EPI == kEpiStage) {
-                    fence_proxy_async();  // every lane's staging writes -> visible to the async proxy
-                    __syncwarp();
-                    if (lane == 0) {
-                        tma_store_5d(&a.mapO[chunk_par], epi.stage, co, t.w0, t.h0 + sub_h, t.d0 + sub_d, t.n0 + sub_n);
-                        tma_store_commit();
-                    }
-                    ++nstore;
-                }
                 if (grouped) {
                     stats_chunk_grouped(t_addr + cb, sbias, a.bias != nullptr, a.stats, a.cout, a.No, co, valid, lane, vox_per_item,
                                         t.n0 + (q * 32) / vox_per_item);

@@ -93,8 +93,8 @@ class UNetEngine:
         self.fuse_norm = os.environ.get("BSG_FUSE_NORM", "1") != "0" and not self.split
         self.fused_norms = 0
         self.try_kwpack = os.environ.get("BSG_KWPACK", "1") != "0" and not self.split
-        # tile-kernel epilogue through shared memory + TMA tensor stores: 1 = every tile-kernel layer (measurement switch;
-        # measured slower than the direct per-thread stores, see conv_plan.cu), default off
+        # tile-kernel epilogue through shared memory + TMA tensor stores (measurement switch): 0 = planner's choice, 1 = every
+        # tile-kernel layer, 2 = none, 3 = the transposed convs only
         self.tma_store = int(os.environ.get("BSG_TMA_STORE", "0"))
         self.kwpack = False  # the first conv reads the kw-packed input layout (set by _add_block when its plan took it)
         self.flops_algo = 0.0    # algorithmic FLOPs on the real channel counts (the 4 input channels are padded to 16)
@@ -175,7 +175,7 @@ class UNetEngine:
         wp, bp, gamma, beta = self._pack_block(blk, cin_pad, kwpack, src.parts)
         if act == L.BSG_ACT_NONE:
             stats = self._carve_stats(cout)
-        desc = dict(out_split_stride=cout if self.split else 0, tma_store=self.tma_store,
+        desc = dict(out_split_stride=cout if self.split else 0, tma_store={1: 1, 2: 2}.get(self.tma_store, 0),
                     kind=L.BSG_CONV_K3, stride=stride, N=self.batch, D=d, H=h, W=wd, cin=cin_pad,
                     in_ptr=src.ptr(), in_ctot=src.ctot, cout=cout, out_ptr=dst.buf.data_ptr(),
                     out_ctot=dst.ctot, out_coff=dst.coff, weights=wp.data_ptr(), bias=bp.data_ptr(), act=act,
@@ -271,7 +271,7 @@ class UNetEngine:
                           out_coff=dst.coff, weights=wp.data_ptr(), bias=None, act=L.BSG_ACT_NONE, slope=0.0,
                           stats=None, out_f16=self.f16, in_f16=self.f16, use_khshift=0, max_ctas=0,
                           overflow=self._overflow_slot(), out_split_stride=w.shape[1] if self.split else 0,
-                          tma_store=self.tma_store)
+                          tma_store={1: 1, 2: 2, 3: 1}.get(self.tma_store, 0))
         self.flops += plan.info().flops
         self.flops_algo += 2.0 * 8 * w.shape[0] * w.shape[1] * d * h * wd * self.batch
         self._note(f"convT2 {src.c}->{w.shape[1]} @{'x'.join(map(str, spatial_in))}", plan)
