@@ -324,11 +324,16 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
             (d->pair == 1 || mtiles * a.n_ntiles >= 2ll * sm_count_cached()))
             a.pair = 1;
     }
-    // epilogue through shared memory + TMA tensor stores (tma_store = 1 only).  Measured on the transposed convs, whose
-    // per-thread output rows are two voxels apart (64->64 @64^3 x 4: 0.355 ms direct, 0.464 ms staged; 64->32: 0.155 /
-    // 0.196 ms): a store of 32 separate 64-byte rows costs the TMA unit more than the load/store unit, and the extra
-    // staging round trip lengthens the latency-bound TMEM -> convert -> store chain — so the planner never picks it
-    a.tma_out = d->tma_store == 1 && d->out_split_stride == 0 && d->cout % 8 == 0;
+    // Epilogue through shared memory + TMA tensor stores.  A transposed conv's output voxels are two apart, so the direct
+    // epilogue's per-thread rows are 32 separate 32-byte writes per store instruction; staged, a warp's 32 voxels leave as
+    // one tensor store of 64-channel rows = whole 128-byte lines.  Measured per 4 forwards: 64->64 @64^3 0.348 -> 0.321 ms,
+    // 128->128 @32^3 0.107 -> 0.094, 256->256 @16^3 0.043 -> 0.038; with 32-channel (64-byte, half-line) rows the staged
+    // route LOSES (64->32 @64^3: 0.160 -> 0.184 ms), as it does on the stride-1 / stride-2 convs whose direct rows are
+    // already contiguous (33 KB of staging taken from their pipeline: -7 % on model 2's forward).  So: transposed convs
+    // with >= 64-channel rows only; tma_store = 1 forces it anywhere, 2 forbids it.
+    a.store_cols = (a.cout_pad % 64 == 0 && a.ntile % 64 == 0) ? 64 : 32;
+    a.tma_out = (d->tma_store == 1 || (d->tma_store <= 0 && d->kind == BSG_CONVT_K2S2 && a.store_cols == 64)) &&
+                d->out_split_stride == 0 && d->cout % 8 == 0;
     // kh halo reuse: needs the canonical 8 x 16 x 1 x 1 box, stride 1, 27 taps and >= 3 pipeline stages
     const uint32_t budget = 227 * 1024 - 4096 - 6144 - (a.tma_out ? kTmaOutSmemBytes : 0);  // barriers + bias + alignment slack + room for co-resident CTAs
     auto stage_bytes = [&](int khs, int taps3, uint32_t* ab, uint32_t* bb) {
@@ -415,7 +420,6 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
         uint64_t dims[5] = {static_cast<uint64_t>(d->cout), static_cast<uint64_t>(a.Wo), static_cast<uint64_t>(a.Ho),
                             static_cast<uint64_t>(a.Do), static_cast<uint64_t>(a.No)};
         uint64_t str[4] = {oct * 2 * om, oct * 2 * Wo_ * om, oct * 2 * Wo_ * Ho_ * om, oct * 2 * Wo_ * Ho_ * Do_};
-        a.store_cols = (a.cout_pad % 64 == 0 && a.ntile % 64 == 0) ? 64 : 32;
         uint32_t box[5] = {static_cast<uint32_t>(a.store_cols), static_cast<uint32_t>(a.bw), static_cast<uint32_t>(sh),
                            static_cast<uint32_t>(sd), static_cast<uint32_t>(sn)};
         const __nv_bfloat16* obase = static_cast<const __nv_bfloat16*>(d->out) + d->out_coff;

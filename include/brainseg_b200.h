@@ -96,10 +96,10 @@ typedef struct bsg_conv_desc {
     int kw_taps;         /* 0 / 3: 3x3x3 kernel.  1: 3x3x1 kernel (kd, kh taps only), weights [9 taps (kd, kh)][cout_pad][cin]:
                             the network's first conv on an input whose w neighbours were packed into the channels by
                             bsg_gather_patch_tta(kwpack = 1) — 9 taps of K = 16 instead of 27.  Brick kernel only. */
-    int tma_store;       /* tile kernel epilogue: 1 = every epilogue warp stages its 32 voxels x 32 channels in shared memory
-                            and writes them with one TMA tensor store (cp.async.bulk.tensor, one 64-byte row per voxel)
-                            instead of 32 per-thread rows through the load/store unit.  Anything else: direct stores (the
-                            default: the staged route measured 25-30 % slower on the transposed convs it was built for). */
+    int tma_store;       /* tile kernel epilogue through shared memory + TMA tensor stores (each epilogue warp stages its 32
+                            voxels x 32 / 64 channels and writes them with one cp.async.bulk.tensor store).  -1 / 0: planner's
+                            choice — on for transposed convs whose store rows are whole 128-byte lines (Cout_pad % 64 == 0),
+                            where it measured 8-12 % faster than the direct per-thread rows; 1: on; 2: off. */
 } bsg_conv_desc;
 
 typedef struct bsg_conv_plan bsg_conv_plan;

@@ -178,7 +178,9 @@ def test_gather_kwpack_matches_torch_layout():
     (128, 128, 3, (4, 4, 4), 1),      # 4x4x4x2 box, odd batch (partial tile along n), N tiles of 256 = 2 parities
     (320, 320, 2, (4, 4, 4), 1),      # cout_pad 320: N tiles straddle parity boundaries
     (64, 48, 1, (6, 10, 12), 1),      # cout 48 (channels 48..63 of the second chunk clipped), partial tiles in h and w
-    (64, 64, 2, (8, 16, 16), 0),      # the direct (per-thread row) epilogue — the planner's choice — for comparison
+    (64, 64, 2, (8, 16, 16), 0),      # planner's choice (staged: 64-channel rows are whole lines)
+    (64, 64, 2, (8, 16, 16), 2),      # the direct (per-thread row) epilogue
+    (64, 32, 1, (8, 16, 16), 0),      # planner's choice (direct: 32-channel rows are half lines)
 ])
 def test_transposed_conv_tma_store(cin, cout, N, shape, tma):
     """ConvTranspose3d k2 s2 (generic_UNet.py:363-364) through the tile kernel with tma_store = 1: the epilogue stages 32
@@ -227,7 +229,7 @@ def test_tile_conv_with_forced_tma_store(cin, cout, stride, shape, stats):
     bp = P.pad_bias(b, cout).to(dev)
     Do, Ho, Wo = D // stride, H // stride, W // stride
     outs, sts = [], []
-    for tma in (1, 0):
+    for tma in (1, 2):
         out = torch.zeros(N, Do, Ho, Wo, cout, dtype=torch.float16, device=dev)
         st = torch.zeros(N, cout, 2, dtype=torch.float64, device=dev) if stats else None
         plan = L.ConvPlan(kind=L.BSG_CONV_K3, stride=stride, N=N, D=D, H=H, W=W, cin=cin, in_ptr=xb.data_ptr(), in_ctot=cin,
