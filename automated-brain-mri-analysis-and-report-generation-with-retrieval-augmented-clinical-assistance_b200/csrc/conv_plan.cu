@@ -1,6 +1,7 @@
 // Host planner for the tcgen05 conv kernel: picks the tile box / N tile / K chunk / pipeline depth for a layer,
 // encodes the TMA tensor maps once, and launches.  Exposed through the C ABI as bsg_conv_plan_*.
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 #include "bsg_common.cuh"
@@ -34,7 +35,7 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-               const uint32_t* box, int cc, bool oob_nan = false) {
+               const uint32_t* box, int cc, bool oob_nan = false, int promo_bytes = 256) {
     auto fn = get_encode_fn();
     if (fn == nullptr) return set_error(BSG_ECUDA, "cuTensorMapEncodeTiled entry point not available");
     uint32_t estr[5] = {1, 1, 1, 1, 1};
@@ -44,7 +45,11 @@ int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dim
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
                     reinterpret_cast<const cuuint64_t*>(dims), reinterpret_cast<const cuuint64_t*>(strides_bytes),
                     reinterpret_cast<const cuuint32_t*>(box), reinterpret_cast<const cuuint32_t*>(estr),
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                    promo_bytes >= 256   ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                    : promo_bytes >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                    : promo_bytes >= 64  ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                         : CU_TENSOR_MAP_L2_PROMOTION_NONE,
                     oob_nan ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA : CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return set_error(BSG_ECUDA,
@@ -392,7 +397,8 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
             uint64_t str[4] = {ct * 4, ct * 4 * d->W, ct * 4 * d->W * d->H, ct * 2 * d->W * d->H * d->D};
             uint32_t box[5] = {static_cast<uint32_t>(a.cc), static_cast<uint32_t>(a.bw), static_cast<uint32_t>(a.bh),
                                static_cast<uint32_t>(a.bd), static_cast<uint32_t>(a.bn)};
-            rc = encode_map(&a.mapA[par], base, 5, dims, str, box, a.cc);
+            static const int s2_promo = getenv("BSG_S2_PROMO") ? atoi(getenv("BSG_S2_PROMO")) : 256;  // measurement switch
+            rc = encode_map(&a.mapA[par], base, 5, dims, str, box, a.cc, false, s2_promo);
         }
     }
     if (rc == BSG_OK) {
