@@ -645,6 +645,18 @@ def run_ours(args):
                 torch.cuda.synchronize()
                 singles.append(time.perf_counter() - t0)
                 singles_nopost.append(t_seg)
+            # ... and with the post-processing fed SURVEY §8d's blobby label volume (≈225 components) instead of the
+            # random-init nets' noise (one giant component + ~1e5 single-voxel foci, 80 ms of mostly host-side glue)
+            blob0 = torch.from_numpy(np.ascontiguousarray(np.roll(gt0.numpy(), 3, axis=0))).to(dev) if rank == 0 else None
+            singles_blobby = []
+            for rep in range(3):
+                barrier()
+                t0 = time.perf_counter()
+                pend = lp.submit(case0, gt0)
+                res = lp.finish(pend, post=(rank == 0), labels=blob0)
+                res["segmentation"].cpu()
+                torch.cuda.synchronize()
+                singles_blobby.append(time.perf_counter() - t0)
             # one more single case with phase events: this rank's forwards of each model and the exchange behind them
             barrier()
             lp.trace = []
@@ -656,15 +668,17 @@ def run_ours(args):
                                   dtype=torch.float64, device=dev)
             dist.all_reduce(phases, op=dist.ReduceOp.MAX)
             lp.finish(pend, post=False)
-            tt = torch.tensor([t_lat, statistics.median(singles), statistics.median(singles_nopost)], dtype=torch.float64, device=dev)
+            tt = torch.tensor([t_lat, statistics.median(singles), statistics.median(singles_nopost),
+                               statistics.median(singles_blobby)], dtype=torch.float64, device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            t_lat, t_single_lat, t_single_seg = tt.tolist()
+            t_lat, t_single_lat, t_single_seg, t_single_blobby = tt.tolist()
             res = lp.finish(lp.submit(case0, gt0), post=False)
             same = None
             if ref_labels is not None:
                 same = float((res["segmentation"] == ref_labels).float().mean().item())
             records[route] = {"ms_per_case": t_lat / args.steps * 1e3, "cases_per_s": args.steps / t_lat,
                               "single_case_ms": t_single_lat * 1e3, "single_case_ms_without_post": t_single_seg * 1e3,
+                              "single_case_ms_blobby_post": t_single_blobby * 1e3,
                               "gpu_launches": int(lat_launches), "forwards_in_flight": lat_batch,
                               "single_case_phases_ms_max_over_ranks": {
                                   "model1_forwards": phases[0].item(), "model1_exchange_after_forwards": phases[1].item(),
@@ -675,7 +689,8 @@ def run_ours(args):
                               "exchange_bytes_per_case": int((sh.peer_bytes + sh.nccl_bytes) / max(1, sh.launches) * 2),
                               "labels_equal_to_1gpu": same, "label_sha256_16": sha16(res["segmentation"])}
             log(f"latency mode [{route}]: {t_lat / args.steps * 1e3:.1f} ms per case pipelined, single case "
-                f"{t_single_lat * 1e3:.1f} ms ({t_single_seg * 1e3:.1f} ms to the label volumes); labels equal to 1-GPU: {same}")
+                f"{t_single_lat * 1e3:.1f} ms ({t_single_seg * 1e3:.1f} ms to the label volumes, {t_single_blobby * 1e3:.1f} ms with "
+                f"post-processing on blobby labels); labels equal to 1-GPU: {same}")
             if sharded_only and route == routes[0]:
                 out, t_res, t_e2e, t_single, launches = lout, t_lat, t_lat, t_single_lat, lat_launches
                 if out is None:  # rank 0 did not own the last case: any owned result serves the line
