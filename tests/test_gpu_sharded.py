@@ -110,6 +110,36 @@ def test_finalize_peer_signal_orders_the_ranks_in_the_kernel():
         assert all(int(f[2 * R + 1]) == 0 for f in flags), "an in-kernel wait timed out"
 
 
+@pytest.mark.timeout(120)
+def test_finalize_peer_signal_gives_up_on_a_missing_rank():
+    """A rank that never launches its exchange kernel must not wedge the others: the in-kernel waits are bounded (10 s
+    each) and leave a code in word 2R + 1 of the waiting rank's flag block — here 0x100 + 1 (rank 1's slab never
+    landed; the earlier code 1 + 1, rank 1 never announced, is overwritten by it)."""
+    from brainseg_b200 import _lib as L
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    R, ncls, nvox = 2, 3, 4 * 256
+    accs = [torch.rand(ncls, nvox, device=dev) for _ in range(R)]
+    wsum = torch.full((nvox,), float(R), device=dev)
+    segs = [torch.zeros(nvox, dtype=torch.uint8, device=dev) for _ in range(R)]
+    flags = [torch.zeros(2 * R + 2, dtype=torch.int32, device=dev) for _ in range(R)]
+    table = torch.tensor([a.data_ptr() for a in accs], dtype=torch.int64, device=dev)
+    seg_table = torch.tensor([s.data_ptr() for s in segs], dtype=torch.int64, device=dev)
+    flag_table = torch.tensor([f.data_ptr() for f in flags], dtype=torch.int64, device=dev)
+    order = (C.c_int * ncls)(1, 2, 3)
+    import time
+    t0 = time.perf_counter()
+    L.check(L.lib().bsg_finalize_peer_signal(_ptr(table), 1, R, _ptr(wsum), ncls, nvox, 0, nvox // 2, 1, order,
+                                             _ptr(seg_table), R, _ptr(flag_table), 0, 1, L.stream_ptr()))
+    torch.cuda.synchronize()
+    took = time.perf_counter() - t0
+    code = int(flags[0][2 * R + 1])
+    print(f"kernel gave up after {took:.1f} s with status 0x{code:x}")
+    assert 15.0 < took < 40.0
+    assert code == 0x100 + 1
+    assert int(flags[1][0]) == 1 and int(flags[1][R + 0]) == 1  # rank 0 did announce and did report its slab to rank 1
+
+
 def test_nccl_route_single_rank_communicator():
     """bsg_nccl_unique_id / comm_create / reduce_accumulator / comm_destroy on a one-rank communicator: the library
     resolves libnccl at run time and the all-reduce of one rank leaves the accumulator unchanged."""
