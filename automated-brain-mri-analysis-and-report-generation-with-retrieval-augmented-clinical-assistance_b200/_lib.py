@@ -27,7 +27,7 @@ class ConvDesc(C.Structure):
         ("act", C.c_int), ("slope", C.c_float), ("stats", C.c_void_p), ("out_f16", C.c_int),
         ("use_khshift", C.c_int), ("max_ctas", C.c_int), ("in_f16", C.c_int), ("algo", C.c_int), ("pair", C.c_int),
         ("overflow", C.c_void_p), ("in_norm", C.c_void_p), ("in_norm_c", C.c_int), ("in_norm_cc", C.c_int),
-        ("out_split_stride", C.c_int), ("kw_taps", C.c_int), ("tma_store", C.c_int),
+        ("out_split_stride", C.c_int), ("kw_taps", C.c_int), ("tma_store", C.c_int), ("mblock", C.c_int),
     ]
 
 

@@ -314,8 +314,23 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
         a.ntile = a.cout_pad * m;
         a.n_ntiles = 8 / m;
     }
+    // M blocking: a work item = two M tiles (planes d0, d0 + 1 of one activation box) against ONE weight stage — two
+    // accumulators x two buffers fill the 512 TMEM columns.  Halves the weight bytes per MMA cycle through L2 and shared
+    // memory.  Evidence (profiles/r02_conv_tile_stride2_full.md): the stride-2 convs with >= 64 input channels run one-tap
+    // stages of 16 KB activations + 16 KB weights per 256 MMA cycles; six of them in flight against ~2500 cycles of TMA
+    // latency under load supply 75 B/clk where full rate needs 128 — tensor pipe 53-55 %.
+    a.mb = 1;
+    {
+        const long long mtiles = static_cast<long long>(a.tw) * a.th * a.td * a.tn;
+        const bool can = d->kind == BSG_CONV_K3 && a.bw == 8 && a.bd == 1 && a.bn == 1 && a.ntile <= 128 && a.Do % 2 == 0;
+        const bool want = d->mblock == 1 || (d->mblock <= 0 && stride == 2 && mtiles * a.n_ntiles >= 4ll * sm_count_cached());
+        if (can && want) {
+            a.mb = 2;
+            a.td = ceil_div(a.Do, 2);
+        }
+    }
     a.tmem_cols = 32;
-    while (a.tmem_cols < static_cast<uint32_t>(2 * a.ntile)) a.tmem_cols *= 2;
+    while (a.tmem_cols < static_cast<uint32_t>(2 * a.ntile * a.mb)) a.tmem_cols *= 2;
 
     // pair mode: 2-CTA clusters share every weight stage (each CTA fetches half of the N rows and multicasts them), which
     // halves the L2 -> SM weight traffic of the layers that re-read their weights once per 128-voxel tile
@@ -324,7 +339,7 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
         const long long mtiles = static_cast<long long>(a.tw) * a.th * a.td * a.tn;
         // measured (gpurun_out/bringup16.log): +3 % on the stride-1 layers with N >= 128, nothing on the stride-2 layers
         // (they are bound by the per-stage issue overhead of their 1-tap stages, not by weight traffic)
-        const bool wanted = d->pair == 1 || (d->pair != 0 && a.ntile >= 128 && stride == 1);
+        const bool wanted = d->pair == 1 || (d->pair != 0 && a.ntile >= 128 && stride == 1 && a.mb == 1);
         if (wanted && d->kind != BSG_CONVT_K2S2 && a.ntile % 16 == 0 && mtiles % 2 == 0 &&
             (d->pair == 1 || mtiles * a.n_ntiles >= 2ll * sm_count_cached()))
             a.pair = 1;
@@ -342,7 +357,7 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
     // kh halo reuse: needs the canonical 8 x 16 x 1 x 1 box, stride 1, 27 taps and >= 3 pipeline stages
     const uint32_t budget = 227 * 1024 - 4096 - 6144 - (a.tma_out ? kTmaOutSmemBytes : 0);  // barriers + bias + alignment slack + room for co-resident CTAs
     auto stage_bytes = [&](int khs, int taps3, uint32_t* ab, uint32_t* bb) {
-        const uint32_t rows = khs ? static_cast<uint32_t>((a.bh + 2) * 8) : 128u;
+        const uint32_t rows = (khs ? static_cast<uint32_t>((a.bh + 2) * 8) : 128u) * static_cast<uint32_t>(a.mb);
         *ab = round_up(rows * a.cc * 2, 1024) * (taps3 ? 3 : 1);
         *bb = round_up(static_cast<uint32_t>(a.ntile) * a.cc * 2 * ((khs || taps3) ? 3 : 1), 1024);
         return *ab + *bb;
@@ -351,7 +366,7 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
     if (a.ntaps == 27 && stride == 1 && a.bw == 8 && a.bd == 1 && a.bn == 1 && d->use_khshift != 0) {
         uint32_t ab, bb;
         const uint32_t sb = stage_bytes(1, 0, &ab, &bb);
-        if (budget / sb >= 3 || d->use_khshift == 1) khs = 1;
+        if (budget / sb >= 3 || d->use_khshift == 1 || (a.mb == 2 && budget / sb >= 2)) khs = 1;
         if (budget / sb < 2) khs = 0;
     }
     a.khshift = khs;
@@ -364,7 +379,7 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
     }
     a.taps3 = taps3;
     const uint32_t sb = stage_bytes(khs, taps3, &a.a_stage_bytes, &a.b_stage_bytes);
-    a.stage_tx_bytes = (khs ? static_cast<uint32_t>((a.bh + 2) * 8) : 128u) * a.cc * 2 * (taps3 ? 3 : 1) +
+    a.stage_tx_bytes = (khs ? static_cast<uint32_t>((a.bh + 2) * 8) : 128u) * a.mb * a.cc * 2 * (taps3 ? 3 : 1) +
                        static_cast<uint32_t>(a.ntile) * a.cc * 2 * ((khs || taps3) ? 3 : 1);
     a.nstages = static_cast<int>(budget / sb);
     if (a.nstages > 12) a.nstages = 12;
@@ -382,7 +397,7 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
                             static_cast<uint64_t>(d->D), static_cast<uint64_t>(d->N)};
         uint64_t str[4] = {ct * 2, ct * 2 * d->W, ct * 2 * d->W * d->H, ct * 2 * d->W * d->H * d->D};
         uint32_t box[5] = {static_cast<uint32_t>(a.cc), static_cast<uint32_t>(a.bw),
-                           static_cast<uint32_t>(a.bh + (khs ? 2 : 0)), static_cast<uint32_t>(a.bd),
+                           static_cast<uint32_t>(a.bh + (khs ? 2 : 0)), static_cast<uint32_t>(a.bd * a.mb),
                            static_cast<uint32_t>(a.bn)};
         rc = encode_map(&a.mapA[0], in, 5, dims, str, box, a.cc);
     } else {
@@ -396,7 +411,7 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
                                 static_cast<uint64_t>(d->N)};
             uint64_t str[4] = {ct * 4, ct * 4 * d->W, ct * 4 * d->W * d->H, ct * 2 * d->W * d->H * d->D};
             uint32_t box[5] = {static_cast<uint32_t>(a.cc), static_cast<uint32_t>(a.bw), static_cast<uint32_t>(a.bh),
-                               static_cast<uint32_t>(a.bd), static_cast<uint32_t>(a.bn)};
+                               static_cast<uint32_t>(a.bd * a.mb), static_cast<uint32_t>(a.bn)};
             static const int s2_promo = getenv("BSG_S2_PROMO") ? atoi(getenv("BSG_S2_PROMO")) : 256;  // measurement switch
             rc = encode_map(&a.mapA[par], base, 5, dims, str, box, a.cc, false, s2_promo);
         }

@@ -21,6 +21,8 @@ struct ConvArgs {
     int pair;             // 1: launched as 2-CTA clusters; the two CTAs work on neighbouring M tiles of the same N tile
                           //    in lock-step, each fetches half of every weight stage and multicasts it to both
     int bw, bh, bd, bn;   // output tile box, bw*bh*bd*bn == 128
+    int mb;               // M blocking: M tiles (adjacent planes) per work item and weight stage, 1 or 2 (2 needs bd == bn == 1,
+                          // ntile <= 128: two accumulators x two buffers fill the 512 TMEM columns)
     int tw, th, td, tn;   // tile counts per dimension
     int n_ntiles, ntile;  // N tiling (ntile % 32 == 0, ntile <= 256)
     int Wo, Ho, Do, No;   // extents of the tile coordinate space

@@ -38,7 +38,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvArgs& a, int tile) {
     s /= a.td;
     t.w0 = iw * a.bw;
     t.h0 = ih * a.bh;
-    t.d0 = id * a.bd;
+    t.d0 = id * a.bd * a.mb;  // mb = 2: a work item is two M tiles, adjacent planes d0 and d0 + 1 (bd == 1 then)
     t.n0 = s * a.bn;
     return t;
 }
@@ -265,6 +265,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             // distance between the A operands of consecutive kh taps inside a stage: one row group of the haloed box
             // (KHS) or one whole 128-row box (three boxes per stage)
             const uint32_t a_kh16 = X3 ? (a.a_stage_bytes / 3) >> 4 : kSbo >> 4;
+            // M blocking: plane d0 + 1 follows plane d0 inside every activation box ((bh [+ 2]) x bw rows further)
+            const uint32_t a_m16 = (static_cast<uint32_t>((a.bh + (KHS ? 2 : 0)) * a.bw) * kRowBytes) >> 4;
             int stage = 0;
             uint32_t phase = 0;
             uint32_t tcount = 0;
@@ -274,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 const uint32_t acc_phase = (tcount >> 1) & 1u;
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * static_cast<uint32_t>(a.ntile);
+                const uint32_t d_tmem = tmem_base + acc * static_cast<uint32_t>(a.ntile * a.mb);
                 for (int ks = 0; ks < ksteps; ++ks) {
                     if (!ready) mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
@@ -289,6 +291,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                             const uint32_t ad = sa16 + kh * a_kh16 + ((k * 32) >> 4);
                             const uint32_t bd = sb16 + kh * b_tap16 + ((k * 32) >> 4);
                             umma_bf16_lo(d_tmem, ad, bd, desc_hi, idesc, (kh | k) != 0 ? 1u : (ks != 0 ? 1u : 0u));
+                            // M blocking: the second M tile (the next plane of the same activation box) against the
+                            // SAME weight operand — half the weight bytes per MMA cycle through shared memory and L2
+                            if (a.mb == 2)
+                                umma_bf16_lo(d_tmem + static_cast<uint32_t>(a.ntile), ad + a_m16, bd, desc_hi, idesc,
+                                             (kh | k) != 0 ? 1u : (ks != 0 ? 1u : 0u));
                             // probe the next stage's barrier behind the first MMA: its latency overlaps queued work
                             if (kh == 0 && k == 0) ready = mbar_try_wait(&full_bar[nstage], nphase);
                         }
@@ -357,7 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const TileCoord t = decode_tile(a, tile_of(item));
             const uint32_t acc = tcount & 1u;
             const uint32_t acc_phase = (tcount >> 1) & 1u;
-            const int w = t.w0 + iw, h = t.h0 + ih, d = t.d0 + id, n = t.n0 + in;
+            const int w = t.w0 + iw, h = t.h0 + ih, n = t.n0 + in;
             if (a.stats != nullptr && !grouped) {
                 const int n_warp = __shfl_sync(0xffffffffu, n, 0);
                 if (n_warp != stat_n || t.nt != stat_nt) {
@@ -367,15 +374,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     stat_nt = t.nt;
                 }
             }
-            const bool valid = (w < a.Wo) && (h < a.Ho) && (d < a.Do) && (n < a.No);
             const int q0 = t.nt * a.ntile;  // first GEMM column of this tile
             __nv_bfloat16* obase = a.out + n * a.os_n + a.out_c_off;
-            __nv_bfloat16* orow = obase + static_cast<long long>(d) * a.os_d + static_cast<long long>(h) * a.os_h +
-                                  static_cast<long long>(w) * a.os_w;
-
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const uint32_t t_addr = tmem_base + acc * static_cast<uint32_t>(a.ntile) + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+            for (int mt = 0; mt < a.mb; ++mt) {  // the item's M tiles (M blocking: planes d0 and d0 + 1)
+            const int d = t.d0 + id + mt;
+            const bool valid = (w < a.Wo) && (h < a.Ho) && (d < a.Do) && (n < a.No);
+            __nv_bfloat16* orow = obase + static_cast<long long>(d) * a.os_d + static_cast<long long>(h) * a.os_h +
+                                  static_cast<long long>(w) * a.os_w;
+            const uint32_t t_addr = tmem_base + (acc * static_cast<uint32_t>(a.mb) + static_cast<uint32_t>(mt)) * static_cast<uint32_t>(a.ntile) +
+                                    (static_cast<uint32_t>(q * 32) << 16);
             // This warp's chunks: half, half + 2, ...  ONE copy of the chunk body in the instruction stream (a runtime
             // loop): unrolled over the 8 chunk positions it was ~110 KB of SASS per warp flavour and the epilogue
             // warps spent a quarter of their time waiting for instruction fetches (ncu: stall_no_inst, transposed conv).
@@ -437,7 +447,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     fence_proxy_async();  // every lane's staging writes -> visible to the async proxy
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_5d(&a.mapO[upar], epi.stage, co0, t.w0, t.h0 + sub_h, t.d0 + sub_d, t.n0 + sub_n);
+                        tma_store_5d(&a.mapO[upar], epi.stage, co0, t.w0, t.h0 + sub_h, t.d0 + sub_d + mt, t.n0 + sub_n);
                         tma_store_commit();
                     }
                     ++nstore;
@@ -480,6 +490,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                         }
                 }
             }
+            }  // mt
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);

@@ -96,6 +96,7 @@ class UNetEngine:
         # tile-kernel epilogue through shared memory + TMA tensor stores (measurement switch): 0 = planner's choice, 1 = every
         # tile-kernel layer, 2 = none, 3 = the transposed convs only
         self.tma_store = int(os.environ.get("BSG_TMA_STORE", "0"))
+        self.mblock = int(os.environ.get("BSG_MBLOCK", "0"))  # tile-kernel M blocking: 0 planner's choice, 1 wherever possible, 2 off
         self.kwpack = False  # the first conv reads the kw-packed input layout (set by _add_block when its plan took it)
         self.flops_algo = 0.0    # algorithmic FLOPs on the real channel counts (the 4 input channels are padded to 16)
         self.act_dtype = torch.float16 if self.f16 else torch.bfloat16
@@ -176,6 +177,7 @@ class UNetEngine:
         if act == L.BSG_ACT_NONE:
             stats = self._carve_stats(cout)
         desc = dict(out_split_stride=cout if self.split else 0, tma_store={1: 1, 2: 2}.get(self.tma_store, 0),
+                    mblock=self.mblock,
                     kind=L.BSG_CONV_K3, stride=stride, N=self.batch, D=d, H=h, W=wd, cin=cin_pad,
                     in_ptr=src.ptr(), in_ctot=src.ctot, cout=cout, out_ptr=dst.buf.data_ptr(),
                     out_ctot=dst.ctot, out_coff=dst.coff, weights=wp.data_ptr(), bias=bp.data_ptr(), act=act,
