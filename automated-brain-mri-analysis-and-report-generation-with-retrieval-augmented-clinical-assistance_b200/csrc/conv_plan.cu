@@ -322,7 +322,8 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
     a.mb = 1;
     {
         const long long mtiles = static_cast<long long>(a.tw) * a.th * a.td * a.tn;
-        const bool can = d->kind == BSG_CONV_K3 && a.bw == 8 && a.bd == 1 && a.bn == 1 && a.ntile <= 128 && a.Do % 2 == 0;
+        const bool can = d->kind == BSG_CONV_K3 && a.bw == 8 && a.bd == 1 && a.bn == 1 && a.ntile <= 128 && a.Do % 2 == 0 &&
+                         d->out_split_stride == 0 && d->tma_store != 1;  // direct 16-bit epilogue only
         const bool want = d->mblock == 1 || (d->mblock <= 0 && stride == 2 && mtiles * a.n_ntiles >= 4ll * sm_count_cached());
         if (can && want) {
             a.mb = 2;
@@ -528,7 +529,7 @@ int bsg_conv_plan_info(const bsg_conv_plan* plan, bsg_conv_info* info) {
     info->n_ntiles = a.n_ntiles;
     info->cc = a.cc;
     info->nstages = a.nstages;
-    info->khshift = a.khshift + (a.taps3 ? 3 : 0) + (a.pair ? 100 : 0);  /* 1: kh halo reuse, 3: three kh taps per stage, +100: 2-CTA pair mode */
+    info->khshift = a.khshift + (a.taps3 ? 3 : 0) + (a.mb == 2 ? 10 : 0) + (a.pair ? 100 : 0);  /* 1: kh halo reuse, 3: three kh taps per stage, +10: M blocking, +100: 2-CTA pair mode */
     info->grid = plan->grid;
     info->smem_bytes = plan->smem_bytes;
     info->flops = plan->flops;

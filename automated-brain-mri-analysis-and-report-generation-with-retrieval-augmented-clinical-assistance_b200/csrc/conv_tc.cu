@@ -11,6 +11,7 @@ size_t conv_tc_smem_bytes(const ConvArgs& a) {
 cudaError_t launch_conv_tc(const ConvArgs& a, int grid, size_t smem_bytes, cudaStream_t stream) {
     if (a.split_stride != 0) return launch_conv_tc_split(a, grid, smem_bytes, stream);
     if (a.tma_out) return launch_conv_tc_tma(a, grid, smem_bytes, stream);
+    if (a.mb == 2) return launch_conv_tc_mb(a, grid, smem_bytes, stream);
     return launch_modes<kEpiDirect>(a, grid, smem_bytes, stream);
 }
 

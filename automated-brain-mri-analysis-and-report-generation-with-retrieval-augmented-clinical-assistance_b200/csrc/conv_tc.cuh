@@ -56,6 +56,7 @@ struct ConvArgs {
 constexpr unsigned kTmaOutSmemBytes = 8 * 2 * 4096 + 1024;  // two staging buffers per epilogue warp + alignment
 cudaError_t launch_conv_tc(const ConvArgs& a, int grid, size_t smem_bytes, cudaStream_t stream);  // pair: grid even
 cudaError_t launch_conv_tc_tma(const ConvArgs& a, int grid, size_t smem_bytes, cudaStream_t stream);
+cudaError_t launch_conv_tc_mb(const ConvArgs& a, int grid, size_t smem_bytes, cudaStream_t stream);
 cudaError_t launch_conv_tc_split(const ConvArgs& a, int grid, size_t smem_bytes, cudaStream_t stream);
 size_t conv_tc_smem_bytes(const ConvArgs& a);
 

@@ -53,7 +53,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvArgs& a, int tile) {
 // one 3-tap weight box): the layers whose one-tap stages are bound by the per-stage round trip rather than by MMA time
 // (stride-2 32->64, the <= 8^3 levels) run a third of the stages.
 constexpr int kModeGeneric = 0, kModeKhs = 1, kModeS2 = 2, kModeS1 = 3, kModeS2x3 = 4, kModeS1x3 = 5;
-template <int CC, int MODE, int EPI>
+template <int CC, int MODE, int EPI, int MB>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvArgs a) {
     constexpr bool KHS = MODE == kModeKhs;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 const uint32_t acc_phase = (tcount >> 1) & 1u;
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * static_cast<uint32_t>(a.ntile * a.mb);
+                const uint32_t d_tmem = tmem_base + acc * static_cast<uint32_t>(a.ntile * MB);
                 for (int ks = 0; ks < ksteps; ++ks) {
                     if (!ready) mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                             umma_bf16_lo(d_tmem, ad, bd, desc_hi, idesc, (kh | k) != 0 ? 1u : (ks != 0 ? 1u : 0u));
                             // M blocking: the second M tile (the next plane of the same activation box) against the
                             // SAME weight operand — half the weight bytes per MMA cycle through shared memory and L2
-                            if (a.mb == 2)
+                            if constexpr (MB == 2)
                                 umma_bf16_lo(d_tmem + static_cast<uint32_t>(a.ntile), ad + a_m16, bd, desc_hi, idesc,
                                              (kh | k) != 0 ? 1u : (ks != 0 ? 1u : 0u));
                             // probe the next stage's barrier behind the first MMA: its latency overlaps queued work
@@ -379,12 +379,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
 #pragma unroll 1
-            for (int mt = 0; mt < a.mb; ++mt) {  // the item's M tiles (M blocking: planes d0 and d0 + 1)
+            for (int mt = 0; mt < MB; ++mt) {  // the item's M tiles (M blocking: planes d0 and d0 + 1)
             const int d = t.d0 + id + mt;
             const bool valid = (w < a.Wo) && (h < a.Ho) && (d < a.Do) && (n < a.No);
             __nv_bfloat16* orow = obase + static_cast<long long>(d) * a.os_d + static_cast<long long>(h) * a.os_h +
                                   static_cast<long long>(w) * a.os_w;
-            const uint32_t t_addr = tmem_base + (acc * static_cast<uint32_t>(a.mb) + static_cast<uint32_t>(mt)) * static_cast<uint32_t>(a.ntile) +
+            const uint32_t t_addr = tmem_base + (acc * static_cast<uint32_t>(MB) + static_cast<uint32_t>(mt)) * static_cast<uint32_t>(a.ntile) +
                                     (static_cast<uint32_t>(q * 32) << 16);
             // This warp's chunks: half, half + 2, ...  ONE copy of the chunk body in the instruction stream (a runtime
             // loop): unrolled over the 8 chunk positions it was ~110 KB of SASS per warp flavour and the epilogue
@@ -512,10 +512,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
 }
 
-template <int CC, int MODE, int EPI>
+template <int CC, int MODE, int EPI, int MB>
 static cudaError_t launch_variant(const ConvArgs& a, int grid, size_t smem_bytes, cudaStream_t stream) {
     static unsigned long long attr_done = 0;  // per device
-    if (cudaError_t e = ensure_max_smem(conv_tc_kernel<CC, MODE, EPI>, &attr_done, 232448); e != cudaSuccess) return e;
+    if (cudaError_t e = ensure_max_smem(conv_tc_kernel<CC, MODE, EPI, MB>, &attr_done, 232448); e != cudaSuccess) return e;
     if (a.pair) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(static_cast<unsigned>(grid));
@@ -529,42 +529,47 @@ static cudaError_t launch_variant(const ConvArgs& a, int grid, size_t smem_bytes
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, conv_tc_kernel<CC, MODE, EPI>, a);
+        return cudaLaunchKernelEx(&cfg, conv_tc_kernel<CC, MODE, EPI, MB>, a);
     }
-    conv_tc_kernel<CC, MODE, EPI><<<grid, kThreads, smem_bytes, stream>>>(a);
+    conv_tc_kernel<CC, MODE, EPI, MB><<<grid, kThreads, smem_bytes, stream>>>(a);
     return cudaGetLastError();
 }
 
-template <int EPI>
+// MB = 2 (M blocking) exists for the tap-table modes only: the planner never pairs it with the generic mode.
+template <int EPI, int MB = 1>
 static cudaError_t launch_modes(const ConvArgs& a, int grid, size_t smem_bytes, cudaStream_t stream) {
     if (a.khshift) {
-        if (a.cc == 64) return launch_variant<64, kModeKhs, EPI>(a, grid, smem_bytes, stream);
-        if (a.cc == 32) return launch_variant<32, kModeKhs, EPI>(a, grid, smem_bytes, stream);
-        return launch_variant<16, kModeKhs, EPI>(a, grid, smem_bytes, stream);
+        if (a.cc == 64) return launch_variant<64, kModeKhs, EPI, MB>(a, grid, smem_bytes, stream);
+        if (a.cc == 32) return launch_variant<32, kModeKhs, EPI, MB>(a, grid, smem_bytes, stream);
+        return launch_variant<16, kModeKhs, EPI, MB>(a, grid, smem_bytes, stream);
     }
     if (a.taps3 && a.ntaps == 27 && !a.pair) {
         if (a.stride == 2) {
-            if (a.cc == 64) return launch_variant<64, kModeS2x3, EPI>(a, grid, smem_bytes, stream);
-            if (a.cc == 32) return launch_variant<32, kModeS2x3, EPI>(a, grid, smem_bytes, stream);
-            return launch_variant<16, kModeS2x3, EPI>(a, grid, smem_bytes, stream);
+            if (a.cc == 64) return launch_variant<64, kModeS2x3, EPI, MB>(a, grid, smem_bytes, stream);
+            if (a.cc == 32) return launch_variant<32, kModeS2x3, EPI, MB>(a, grid, smem_bytes, stream);
+            return launch_variant<16, kModeS2x3, EPI, MB>(a, grid, smem_bytes, stream);
         }
-        if (a.cc == 64) return launch_variant<64, kModeS1x3, EPI>(a, grid, smem_bytes, stream);
-        if (a.cc == 32) return launch_variant<32, kModeS1x3, EPI>(a, grid, smem_bytes, stream);
-        return launch_variant<16, kModeS1x3, EPI>(a, grid, smem_bytes, stream);
+        if (a.cc == 64) return launch_variant<64, kModeS1x3, EPI, MB>(a, grid, smem_bytes, stream);
+        if (a.cc == 32) return launch_variant<32, kModeS1x3, EPI, MB>(a, grid, smem_bytes, stream);
+        return launch_variant<16, kModeS1x3, EPI, MB>(a, grid, smem_bytes, stream);
     }
     if (a.stride == 2 && a.ntaps == 27) {
-        if (a.cc == 64) return launch_variant<64, kModeS2, EPI>(a, grid, smem_bytes, stream);
-        if (a.cc == 32) return launch_variant<32, kModeS2, EPI>(a, grid, smem_bytes, stream);
-        return launch_variant<16, kModeS2, EPI>(a, grid, smem_bytes, stream);
+        if (a.cc == 64) return launch_variant<64, kModeS2, EPI, MB>(a, grid, smem_bytes, stream);
+        if (a.cc == 32) return launch_variant<32, kModeS2, EPI, MB>(a, grid, smem_bytes, stream);
+        return launch_variant<16, kModeS2, EPI, MB>(a, grid, smem_bytes, stream);
     }
     if (a.stride == 1 && a.ntaps == 27) {
-        if (a.cc == 64) return launch_variant<64, kModeS1, EPI>(a, grid, smem_bytes, stream);
-        if (a.cc == 32) return launch_variant<32, kModeS1, EPI>(a, grid, smem_bytes, stream);
-        return launch_variant<16, kModeS1, EPI>(a, grid, smem_bytes, stream);
+        if (a.cc == 64) return launch_variant<64, kModeS1, EPI, MB>(a, grid, smem_bytes, stream);
+        if (a.cc == 32) return launch_variant<32, kModeS1, EPI, MB>(a, grid, smem_bytes, stream);
+        return launch_variant<16, kModeS1, EPI, MB>(a, grid, smem_bytes, stream);
     }
-    if (a.cc == 64) return launch_variant<64, kModeGeneric, EPI>(a, grid, smem_bytes, stream);
-    if (a.cc == 32) return launch_variant<32, kModeGeneric, EPI>(a, grid, smem_bytes, stream);
-    return launch_variant<16, kModeGeneric, EPI>(a, grid, smem_bytes, stream);
+    if constexpr (MB == 2) {
+        return cudaErrorInvalidConfiguration;
+    } else {
+        if (a.cc == 64) return launch_variant<64, kModeGeneric, EPI, MB>(a, grid, smem_bytes, stream);
+        if (a.cc == 32) return launch_variant<32, kModeGeneric, EPI, MB>(a, grid, smem_bytes, stream);
+        return launch_variant<16, kModeGeneric, EPI, MB>(a, grid, smem_bytes, stream);
+    }
 }
 
 }  // namespace

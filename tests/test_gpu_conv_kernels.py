@@ -250,3 +250,54 @@ def test_tile_conv_with_forced_tma_store(cin, cout, stride, shape, stats):
     assert (outs[0].float() - outs[1].float()).abs().max().item() <= 2e-3 * max(ref.abs().max().item(), 1.0)
     if stats:
         assert torch.allclose(sts[0], sts[1], rtol=1e-4, atol=1e-3)
+
+
+# ---------------------------------------------------------------------------------------------- M blocking
+@pytest.mark.parametrize("cin,cout,stride,shape,stats", [
+    (64, 128, 2, (16, 32, 32), True),    # stride 2, one-tap stages (the planner's own choice at the benchmark sizes)
+    (32, 64, 2, (16, 32, 16), False),    # stride 2, three kh taps per stage, 32-channel parity views
+    (128, 128, 1, (8, 16, 16), True),    # stride 1, haloed kh box with two planes per stage
+    (64, 96, 1, (6, 16, 24), False),     # N tile 96, planes 4 and 5 form the last pair
+    (64, 128, 2, (12, 40, 24), True),    # partial tiles in h / w next to the plane pairs (Do = 6, Ho = 20, Wo = 12)
+])
+def test_tile_conv_m_blocking(cin, cout, stride, shape, stats):
+    """mblock = 1: a work item is two M tiles (adjacent output planes) sharing every weight stage, two accumulators per
+    TMEM buffer.  Against torch's conv3d and against the unblocked plan (same tap order: equal up to nothing — the MMA
+    sequence per tile is the same, so the results are bit-identical)."""
+    L, P, dev = _setup()
+    D, H, W = shape
+    N = 2
+    g = torch.Generator(device="cpu").manual_seed(cin + cout + stride + D)
+    x = torch.randn(N, cin, D, H, W, generator=g).to(torch.float16)
+    xb = x.permute(0, 2, 3, 4, 1).contiguous().to(dev)
+    w = torch.randn(cout, cin, 3, 3, 3, generator=g) / (27 * cin) ** 0.5
+    wp = P.pack_conv3_weight(w.to(dev), cin, torch.float16)
+    b = torch.randn(cout, generator=g).to(dev)
+    bp = P.pad_bias(b, cout).to(dev)
+    Do, Ho, Wo = D // stride, H // stride, W // stride
+    outs, sts, marks = [], [], []
+    for mblock in (1, 2):
+        out = torch.zeros(N, Do, Ho, Wo, cout, dtype=torch.float16, device=dev)
+        st = torch.zeros(N, cout, 2, dtype=torch.float64, device=dev) if stats else None
+        plan = L.ConvPlan(kind=L.BSG_CONV_K3, stride=stride, N=N, D=D, H=H, W=W, cin=cin, in_ptr=xb.data_ptr(), in_ctot=cin,
+                          cout=cout, out_ptr=out.data_ptr(), out_ctot=cout, out_coff=0, weights=wp.data_ptr(),
+                          bias=bp.data_ptr(), act=0 if stats else 1, slope=0.01, stats=st.data_ptr() if stats else None,
+                          use_khshift=-1, max_ctas=0, in_f16=1, out_f16=1, algo=0, pair=0, mblock=mblock)
+        marks.append(plan.info().khshift)
+        plan.run()
+        torch.cuda.synchronize()
+        outs.append(out)
+        sts.append(st)
+    assert marks[0] % 100 >= 10 and marks[1] % 100 < 10, f"plan markers {marks}: M blocking not taken / not switched off"
+    ref = F.conv3d(x.float().to(dev), w.to(torch.float16).float().to(dev), b, stride=stride, padding=1)
+    pre = ref
+    if not stats:
+        ref = F.leaky_relu(ref, 0.01)
+    got = outs[0].permute(0, 4, 1, 2, 3).float()
+    err = (got - ref).abs().max().item()
+    print(f"M blocking {cin}->{cout} s{stride} @{D}x{H}x{W}: plan markers {marks}, max err {err:.4g}")
+    assert err <= 3e-3 * max(ref.abs().max().item(), 1.0)
+    assert (outs[0].float() - outs[1].float()).abs().max().item() <= 2e-3 * max(ref.abs().max().item(), 1.0)
+    if stats:
+        s_ref = torch.stack([pre.sum(dim=(2, 3, 4)), (pre * pre).sum(dim=(2, 3, 4))], dim=-1)
+        assert ((sts[0].float() - s_ref).abs() / (s_ref.abs() + 1.0)).max().item() < 1e-3
