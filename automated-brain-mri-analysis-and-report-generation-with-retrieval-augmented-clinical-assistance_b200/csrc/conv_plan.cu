@@ -324,7 +324,12 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
         const long long mtiles = static_cast<long long>(a.tw) * a.th * a.td * a.tn;
         const bool can = d->kind == BSG_CONV_K3 && a.bw == 8 && a.bd == 1 && a.bn == 1 && a.ntile <= 128 && a.Do % 2 == 0 &&
                          d->out_split_stride == 0 && d->tma_store != 1;  // direct 16-bit epilogue only
-        const bool want = d->mblock == 1 || (d->mblock <= 0 && stride == 2 && mtiles * a.n_ntiles >= 4ll * sm_count_cached());
+        // Measured per 4 forwards (gpurun_out/r02_layers24_*): stride 2 32->64 @128^3 0.250 -> 0.214 ms, 64->128 @128^3
+        // 0.577 -> 0.533; stride 1 (haloed kh box, two planes per stage, against the 2-CTA weight multicast it replaces)
+        // 128->128 @64^3 0.766 -> 0.717, 256->128 @64^3 1.369 -> 1.302 — but 0.087 -> 0.091 and 0.158 -> 0.165 on the
+        // @32^3 layers, whose 1024 tiles no longer balance over 148 CTAs in pairs: stride 1 only from 16 waves on.
+        const long long items = mtiles * a.n_ntiles;
+        const bool want = d->mblock == 1 || (d->mblock <= 0 && items >= (stride == 2 ? 4ll : 16ll) * sm_count_cached());
         if (can && want) {
             a.mb = 2;
             a.td = ceil_div(a.Do, 2);

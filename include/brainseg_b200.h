@@ -101,7 +101,8 @@ typedef struct bsg_conv_desc {
                             choice — on for transposed convs whose store rows are whole 128-byte lines (Cout_pad % 64 == 0),
                             where it measured 8-12 % faster than the direct per-thread rows; 1: on; 2: off. */
     int mblock;          /* tile kernel M blocking (two M tiles = adjacent planes per work item and weight stage; needs the 8 x 16
-                            tile box and an N tile <= 128): -1 / 0 planner's choice (stride-2 convs), 1 on where possible, 2 off */
+                            tile box and an N tile <= 128): -1 / 0 planner's choice (layers with enough tiles: from 4 waves of CTAs on at
+                            stride 2, from 16 on at stride 1), 1 on where possible, 2 off */
 } bsg_conv_desc;
 
 typedef struct bsg_conv_plan bsg_conv_plan;
