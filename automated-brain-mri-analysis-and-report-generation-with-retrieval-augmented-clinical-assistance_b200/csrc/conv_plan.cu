@@ -199,6 +199,9 @@ int bsg_check_device(void) {
     BSG_CUDA_OK(cudaGetDevice(&dev));
     BSG_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
     if (major != 10) return set_error(BSG_EARCH, "device compute capability %d.x is not sm_100", major);
+    if (const char* g = getenv("BSG_L2_FETCH")) {  // measurement switch: DRAM -> L2 fetch granularity hint (32 / 64 / 128 bytes)
+        BSG_CUDA_OK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, static_cast<size_t>(atoi(g))));
+    }
     return BSG_OK;
 }
 
