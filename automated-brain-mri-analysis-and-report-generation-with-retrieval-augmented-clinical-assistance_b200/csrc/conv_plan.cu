@@ -1,7 +1,6 @@
 // Host planner for the tcgen05 conv kernel: picks the tile box / N tile / K chunk / pipeline depth for a layer,
 // encodes the TMA tensor maps once, and launches.  Exposed through the C ABI as bsg_conv_plan_*.
 #include <cudaTypedefs.h>
-#include <stdlib.h>
 #include <string.h>
 #include <new>
 #include "bsg_common.cuh"
@@ -35,7 +34,7 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-               const uint32_t* box, int cc, bool oob_nan = false, int promo_bytes = 256) {
+               const uint32_t* box, int cc, bool oob_nan = false) {
     auto fn = get_encode_fn();
     if (fn == nullptr) return set_error(BSG_ECUDA, "cuTensorMapEncodeTiled entry point not available");
     uint32_t estr[5] = {1, 1, 1, 1, 1};
@@ -45,11 +44,7 @@ int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dim
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
                     reinterpret_cast<const cuuint64_t*>(dims), reinterpret_cast<const cuuint64_t*>(strides_bytes),
                     reinterpret_cast<const cuuint32_t*>(box), reinterpret_cast<const cuuint32_t*>(estr),
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                    promo_bytes >= 256   ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
-                    : promo_bytes >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
-                    : promo_bytes >= 64  ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
-                                         : CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     oob_nan ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA : CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return set_error(BSG_ECUDA,
@@ -199,9 +194,6 @@ int bsg_check_device(void) {
     BSG_CUDA_OK(cudaGetDevice(&dev));
     BSG_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
     if (major != 10) return set_error(BSG_EARCH, "device compute capability %d.x is not sm_100", major);
-    if (const char* g = getenv("BSG_L2_FETCH")) {  // measurement switch: DRAM -> L2 fetch granularity hint (32 / 64 / 128 bytes)
-        BSG_CUDA_OK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, static_cast<size_t>(atoi(g))));
-    }
     return BSG_OK;
 }
 
@@ -421,8 +413,7 @@ int bsg_conv_plan_create(const bsg_conv_desc* d, bsg_conv_plan** out_plan) {
             uint64_t str[4] = {ct * 4, ct * 4 * d->W, ct * 4 * d->W * d->H, ct * 2 * d->W * d->H * d->D};
             uint32_t box[5] = {static_cast<uint32_t>(a.cc), static_cast<uint32_t>(a.bw), static_cast<uint32_t>(a.bh),
                                static_cast<uint32_t>(a.bd * a.mb), static_cast<uint32_t>(a.bn)};
-            static const int s2_promo = getenv("BSG_S2_PROMO") ? atoi(getenv("BSG_S2_PROMO")) : 256;  // measurement switch
-            rc = encode_map(&a.mapA[par], base, 5, dims, str, box, a.cc, false, s2_promo);
+            rc = encode_map(&a.mapA[par], base, 5, dims, str, box, a.cc);
         }
     }
     if (rc == BSG_OK) {

@@ -1,4 +1,4 @@
-# round 2, call 26: DRAM -> L2 fetch granularity hint (cudaLimitMaxL2FetchGranularity 32 / 64 / 128) on the per-layer table:
+# round 2, call 26 (needs the BSG_L2_FETCH switch, removed again afterwards): DRAM -> L2 fetch granularity hint
 # does the 2x DRAM over-read of the 32-channel stride-2 conv (its input is one half of every 128-byte line of the concat
 # buffer) come from whole-line fetches?
 cd "$GRAFT_REPO_ROOT"
