@@ -426,19 +426,20 @@ __device__ __forceinline__ bool exceeds_half(float a, float w) {
 }
 
 // One voxel's decision from its class probabilities (argmax, or the ordered > 0.5 assignment of the region trainers).
-__device__ __forceinline__ int decide_label(const FinalizeParams& fp, const float (&p)[kMaxClasses]) {
+template <int MAXC>
+__device__ __forceinline__ int decide_label(const FinalizeParams& fp, const float (&p)[MAXC]) {
     int lab = 0;
     if (fp.mode == 0) {
         float best = p[0];
 #pragma unroll
-        for (int k = 1; k < kMaxClasses; ++k)
+        for (int k = 1; k < MAXC; ++k)
             if (k < fp.ncls && p[k] > best) {
                 best = p[k];
                 lab = k;
             }
     } else {
 #pragma unroll
-        for (int k = 0; k < kMaxClasses; ++k)
+        for (int k = 0; k < MAXC; ++k)
             if (k < fp.ncls && p[k] > 0.5f) lab = fp.order[k];
     }
     return lab;
@@ -447,18 +448,20 @@ __device__ __forceinline__ int decide_label(const FinalizeParams& fp, const floa
 // VEC voxels per thread and step (VEC = 4: 128-bit loads of the accumulators / weight sums, 32-bit label stores; the
 // host picks it when nvox and every pointer allow).  class_probabilities = aggregated_results /
 // aggregated_nb_of_predictions (IEEE division, as numpy), then np.mean over the folds.
+// MAXC: compile-time bound of the class count (4 for the BraTS region / label sets, else 8) — with arrays of 8 classes the
+// kernel needed 96 registers, two blocks per SM, and its 32 KB of loads in flight per SM held it at 37 % of HBM bandwidth.
 // K1 (one accumulator, the common case): all class loads of a voxel group are issued before the first division — inside
 // the runtime fold loop the compiler keeps each load next to its use and a thread walks its four streams one memory
 // round trip after the other (measured 22 % of HBM bandwidth that way).
-template <int VEC, bool K1>
-__global__ void __launch_bounds__(kThreads) finalize_kernel(const FinalizeParams fp, const float* __restrict__ wsum,
+template <int VEC, bool K1, int MAXC>
+__global__ void __launch_bounds__(kThreads, MAXC == 4 ? 4 : 2) finalize_kernel(const FinalizeParams fp, const float* __restrict__ wsum,
                                                             size_t nvox, float* __restrict__ probs,
                                                             uint8_t* __restrict__ seg) {
     const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
     const size_t ngroups = nvox / VEC;
     for (size_t g = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
         const size_t i = g * VEC;
-        float wv[VEC], p[VEC][kMaxClasses];
+        float wv[VEC], p[VEC][MAXC];
         if constexpr (VEC == 4) {
             const float4 t = __ldcs(reinterpret_cast<const float4*>(wsum + i));
             wv[0] = t.x, wv[1] = t.y, wv[2] = t.z, wv[3] = t.w;
@@ -466,12 +469,12 @@ __global__ void __launch_bounds__(kThreads) finalize_kernel(const FinalizeParams
             wv[0] = __ldcs(wsum + i);
         }
         if constexpr (K1) {
-            float a[kMaxClasses][VEC];
+            float a[MAXC][VEC];
             // regions decision without probabilities: fl(a / w) > 0.5 is decided EXACTLY by one fp64 product and compare
             // (see exceeds_half) — the 12 IEEE divisions per thread made this pass ALU-bound at 18-22 % of HBM bandwidth
             const bool by_compare = fp.mode == 1 && probs == nullptr;
 #pragma unroll
-            for (int k = 0; k < kMaxClasses; ++k) {
+            for (int k = 0; k < MAXC; ++k) {
                 if (k < fp.ncls) {
                     if constexpr (VEC == 4) {
                         const float4 t = __ldcs(reinterpret_cast<const float4*>(fp.acc[0] + k * nvox + i));
@@ -482,7 +485,7 @@ __global__ void __launch_bounds__(kThreads) finalize_kernel(const FinalizeParams
                 }
             }
 #pragma unroll
-            for (int k = 0; k < kMaxClasses; ++k) {
+            for (int k = 0; k < MAXC; ++k) {
                 if (k < fp.ncls) {
 #pragma unroll
                     for (int v = 0; v < VEC; ++v)
@@ -491,7 +494,7 @@ __global__ void __launch_bounds__(kThreads) finalize_kernel(const FinalizeParams
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < kMaxClasses; ++k) {
+            for (int k = 0; k < MAXC; ++k) {
                 if (k < fp.ncls) {
                     float s[VEC];
                     for (int j = 0; j < fp.K; ++j) {
@@ -512,7 +515,7 @@ __global__ void __launch_bounds__(kThreads) finalize_kernel(const FinalizeParams
         }
         if (probs) {
 #pragma unroll
-            for (int k = 0; k < kMaxClasses; ++k) {
+            for (int k = 0; k < MAXC; ++k) {
                 if (k < fp.ncls) {
                     if constexpr (VEC == 4)
                         __stcs(reinterpret_cast<float4*>(probs + k * nvox + i), make_float4(p[0][k], p[1][k], p[2][k], p[3][k]));
@@ -525,10 +528,10 @@ __global__ void __launch_bounds__(kThreads) finalize_kernel(const FinalizeParams
             if constexpr (VEC == 4) {
                 uint32_t packed = 0;
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) packed |= static_cast<uint32_t>(decide_label(fp, p[v]) & 255) << (8 * v);
+                for (int v = 0; v < VEC; ++v) packed |= static_cast<uint32_t>(decide_label<MAXC>(fp, p[v]) & 255) << (8 * v);
                 *reinterpret_cast<uint32_t*>(seg + i) = packed;
             } else {
-                seg[i] = static_cast<uint8_t>(decide_label(fp, p[0]));
+                seg[i] = static_cast<uint8_t>(decide_label<MAXC>(fp, p[0]));
             }
         }
     }
@@ -726,17 +729,25 @@ int bsg_finalize(const float* const* acc_list_host, int K, const float* wsum, in
     bool vec = nvox % 4 == 0 && aligned16(wsum) && aligned16(probs) && (reinterpret_cast<uintptr_t>(seg) & 3) == 0;
     for (int j = 0; j < K; ++j) vec = vec && aligned16(acc_list_host[j]);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    // one 4-voxel group per thread (no grid-stride tail): ~8.7 k blocks for a BraTS volume, 8 resident per SM
+    // one 4-voxel group per thread (no grid-stride tail): ~8.7 k blocks for a BraTS volume
     const size_t ngroups = vec ? nvox / 4 : nvox;
     const unsigned blocks = static_cast<unsigned>((ngroups + kThreads - 1) / kThreads);
-    if (vec && K == 1)
-        finalize_kernel<4, true><<<blocks, kThreads, 0, s>>>(fp, wsum, nvox, probs, seg);
-    else if (vec)
-        finalize_kernel<4, false><<<blocks, kThreads, 0, s>>>(fp, wsum, nvox, probs, seg);
-    else if (K == 1)
-        finalize_kernel<1, true><<<blocks, kThreads, 0, s>>>(fp, wsum, nvox, probs, seg);
+#define BSG_FINALIZE_LAUNCH(MAXC)                                                              \
+    do {                                                                                       \
+        if (vec && K == 1)                                                                     \
+            finalize_kernel<4, true, MAXC><<<blocks, kThreads, 0, s>>>(fp, wsum, nvox, probs, seg);  \
+        else if (vec)                                                                          \
+            finalize_kernel<4, false, MAXC><<<blocks, kThreads, 0, s>>>(fp, wsum, nvox, probs, seg); \
+        else if (K == 1)                                                                       \
+            finalize_kernel<1, true, MAXC><<<blocks, kThreads, 0, s>>>(fp, wsum, nvox, probs, seg);  \
+        else                                                                                   \
+            finalize_kernel<1, false, MAXC><<<blocks, kThreads, 0, s>>>(fp, wsum, nvox, probs, seg); \
+    } while (0)
+    if (ncls <= 4)
+        BSG_FINALIZE_LAUNCH(4);
     else
-        finalize_kernel<1, false><<<blocks, kThreads, 0, s>>>(fp, wsum, nvox, probs, seg);
+        BSG_FINALIZE_LAUNCH(8);
+#undef BSG_FINALIZE_LAUNCH
     BSG_CUDA_OK(cudaGetLastError());
     return BSG_OK;
 }
