@@ -656,7 +656,9 @@ static int head_launch(const void* feat_bf16, int feat_f16, int cfeat, int ctot,
 #define BSG_HEAD_LAUNCH(NC, CF)                                                                                     \
     head_tta_accumulate_kernel<NC, CF><<<grid, kThreads, 0, st>>>(fp, ctot, P0, P1, P2, ms, hp, feat_f16, gauss, acc, Z, \
                                                                   Y, X, z0, y0, x0, norm_scale_shift, norm_slope, lo_off)
-    if (ncls <= 4 && cfeat <= 32)
+    if (ncls <= 3 && cfeat <= 32)  // the BraTS region heads: 3 classes x 32 features — a fourth, padded class is 25 % more FMAs
+        BSG_HEAD_LAUNCH(3, 32);
+    else if (ncls <= 4 && cfeat <= 32)
         BSG_HEAD_LAUNCH(4, 32);
     else if (ncls <= 4)
         BSG_HEAD_LAUNCH(4, 64);
