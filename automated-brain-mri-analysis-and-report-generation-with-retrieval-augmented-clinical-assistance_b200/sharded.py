@@ -200,8 +200,14 @@ class ShardedExchange:
                                  else "never delivered its slab") + " (in-kernel wait timed out)")
 
     def close(self):
-        """Releases the peer mappings and the communicator (call before destroy_process_group)."""
-        self.check()
+        """Releases the peer mappings and the communicator (call before destroy_process_group).  Collective: every rank
+        runs the whole sequence even when its own check() failed — the failure is raised at the end, after the barriers the
+        other ranks are waiting in."""
+        err = None
+        try:
+            self.check()
+        except L.BsgError as e:
+            err = e
         if self.dist.is_initialized():
             self.dist.barrier()
         self._tables.clear()
@@ -215,3 +221,5 @@ class ShardedExchange:
         if self._comm is not None:
             L.lib().bsg_nccl_comm_destroy(self._comm)
             self._comm = None
+        if err is not None:
+            raise err

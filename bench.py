@@ -696,7 +696,11 @@ def run_ours(args):
                 if out is None:  # rank 0 did not own the last case: any owned result serves the line
                     out = lp.finish(lp.submit(case0, gt0), post=True)
             del lp
-            sh.close()
+            try:
+                sh.close()
+            except Exception as e:  # an in-kernel wait timed out on this rank: keep the line, flag the record
+                records[route]["exchange_error"] = str(e)
+                log(f"latency mode [{route}]: {e}")
         main_route = routes[0]
         latency = dict(records[main_route])
         latency.update({"config": "configs[2]: the 288 (model, tile, mirror) forwards of ONE case dealt round-robin to the "
